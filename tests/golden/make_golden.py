@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ FROM THE REAL REFERENCE.
+
+Runs only in the build container (needs /root/reference, CPU only).  It imports the
+reference's own modules (`pytorch_networks_convae`, `symmetric_layers_torch`,
+`calculate_profiles`) with a matplotlib stub, runs them in float64 (the
+reference's native precision, advect_wi_gaia.py:348,430,468), and stores inputs, weights and
+outputs as .npz.  The GPU boxes have no /root/reference: the tests there read only the .npz.
+
+    python tests/golden/make_golden.py            # regenerate everything
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, REPO)
+
+
+def import_reference():
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.lines"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib.lines"].Line2D = object
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.path.insert(0, REF)
+    import pytorch_networks_convae as P  # noqa
+
+    return P
+
+
+P = import_reference()
+from oracle import ref_numpy as RN  # noqa: E402
+
+RAQ, FKT, FKP = 6.79733173, 475523342.0, 2.58574662  # a CV simulation, load_fluidnet.ipynb:847
+
+
+def make_net(spec: RN.NetSpec, seed=0, perturb_affine=True, cls=None):
+    torch.manual_seed(seed)
+    cls = cls or P.NewFluidNet
+    net = cls(spec.levels, spec.c_i, spec.c_h, spec.c_o, torch.device("cpu"), act_fn="gelu", r_p=spec.r_p,
+              loss_type=spec.loss_type, use_symm=spec.use_symm, dilation=1, a_bound=spec.a_bound,
+              repeats=spec.repeats, f=spec.f, p_pred=spec.p_pred, factor=2).double()
+    if perturb_affine:  # default init leaves GroupNorm affine = (1, 0): perturb so it is exercised
+        g = torch.Generator().manual_seed(seed + 100)
+        with torch.no_grad():
+            for n, p_ in net.named_parameters():
+                if n.endswith("layers.1.weight") or n.startswith("gn.") and n.endswith("weight"):
+                    p_.add_(0.2 * torch.randn(p_.shape, generator=g, dtype=p_.dtype))
+                elif n.endswith("layers.1.bias") or n.startswith("gn.") and n.endswith("bias") or n.endswith("learnable_bias"):
+                    p_.add_(0.2 * torch.randn(p_.shape, generator=g, dtype=p_.dtype))
+    net.eval()
+    return net
+
+
+def set_grid(net, H, W):
+    for m in net.unpool:  # pytorch_networks_convae.py:1227-1229 hard-codes (128, 506)
+        m.size = (H, W)
+
+
+def ref_step(net, ad, T, xc, yc, raq, fkt, fkp):
+    """Body of TS.forward's loop (pytorch_networks_convae.py:379-473) around the REFERENCE
+    modules, minus the hard-coded view(-1,1,128,506) at :414-417."""
+    raq_nd, fkt_nd, fkp_nd = RN.nondim_params(raq, fkt, fkp)
+    tt = lambda s: torch.tensor(s, dtype=T.dtype)
+    V = P.eta_torch(tt(fkt), tt(fkp), 1.0 - yc, T, 0, 0)
+    V = torch.clip(V, 1e-08, 1)
+    H, W = T.shape[-2:]
+    inp = torch.cat((xc / 4.0, yc / 4.0, torch.log10(V) / 8, tt(raq_nd).expand(1, 1, H, W),
+                     tt(fkt_nd).expand(1, 1, H, W), tt(fkp_nd).expand(1, 1, H, W), T), axis=1)
+    u, v, p = net(inp)
+    s = torch.exp((tt(raq) / 10) * 1.80167667 + torch.log(tt(fkt)) * 0.4330392 + torch.log(tt(fkp)) * -0.46052953) * 5
+    u = (u * s).view(-1, 1, H, W)
+    v = (v * s).view(-1, 1, H, W)
+    inp2 = torch.cat((u, v, T, torch.zeros_like(u) + raq, xc, yc), axis=1)
+    Tn, dt = ad(inp2)
+    Tn[:, :, 0, :] = 1
+    Tn[:, :, -1, :] = 0
+    Tn[:, :, :, 0:1] = Tn[:, :, :, 1:2]
+    Tn[:, :, :, -1:] = Tn[:, :, :, -2:-1]
+    return Tn, dt, u, v, p, V, inp
+
+
+def sd_numpy(net):
+    return {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def set_fp32(net):
+    net.float()
+    net.dx_center_kernel = net.dx_center_kernel.float()
+    net.dy_center_kernel = net.dy_center_kernel.float()
+
+
+@torch.no_grad()
+def golden_rollout(tag, spec, H, W, keep, n_steps, check_numpy_steps=1):
+    net = make_net(spec)
+    set_grid(net, H, W)
+    ad = P.ADNet(torch.device("cpu"), CN_max=0.99).double()
+    xc_np, yc_np = RN.synthetic_grid(H, W)
+    T0_np = RN.synthetic_T0(H, W, seed=1)
+    xc = torch.tensor(xc_np).view(1, 1, H, W)
+    yc = torch.tensor(yc_np).view(1, 1, H, W)
+    T = torch.tensor(T0_np).view(1, 1, H, W)
+    out = {"T0": T0_np, "xc": xc_np, "yc": yc_np, "params": np.array([RAQ, FKT, FKP])}
+    dts = []
+    for i in range(1, n_steps + 1):
+        T, dt, u, v, p, V, inp = ref_step(net, ad, T, xc, yc, RAQ, FKT, FKP)
+        dts.append(float(dt))
+        if i == 1:
+            out.update(u1=u[0, 0].numpy().copy(), v1=v[0, 0].numpy().copy(), p1=p[0].numpy().copy(),
+                       V1=V[0, 0].numpy().copy())
+        if i in keep:
+            out[f"T{i}"] = T[0, 0].numpy().copy()
+    out["dts"] = np.asarray(dts)
+    mT, Tp, dTp = RN.diagnostics(T[0, 0].numpy(), yc_np[:, 0])
+    out.update(meanT=np.float64(mT), Tprof=Tp, dTprof=dTp)
+    sd = sd_numpy(net)
+
+    # --- pin the numpy oracle against the reference (fp64)
+    Tn, dt_n, un, vn, pn, Vn = RN.ts_step(sd, spec, T0_np[None, None], xc_np, yc_np, RAQ, FKT, FKP)
+    print(f"[{tag}] numpy-oracle vs reference, step 1: u {relerr(un[0], out['u1']):.2e} v {relerr(vn[0], out['v1']):.2e} "
+          f"p {relerr(pn[0], out['p1']):.2e} T {np.abs(Tn[0,0]-out['T1']).max():.2e} dt {abs(dt_n-dts[0])/dts[0]:.2e}")
+
+    # --- fp32 noise floor of the reference itself (SURVEY.md section 8c "parity metric caveat")
+    net32 = make_net(spec)
+    set_grid(net32, H, W)
+    set_fp32(net32)
+    inp32 = RN.build_input(T0_np[None, None], xc_np, yc_np, yc_np, RAQ, FKT, FKP)[0].astype(np.float32)
+    u32, v32, p32 = net32(torch.tensor(inp32))
+    s = RN.velocity_scaler(RAQ, FKT, FKP)
+    noise = np.array([relerr(u32[0].numpy() * s, out["u1"]), relerr(v32[0].numpy() * s, out["v1"]),
+                      relerr(p32[0].numpy(), out["p1"])])
+    print(f"[{tag}] reference fp32 vs its own fp64 (rel-L2 u,v,p): {noise}")
+    out["ref_fp32_noise"] = noise
+    np.savez_compressed(os.path.join(HERE, f"{tag}.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, f"{tag}_weights.npz"), **sd)
+    return out
+
+
+@torch.no_grad()
+def golden_ts_unmodified():
+    """128x506 through the UNMODIFIED reference TS(ts=5) (pytorch_networks_convae.py:266-475)."""
+    spec = RN.NetSpec()
+    H, W = 128, 506
+    net = make_net(spec)
+    ad = P.ADNet(torch.device("cpu"), CN_max=0.99).double()
+    ts = P.TS(net, ad, torch.device("cpu"), ts=5, scale=True, p_pred=True, net="newfluidnet").double()
+    xc_np, yc_np = RN.synthetic_grid(H, W)
+    T0_np = RN.synthetic_T0(H, W, seed=1)
+    t64 = lambda s: torch.tensor(s, dtype=torch.float64)
+    raq_nd, fkt_nd, fkp_nd = RN.nondim_params(RAQ, FKT, FKP)
+    xc = t64(xc_np).view(1, 1, H, W)
+    yc = t64(yc_np).view(1, 1, H, W)
+    x, dts, u, v, p, V = ts(t64(T0_np).view(1, 1, H, W), None, None, yc, t64(raq_nd), t64(fkt_nd), t64(fkp_nd),
+                            t64(RAQ), t64(FKT), t64(FKP), xc, yc)
+    out = {"T0": T0_np, "xc": xc_np, "yc": yc_np, "params": np.array([RAQ, FKT, FKP]),
+           "T1": x[1][0, 0].numpy().copy(), "T5": x[5][0, 0].numpy().copy(),
+           "dts": np.array([float(dts[i]) for i in range(1, 6)]),
+           "u5": u[0, 0].numpy().copy(), "v5": v[0, 0].numpy().copy(), "p5": p[0, 0].numpy().copy(),
+           "V5": V[0, 0].numpy().copy()}
+    sd = sd_numpy(net)
+    # numpy oracle, 1 step, vs TS
+    Tn, dt_n, *_ = RN.ts_step(sd, spec, T0_np[None, None], xc_np, yc_np, RAQ, FKT, FKP)
+    print(f"[ts128x506] numpy-oracle vs unmodified TS: T1 {np.abs(Tn[0,0]-out['T1']).max():.2e} dt {abs(dt_n-out['dts'][0])/out['dts'][0]:.2e}")
+    np.savez_compressed(os.path.join(HERE, "ts128x506.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "ts128x506_weights.npz"), **sd)
+
+
+@torch.no_grad()
+def golden_variants():
+    """Small nets covering the other constructor paths: zeros / reflect padding, no
+    symmetry, odd sizes (AvgPool floor, non-integer bicubic ratios), mae head, k=5 trunk."""
+    cases = {
+        "var_zeros_nosym": (RN.NetSpec(levels=3, c_h=8, c_o=2, r_p="zeros", use_symm=False, repeats=2), 36, 52),
+        "var_reflect_sym": (RN.NetSpec(levels=3, c_h=16, c_o=2, r_p="reflect", use_symm=True, repeats=2), 50, 76),
+        "var_replicate_odd": (RN.NetSpec(levels=4, c_h=16, c_o=2, r_p="replicate", use_symm=True, repeats=2), 50, 77),
+        "var_mae_p": (RN.NetSpec(levels=2, c_h=16, c_o=3, r_p="replicate", use_symm=True, repeats=1, loss_type="mae"), 24, 40),
+        "var_k5": (RN.NetSpec(levels=2, c_h=16, c_o=1, r_p="zeros", use_symm=True, repeats=2, f=5, p_pred=False), 32, 48),
+    }
+    for tag, (spec, H, W) in cases.items():
+        net = make_net(spec, seed=3)
+        set_grid(net, H, W)
+        g = torch.Generator().manual_seed(7)
+        inp = torch.randn(2, spec.c_i, H, W, generator=g, dtype=torch.float64)
+        u, v, p = net(inp)
+        sd = sd_numpy(net)
+        un, vn, pn = RN.newfluidnet_forward(sd, spec, inp.numpy())
+        print(f"[{tag}] numpy-oracle vs reference: u {relerr(un, u.numpy()):.2e} v {relerr(vn, v.numpy()):.2e}"
+              + (f" p {relerr(pn, p.numpy()):.2e}" if p is not None else ""))
+        out = {"inp": inp.numpy(), "u": u.numpy(), "v": v.numpy(),
+               "spec": np.array([spec.levels, spec.c_i, spec.c_h, spec.c_o, spec.repeats, spec.f, int(spec.use_symm), int(spec.p_pred)]),
+               "r_p": np.array(spec.r_p), "loss_type": np.array(spec.loss_type), "a_bound": np.float64(spec.a_bound)}
+        if p is not None:
+            out["p"] = p.numpy()
+        out.update({"w::" + k: v_ for k, v_ in sd.items()})
+        np.savez_compressed(os.path.join(HERE, f"{tag}.npz"), **out)
+
+
+@torch.no_grad()
+def golden_ops():
+    """Operator-level vectors: ADNet alone, BoundaryLearnedConvolution2D (k=3, k=5, symm),
+    a FluidLayer, bicubic/avgpool, plus the calc_mlp_profile known answer."""
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    # ADNet with non-uniform grid and mixed-sign velocities (B=2: batch-global dt, :556)
+    H, W = 40, 56
+    xc_np, yc_np = RN.synthetic_grid(H, W)
+    u = torch.randn(2, 1, H, W, generator=g, dtype=torch.float64) * 50
+    v = torch.randn(2, 1, H, W, generator=g, dtype=torch.float64) * 50
+    u[0, 0, 5, 5] = 0.0
+    T = torch.rand(2, 1, H, W, generator=g, dtype=torch.float64)
+    ad = P.ADNet(torch.device("cpu"), CN_max=0.99)
+    xc = torch.tensor(xc_np).view(1, 1, H, W).expand(2, 1, H, W)
+    yc = torch.tensor(yc_np).view(1, 1, H, W).expand(2, 1, H, W)
+    inp = torch.cat((u, v, T, torch.zeros_like(u) + 3.5, xc, yc), 1).clone()
+    Tn, dt = ad(inp)
+    out.update(ad_u=u.numpy(), ad_v=v.numpy(), ad_T=T.numpy(), ad_xc=xc_np, ad_yc=yc_np, ad_raq=np.float64(3.5),
+               ad_Tn=Tn.numpy(), ad_dt=np.float64(float(dt)))
+    Tn_np, dt_np = RN.adnet_forward(u.numpy()[:, 0], v.numpy()[:, 0], T.numpy()[:, 0], 3.5, xc_np, yc_np, 0.99)
+    print(f"[ops] ADNet numpy-oracle vs reference: max abs {np.abs(Tn_np - Tn.numpy()[:,0]).max():.2e}, dt rel {abs(dt_np-float(dt))/float(dt):.2e}")
+    Tn2, _ = ad(inp.clone(), dt=torch.tensor(1e-4, dtype=torch.float64))
+    out.update(ad_Tn_fixed_dt=Tn2.numpy())
+
+    # learned boundary conv
+    for k, symm, ci, co, tag in ((3, False, 5, 8, "blc3"), (5, False, 4, 8, "blc5"), (3, True, 6, 16, "blc3s")):
+        torch.manual_seed(5)
+        m = P.BoundaryLearnedConvolution2D(ci, co, k, use_symm=symm).double()
+        with torch.no_grad():
+            m.learnable_bias.add_(torch.randn(m.learnable_bias.shape, generator=g, dtype=torch.float64))
+        x = torch.randn(2, ci, 20, 28, generator=g, dtype=torch.float64)
+        y = m(x)
+        sd = sd_numpy(m)
+        yn = RN.boundary_learned_conv(x.numpy(), sd, "", k, co, use_symm=symm)
+        print(f"[ops] {tag} numpy-oracle vs reference: {relerr(yn, y.numpy()):.2e}  out shape {tuple(y.shape)}")
+        out.update({f"{tag}_x": x.numpy(), f"{tag}_y": y.numpy()})
+        out.update({f"{tag}_w::{kk}": vv for kk, vv in sd.items()})
+        if k == 3 and not symm:
+            y2 = m(x, bc_x=2, bc_y=2)
+            out[f"{tag}_y_bc2"] = y2.numpy()
+            yn2 = RN.boundary_learned_conv(x.numpy(), sd, "", k, co, use_symm=symm, bc_x=2, bc_y=2)
+            print(f"[ops] {tag} bc=2: {relerr(yn2, y2.numpy()):.2e} out shape {tuple(y2.shape)}")
+
+    # bicubic / avgpool
+    x = torch.randn(1, 3, 15, 31, generator=g, dtype=torch.float64)
+    up = torch.nn.Upsample(size=(50, 77), mode="bicubic")(x)
+    pl = torch.nn.AvgPool2d((2, 2), stride=2)(x)
+    out.update(bic_x=x.numpy(), bic_y=up.numpy(), pool_y=pl.numpy())
+    print(f"[ops] bicubic numpy-oracle vs torch: {np.abs(RN.bicubic_upsample(x.numpy(), (50, 77)) - up.numpy()).max():.2e}; "
+          f"avgpool {np.abs(RN.avg_pool2(x.numpy()) - pl.numpy()).max():.2e}")
+
+    # calc_mlp_profile (calculate_profiles.py:102-134) -- needs cwd = reference dir for the pkl
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        import calculate_profiles as CP
+
+        yp, yprof = CP.calc_mlp_profile([RAQ], [FKT], [FKP])
+        out.update(mlp_pred=yp, mlp_yprof=yprof)
+        print(f"[ops] calc_mlp_profile: first3 {yp[0,:3]} last3 {yp[0,-3:]} mean {yp.mean():.9f}")
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "ops.npz"), **out)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    golden_ops()
+    golden_variants()
+    golden_rollout("roll128", RN.NetSpec(), 128, 128, keep=(1, 10, 100), n_steps=100)
+    golden_rollout("roll64x96", RN.NetSpec(levels=4), 64, 96, keep=(1, 10), n_steps=10)
+    golden_ts_unmodified()
