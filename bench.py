@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the surrogate time-stepping hot path (BASELINE.json metric: rollout cell-updates/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+One "step" = one time step of the rollout (7-channel input build -> conv surrogate -> curl/BC/
+un-scale head -> advection-diffusion update with the CFL dt) over one batch of synthetic T.
+Default workload = BASELINE config 2: 512x512, batch 1, random-init primary network
+(`NewFluidNet(levels=6, c_h=16, c_o=2, k=3, replicate, symmetric, curl)`), float32 kernels.
+With --gpus N every rank runs its own independent rollout (members differ in Ra and T0):
+no data-path collective, weak scaling, value = sum over ranks / max time over ranks.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference
+(`oracle/ref_torch.py`, the reference is PyTorch and cannot travel to the GPU box) on the
+host cores, same metric and config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+PARAMS0 = (6.79733173, 475523342.0, 2.58574662)  # load_fluidnet.ipynb:847 (a CV simulation)
+FLOP_PER_CELL = 61434  # SURVEY.md section 8a, primary config on 2^n grids
+WORKLOADS = {
+    "rollout512": dict(H=512, W=512, B=1, desc="512x512 batch-1 surrogate rollout (BASELINE config 2)"),
+    "rollout128": dict(H=128, W=128, B=1, desc="128x128 batch-1 surrogate rollout (BASELINE config 1 grid)"),
+    "ensemble256": dict(H=256, W=256, B=32, desc="32 members/GPU of 256x256 (BASELINE config 4, weak scaling)"),
+}
+
+
+def member_params(n, rank=0):
+    """Ensemble parameters: member 0 of rank 0 is the reference CV simulation, the others are drawn
+    from the ranges of the 130 simulations of the paper."""
+    rng = np.random.default_rng(2024 + rank)
+    out = []
+    for m in range(n):
+        if m == 0 and rank == 0:
+            out.append(PARAMS0)
+        else:
+            out.append((float(rng.uniform(0.126, 9.98)), float(10 ** rng.uniform(6.0035, 9.8888)),
+                        float(10 ** rng.uniform(0.00525, 1.9928))))
+    return out
+
+
+def primary_net(device, dtype=torch.float32):
+    import pbml_mantle_convection_b200 as P
+
+    torch.manual_seed(0)
+    net = P.NewFluidNet(6, 7, 16, 2, device, act_fn="gelu", r_p="replicate", loss_type="curl", use_symm=True, dilation=1,
+                        a_bound=10, repeats=4, f=3, p_pred=True, factor=2)
+    return net.to(dtype).to(device).eval()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------- CPU arm
+def cpu_port_rate(H, W, n_steps, warmup=1, dtype=torch.float64):
+    """cell-updates/s of the ATen-CPU port of the reference rollout (oracle/ref_torch.py), all host threads."""
+    from oracle import ref_numpy as RN
+    from oracle import ref_torch as RT
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = RN.NetSpec()
+    net = primary_net("cpu", torch.float64)
+    sd = {k: v.detach().numpy() for k, v in net.state_dict().items()}
+    Wt = RT.prepare_weights(sd, spec, dtype)
+    xc, yc = RN.synthetic_grid(H, W)
+    T = torch.tensor(RN.synthetic_T0(H, W, seed=1), dtype=dtype)[None, None]
+    xc, yc = torch.tensor(xc, dtype=dtype), torch.tensor(yc, dtype=dtype)
+    with torch.no_grad():
+        for _ in range(warmup):
+            T = RT.ts_step(Wt, spec, T, xc, yc, *PARAMS0)[0]
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            T = RT.ts_step(Wt, spec, T, xc, yc, *PARAMS0)[0]
+        dt = time.perf_counter() - t0
+    return H * W * n_steps / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    H, W, B = wl["H"], wl["W"], wl["B"]
+    rate, secs, threads = cpu_port_rate(H, W, args.steps, warmup=max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference", "metric": "rollout cell-updates/s", "value": rate, "unit": "cell-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "grid": [H, W], "batch": 1, "note": "one member on the host cores"},
+        "cpu_baseline": {"value": rate, "unit": "cell-updates/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} time steps of the {H}x{W} rollout, float64, ATen CPU port of the reference "
+                                   f"(oracle/ref_torch.py), {threads} threads"},
+        "e2e": {"value": rate, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------- GPU arm
+def time_kernel(fn, iters=20, warm=3, flush=None):
+    """Average device time (ms) of fn() with CUDA events on the current stream; optional L2 flush between launches."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / iters
+
+
+def kernel_rooflines(net, H, W, B, dev, flush):
+    """Live CUDA-event timing of the dominant kernels on this workload's shapes."""
+    from pbml_mantle_convection_b200 import _lib as L
+    from pbml_mantle_convection_b200 import ops
+
+    eng = net._engine(dev)
+    hbm, tf_burst, tf_sus, which = measured_peaks()
+    cells = B * H * W
+    g = torch.Generator(device=dev).manual_seed(5)
+    act = lambda nb: torch.randn(B, nb, H, W, 4, device=dev, generator=g)
+    x16 = act(4)
+    stats = torch.stack([x16.double().sum((2, 3, 4)), (x16.double() ** 2).sum((2, 3, 4))], -1).contiguous()
+    out = {}
+    # (1) trunk layer 16->16 3x3 at level 0, GN+GELU fused on load, stats in the epilogue: 128 B / cell, 4608 FLOP / cell
+    lay = eng.trunk[0][1]
+    src = ops.Source(x16, L.XFORM_GN_GELU, stats, lay.gamma, lay.beta)
+    o16, st16 = torch.empty_like(x16), torch.zeros_like(stats)
+    ms = time_kernel(lambda: ops.conv_fwd([src], lay.wpk, lay.bias, 16, 3, "replicate", impl=net.conv_impl,
+                                          wpk_umma=lay.wpk_umma, out=o16, stats=st16), flush=flush)
+    out["conv16x16_l0"] = {"ms": ms, "bound": "hbm", "achieved": cells * 128 / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                           "tflops": cells * 4608 / (ms * 1e-3) / 1e12}
+    # (2) conv[1]: 103 -> 16 over 7 sources: 29664 FLOP / cell (48 % of the forward), (96+8+16)*4 = 480 B / cell
+    srcs = [src] + [ops.Source(act(4)) for _ in range(5)] + [ops.Source(act(2))]
+    c1 = eng.conv1
+    ms = time_kernel(lambda: ops.conv_fwd(srcs, c1.wpk, c1.bias, 16, 3, "replicate", impl=net.conv_impl,
+                                          wpk_umma=c1.wpk_umma, out=o16, stats=st16), flush=flush)
+    out["conv1_103x16"] = {"ms": ms, "bound": "tensor", "achieved": cells * 29664 / (ms * 1e-3) / 1e12, "peak": tf_burst,
+                           "unit": "TFLOP/s", "gbs": cells * 480 / (ms * 1e-3) / 1e9}
+    # (3) advection-diffusion stencil + CFL reduce: 16 B / cell
+    T = torch.rand(B, H, W, device=dev, generator=g)
+    u = torch.randn(B, H, W, device=dev, generator=g) * 1e3
+    v = torch.randn(B, H, W, device=dev, generator=g) * 1e3
+    grid = eng_grid(H, W, dev)
+    members = ops.make_members([PARAMS0] * B, dev)
+    uv = ops.uvmax_reduce(u, v)
+    To, dto, uvo = torch.empty_like(T), torch.empty(B, dtype=torch.float64, device=dev), torch.zeros_like(uv)
+    ms = time_kernel(lambda: ops.advect_diffuse(T, u, v, grid.xcoef, grid.ycoef, members, uv, grid.dx_min, 0.99, T_out=To,
+                                                dt_out=dto, uv_out=uvo), flush=flush)
+    out["stencil"] = {"ms": ms, "bound": "hbm", "achieved": cells * 16 / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s"}
+    for k in out.values():
+        k["frac"] = k["achieved"] / k["peak"]
+        k["peak_source"] = which
+    return out
+
+
+def eng_grid(H, W, dev):
+    import pbml_mantle_convection_b200 as P
+    from pbml_mantle_convection_b200.engine import Grid
+
+    xc, yc = P.synthetic_grid(H, W)
+    xc, yc = torch.tensor(xc), torch.tensor(yc)
+    return Grid(xc, yc, yc, dev)
+
+
+def launches_per_step(L_, R_):
+    # build_input + conv0 + L*R trunk convs + conv1..3 + (L-1) pools + (L-1) bicubic + head + stencil
+    return 1 + 1 + L_ * R_ + 3 + 2 * (L_ - 1) + 1 + 1
+
+
+def run_ours(args, wl):
+    import torch.distributed as dist
+
+    import pbml_mantle_convection_b200 as P
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (--impl ours) needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, W, B = wl["H"], wl["W"], wl["B"]
+    K, Wm = args.steps, max(args.warmup, 3)
+    net = primary_net(dev)
+    net.conv_impl = args.conv
+    prm = member_params(B, rank)
+    ens = P.EnsembleRollout(net, H, W, prm, dev, cn_max=0.99, per_member_dt=True)
+    T0 = np.stack([P.synthetic_T0(H, W, seed=1 + rank * B + m) for m in range(B)])
+    ens.set_T(T0)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    # ---- device-resident rollout: one CUDA graph per time step, L2 flushed (untimed) between steps
+    ens.run(Wm + (Wm % 2), steps_per_graph=1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    with ClockSampler(local) as clk:
+        wall0 = time.perf_counter()
+        for _ in range(K):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ens.run(1, steps_per_graph=1, track_time=False)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    finite = bool(torch.isfinite(ens.T).all().item())
+
+    # ---- end to end through the drop-in TS call with HOST float64 tensors (advect_wi_gaia.py:590-616)
+    ts = P.TS(net, P.ADNet(dev, CN_max=0.99), dev, ts=1, scale=True, p_pred=True, net="newfluidnet")
+    xc, yc = P.synthetic_grid(H, W)
+    t64 = lambda a_: torch.tensor(a_, dtype=torch.float64)
+    xc_t, yc_t = t64(xc).view(1, 1, H, W), t64(yc).view(1, 1, H, W)
+    nd = ((PARAMS0[0] - 0.12624371) / (9.70723344 - 0.12624371),
+          (np.log10(PARAMS0[1]) - 6.00352841978384) / (9.888820429862925 - 6.00352841978384),
+          (np.log10(PARAMS0[2]) - 0.005251646002323797) / (1.9927988938926755 - 0.005251646002323797))
+    args_ts = (None, None, yc_t, t64(nd[0]), t64(nd[1]), t64(nd[2]), t64(PARAMS0[0]), t64(PARAMS0[1]), t64(PARAMS0[2]), xc_t,
+               yc_t)
+    Tp = t64(T0[:1]).view(1, 1, H, W).pin_memory()
+    K2 = min(K, 50)
+
+    def e2e_step(Tp_):
+        x, dts, u, v, p, V = ts(Tp_, *args_ts)
+        outs = [x[1].cpu(), u.cpu(), v.cpu(), V.cpu(), dts[1].cpu()]  # what the driver reads back every step
+        return outs[0], sum(o.numel() * o.element_size() for o in outs)
+
+    for _ in range(3):
+        Tn, d2h = e2e_step(Tp)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Tc = Tp
+    for _ in range(K2):
+        Tc, d2h = e2e_step(Tc)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_rate = H * W * K2 / e2e_s
+
+    # ---- reduce over ranks: total units / max time
+    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    dev_ms = t_ms.item()
+    value = world * B * H * W * K / (dev_ms * 1e-3)
+    e2e_rate = world * H * W * K2 / e2e_t.item()
+
+    line = None
+    if rank == 0:
+        roofs = kernel_rooflines(net, H, W, B, dev, flush)
+        step_ms = dev_ms / K
+        # dominant kernel = largest share of the step (conv[1] runs once, the level-0 trunk layer R times)
+        share = {"conv1_103x16": roofs["conv1_103x16"]["ms"], "conv16x16_l0": roofs["conv16x16_l0"]["ms"] * 4,
+                 "stencil": roofs["stencil"]["ms"]}
+        dom = max(share, key=share.get)
+        r = roofs[dom]
+        roofline = {"kernel": dom, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
+                    "frac": r["frac"], "traffic": None, "peak_source": r["peak_source"], "ms_per_launch": r["ms"],
+                    "share_of_step": share[dom] / step_ms}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            n_cpu = max(2, min(10, int(20.0 / (2.5e-6 * H * W))))  # ~10-30 s of CPU work
+            rate, secs, threads = cpu_port_rate(H, W, n_cpu)
+            cpu = {"value": rate, "unit": "cell-updates/s", "cores": threads, "kind": "port",
+                   "sample": f"{n_cpu} time steps of the same {H}x{W} batch-1 rollout, float64 ATen-CPU port of the "
+                             f"reference (oracle/ref_torch.py), {secs:.1f} s"}
+        line = {
+            "metric": "rollout cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": wl["desc"], "grid": [H, W], "batch_per_gpu": B,
+                       "net": "NewFluidNet(levels=6,c_i=7,c_h=16,c_o=2,k=3,replicate,symm,curl,repeats=4)", "conv_impl": args.conv,
+                       "l2": "flushed (256 MiB write, untimed) between timed steps; per-step CUDA-event intervals summed",
+                       "parallelism": f"{world} independent rollouts (no collective)" if world > 1 else "single GPU",
+                       "graph": "one CUDA graph per time step"},
+            "surrogate_steps_per_s": world * K / (dev_ms * 1e-3),
+            "gflop_per_step": B * H * W * FLOP_PER_CELL / 1e9,
+            "wall_ms_per_step": 1e3 * wall / K,
+            "roofline": roofline,
+            "kernels": roofs,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_rate, "unit": "cell-updates/s", "h2d_bytes_per_step": int(Tp.numel() * 8), "d2h_bytes_per_step": int(d2h),
+                    "steps": K2, "api": "TS.forward(ts=1) with pinned host float64 T in, (T,u,v,V,dt) read back"},
+            "gpu_launches": launches_per_step(6, 4) * K,
+            "clocks": clk.summary(),
+            "finite": finite,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rollout512", choices=sorted(WORKLOADS))
+    ap.add_argument("--conv", default="auto", choices=["auto", "ffma", "umma_3xtf32", "umma_bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,347 @@
+// C ABI glue: validation, conv dispatch, workspace planning, and the DAG that enqueues a
+// whole surrogate forward (NewFluidNet.forward, pytorch_networks_convae.py:1315-1388) and
+// the TS time-stepping loop (:377-475) without any host synchronisation.
+#include <string.h>
+
+#include <string>
+
+#include "common.cuh"
+
+namespace pbmc {
+
+static thread_local std::string g_last_cuda_error;
+void set_last_cuda_error(cudaError_t e, const char* where) {
+  g_last_cuda_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  (void)cudaGetLastError();  // clear the sticky-less error so later launches are not blamed
+}
+
+int conv_ffma_dispatch(const pbmc_conv_desc& d, cudaStream_t st);
+int conv_umma_dispatch(const pbmc_conv_desc& d, cudaStream_t st);  // conv_umma.cu
+bool conv_umma_supported(const pbmc_conv_desc& d);
+
+}  // namespace pbmc
+
+using namespace pbmc;
+
+struct pbmc_ctx {
+  static constexpr int NSTREAM = PBMC_MAX_LEVELS;
+  cudaStream_t s[NSTREAM];
+  cudaEvent_t ev_fork[NSTREAM + 2];
+  cudaEvent_t ev_join[NSTREAM];
+};
+
+extern "C" const char* pbmc_error_string(int st) {
+  switch (st) {
+    case PBMC_OK: return "ok";
+    case PBMC_ERR_BAD_SHAPE: return "bad shape";
+    case PBMC_ERR_UNSUPPORTED: return "unsupported configuration";
+    case PBMC_ERR_NULL_POINTER: return "null pointer";
+    case PBMC_ERR_MISALIGNED: return "pointer not 16-byte aligned";
+    case PBMC_ERR_WORKSPACE: return "workspace too small";
+    case PBMC_ERR_CUDA: return "CUDA error (see pbmc_last_cuda_error)";
+    case PBMC_ERR_NOT_DEVICE_POINTER: return "pointer is not device memory";
+    default: return "unknown status";
+  }
+}
+extern "C" int pbmc_version(void) { return PBMC_VERSION; }
+extern "C" const char* pbmc_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+extern "C" size_t pbmc_sizeof(const char* name) {
+  if (!name) return 0;
+  if (!strcmp(name, "pbmc_member")) return sizeof(pbmc_member);
+  if (!strcmp(name, "pbmc_src")) return sizeof(pbmc_src);
+  if (!strcmp(name, "pbmc_conv_desc")) return sizeof(pbmc_conv_desc);
+  if (!strcmp(name, "pbmc_layer")) return sizeof(pbmc_layer);
+  if (!strcmp(name, "pbmc_net")) return sizeof(pbmc_net);
+  return 0;
+}
+
+static int check_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return PBMC_ERR_NOT_DEVICE_POINTER;
+  }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? PBMC_OK : PBMC_ERR_NOT_DEVICE_POINTER;
+}
+
+static int validate_conv(const pbmc_conv_desc& d) {
+  if (d.nsrc <= 0 || d.nsrc > PBMC_MAX_SRC) return PBMC_ERR_BAD_SHAPE;
+  if (d.B <= 0 || d.H <= 0 || d.W <= 0 || d.cout <= 0) return PBMC_ERR_BAD_SHAPE;
+  if (d.ksize != 3 && d.ksize != 5) return PBMC_ERR_UNSUPPORTED;
+  if (d.pad_mode < PBMC_PAD_ZEROS || d.pad_mode > PBMC_PAD_REFLECT) return PBMC_ERR_UNSUPPORTED;
+  if (d.pad_mode == PBMC_PAD_REFLECT && (d.H <= d.ksize / 2 || d.W <= d.ksize / 2)) return PBMC_ERR_BAD_SHAPE;
+  if (!d.wpk || !d.bias || !d.out) return PBMC_ERR_NULL_POINTER;
+  if (!aligned16(d.wpk) || !aligned16(d.bias) || !aligned16(d.out)) return PBMC_ERR_MISALIGNED;
+  for (int s = 0; s < d.nsrc; ++s) {
+    const pbmc_src& S = d.src[s];
+    if (!S.ptr) return PBMC_ERR_NULL_POINTER;
+    if (!aligned16(S.ptr)) return PBMC_ERR_MISALIGNED;
+    if (S.nblk <= 0) return PBMC_ERR_BAD_SHAPE;
+    if ((S.xform == PBMC_XFORM_GN_GELU || S.xform == PBMC_XFORM_GN) && (!S.stats || !S.gamma || !S.beta))
+      return PBMC_ERR_NULL_POINTER;
+    if (S.xform < PBMC_XFORM_NONE || S.xform > PBMC_XFORM_GELU) return PBMC_ERR_UNSUPPORTED;
+  }
+  return PBMC_OK;
+}
+
+static int conv_enqueue(const pbmc_conv_desc& d, cudaStream_t st) {
+  int rc = validate_conv(d);
+  if (rc != PBMC_OK) return rc;
+  int impl = d.impl;
+  if (impl == PBMC_CONV_AUTO) impl = (d.wpk_umma && conv_umma_supported(d)) ? PBMC_CONV_UMMA_3XTF32 : PBMC_CONV_FFMA;
+  if (impl == PBMC_CONV_FFMA) return conv_ffma_dispatch(d, st);
+  if (impl == PBMC_CONV_UMMA_3XTF32 || impl == PBMC_CONV_UMMA_BF16) {
+    if (!d.wpk_umma || !conv_umma_supported(d)) return PBMC_ERR_UNSUPPORTED;
+    pbmc_conv_desc e = d;
+    e.impl = impl;
+    return conv_umma_dispatch(e, st);
+  }
+  return PBMC_ERR_UNSUPPORTED;
+}
+
+extern "C" int pbmc_conv_fwd(const pbmc_conv_desc* d, void* stream) {
+  if (!d) return PBMC_ERR_NULL_POINTER;
+  int rc = check_device_ptr(d->out);
+  if (rc != PBMC_OK) return rc;
+  return conv_enqueue(*d, (cudaStream_t)stream);
+}
+
+extern "C" int pbmc_ctx_create(pbmc_ctx** out) {
+  if (!out) return PBMC_ERR_NULL_POINTER;
+  pbmc_ctx* c = new pbmc_ctx();
+  for (int i = 0; i < pbmc_ctx::NSTREAM; ++i) {
+    PBMC_CUDA(cudaStreamCreateWithFlags(&c->s[i], cudaStreamNonBlocking));
+    PBMC_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < pbmc_ctx::NSTREAM + 2; ++i) PBMC_CUDA(cudaEventCreateWithFlags(&c->ev_fork[i], cudaEventDisableTiming));
+  *out = c;
+  return PBMC_OK;
+}
+extern "C" int pbmc_ctx_destroy(pbmc_ctx* c) {
+  if (!c) return PBMC_OK;
+  for (int i = 0; i < pbmc_ctx::NSTREAM; ++i) {
+    cudaStreamDestroy(c->s[i]);
+    cudaEventDestroy(c->ev_join[i]);
+  }
+  for (int i = 0; i < pbmc_ctx::NSTREAM + 2; ++i) cudaEventDestroy(c->ev_fork[i]);
+  delete c;
+  return PBMC_OK;
+}
+
+// ------------------------------------------------------------------ workspace plan
+namespace {
+struct Plan {
+  int L, R, CB, CIB, COB3;
+  int Hl[PBMC_MAX_LEVELS], Wl[PBMC_MAX_LEVELS];
+  size_t inp, x0, pooled[PBMC_MAX_LEVELS], ping[PBMC_MAX_LEVELS][2], up[PBMC_MAX_LEVELS], h1, h2, h3;
+  size_t stats, stats_bytes, chan_sum, uvmax, total;
+  // stats slots: 0 = conv0, 1 + l*R + r = trunk, 1 + L*R = conv1
+  size_t stat_off(int slot, int B) const { return stats + (size_t)slot * B * CB * 2 * sizeof(double); }
+};
+
+inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int make_plan(const pbmc_net& n, int B, int H, int W, Plan& P) {
+  if (n.levels < 1 || n.levels > PBMC_MAX_LEVELS || n.repeats < 1 || n.repeats > PBMC_MAX_REPEATS) return PBMC_ERR_UNSUPPORTED;
+  if (n.c_h < 4 || n.c_h % 4 != 0 || n.c_i < 1 || n.c_o < 1 || n.c_o > 4) return PBMC_ERR_UNSUPPORTED;
+  if (B <= 0 || H < 3 || W < 3) return PBMC_ERR_BAD_SHAPE;
+  P.L = n.levels; P.R = n.repeats; P.CB = n.c_h / 4; P.CIB = (n.c_i + 3) / 4; P.COB3 = (n.c_o + 3) / 4;
+  P.Hl[0] = H; P.Wl[0] = W;
+  for (int l = 1; l < P.L; ++l) {
+    P.Hl[l] = P.Hl[l - 1] / 2; P.Wl[l] = P.Wl[l - 1] / 2;
+    if (P.Hl[l] < 1 || P.Wl[l] < 1) return PBMC_ERR_BAD_SHAPE;
+    if (n.pad_mode == PBMC_PAD_REFLECT && (P.Hl[l] <= n.ksize / 2 || P.Wl[l] <= n.ksize / 2)) return PBMC_ERR_BAD_SHAPE;
+  }
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  const size_t px = (size_t)H * W;
+  P.inp = take((size_t)B * P.CIB * px * 16);
+  P.x0 = take((size_t)B * P.CB * px * 16);
+  for (int l = 0; l < P.L; ++l) {
+    const size_t pl = (size_t)P.Hl[l] * P.Wl[l];
+    P.pooled[l] = l ? take((size_t)B * P.CB * pl * 16) : 0;
+    P.ping[l][0] = take((size_t)B * P.CB * pl * 16);
+    P.ping[l][1] = take((size_t)B * P.CB * pl * 16);
+    P.up[l] = l ? take((size_t)B * P.CB * px * 16) : 0;
+  }
+  P.h1 = take((size_t)B * P.CB * px * 16);
+  P.h2 = take((size_t)B * P.CB * px * 16);
+  P.h3 = take((size_t)B * P.COB3 * px * 16);
+  const int nslots = 2 + P.L * P.R;
+  P.stats_bytes = (size_t)nslots * B * P.CB * 2 * sizeof(double) + (size_t)B * P.COB3 * 4 * sizeof(double) +
+                  (size_t)2 * B * sizeof(uint32_t);
+  P.stats = take(P.stats_bytes);
+  P.chan_sum = P.stats + (size_t)nslots * B * P.CB * 2 * sizeof(double);
+  P.uvmax = P.chan_sum + (size_t)B * P.COB3 * 4 * sizeof(double);
+  P.total = off;
+  return PBMC_OK;
+}
+
+inline pbmc_src make_src(const float* ptr, int nblk, int xform, const double* stats, const pbmc_layer* producer,
+                         double inv_count) {
+  pbmc_src s;
+  s.ptr = ptr; s.nblk = nblk; s.xform = xform; s.stats = stats;
+  s.gamma = producer ? producer->gamma : nullptr;
+  s.beta = producer ? producer->beta : nullptr;
+  s.inv_count = inv_count;
+  return s;
+}
+
+inline void fill_conv(pbmc_conv_desc& d, const pbmc_net& n, const pbmc_layer& L, int B, int H, int W, float* out,
+                      double* ostats, double* ochan, int epi_act) {
+  memset(&d, 0, sizeof(d));
+  d.B = B; d.H = H; d.W = W;
+  d.cout = L.cout; d.ksize = L.ksize; d.pad_mode = n.pad_mode; d.epi_act = epi_act; d.impl = n.conv_impl;
+  d.wpk = L.wpk; d.wpk_umma = L.wpk_umma; d.bias = L.bias; d.out = out; d.out_stats = ostats; d.out_chan_sum = ochan;
+}
+}  // namespace
+
+extern "C" size_t pbmc_workspace_bytes(const pbmc_net* n, int B, int H, int W) {
+  Plan P;
+  if (!n || make_plan(*n, B, H, W, P) != PBMC_OK) return 0;
+  return P.total;
+}
+
+#define RC(call)                 \
+  do {                           \
+    int _rc = (call);            \
+    if (_rc != PBMC_OK) return _rc; \
+  } while (0)
+
+// Enqueue one surrogate forward.  `uv` points at the 2*B uint32 slots (uvmax of this step).
+static int surrogate_enqueue(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, char* ws, const float* inp,
+                             const pbmc_member* members, float* u, float* v, float* p, uint32_t* uvmax, int B, int H,
+                             int W, cudaStream_t st) {
+  const int L = P.L, R = P.R, CB = P.CB;
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  auto S = [&](int slot) { return reinterpret_cast<double*>(ws + P.stat_off(slot, B)); };
+  double* chan_sum = reinterpret_cast<double*>(ws + P.chan_sum);
+  // zero all statistics accumulators (GroupNorm sums, zero-mean sums) in one memset
+  PBMC_CUDA(cudaMemsetAsync(ws + P.stats, 0, P.stats_bytes - (size_t)2 * B * sizeof(uint32_t), st));
+  if (uvmax) PBMC_CUDA(cudaMemsetAsync(uvmax, 0, (size_t)B * sizeof(uint32_t), st));
+
+  pbmc_conv_desc d;
+  // conv[0]: FluidLayer(c_i -> c_h), :1317
+  fill_conv(d, n, n.conv0, B, H, W, F(P.x0), S(0), nullptr, PBMC_ACT_NONE);
+  d.nsrc = 1;
+  d.src[0] = make_src(inp, P.CIB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
+  RC(conv_enqueue(d, st));
+  PBMC_CUDA(cudaEventRecord(ctx->ev_fork[0], st));
+
+  // pyramid levels (:1319-1327): level l runs on stream l (level 0 on the caller's stream)
+  const float* level_in[PBMC_MAX_LEVELS];
+  level_in[0] = F(P.x0);
+  for (int l = 0; l < L; ++l) {
+    cudaStream_t sl = l ? ctx->s[l] : st;
+    const int Hl = P.Hl[l], Wl = P.Wl[l];
+    if (l > 0) {
+      // pool^l(x_in) computed incrementally from level l-1's pooled input (identical composition)
+      PBMC_CUDA(cudaStreamWaitEvent(sl, ctx->ev_fork[l - 1], 0));
+      pbmc_src ps = (l == 1) ? make_src(F(P.x0), CB, PBMC_XFORM_GN_GELU, S(0), &n.conv0, 1.0 / (4.0 * H * W))
+                             : make_src(F(P.pooled[l - 1]), CB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
+      RC(pbmc_avgpool2(&ps, F(P.pooled[l]), B, P.Hl[l - 1], P.Wl[l - 1], sl));
+      PBMC_CUDA(cudaEventRecord(ctx->ev_fork[l], sl));
+      level_in[l] = F(P.pooled[l]);
+    }
+    const double invc = 1.0 / (4.0 * Hl * Wl);
+    for (int r = 0; r < R; ++r) {
+      const pbmc_layer& Lr = n.trunk[l * PBMC_MAX_REPEATS + r];
+      fill_conv(d, n, Lr, B, Hl, Wl, F(P.ping[l][r & 1]), S(1 + l * R + r), nullptr, PBMC_ACT_NONE);
+      d.nsrc = 1;
+      if (r == 0) {
+        d.src[0] = (l == 0) ? make_src(F(P.x0), CB, PBMC_XFORM_GN_GELU, S(0), &n.conv0, invc)
+                            : make_src(level_in[l], CB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
+      } else {
+        d.src[0] = make_src(F(P.ping[l][(r - 1) & 1]), CB, PBMC_XFORM_GN_GELU, S(1 + l * R + r - 1),
+                            &n.trunk[l * PBMC_MAX_REPEATS + r - 1], invc);
+      }
+      RC(conv_enqueue(d, sl));
+    }
+    if (l > 0) {
+      pbmc_src us = make_src(F(P.ping[l][(R - 1) & 1]), CB, PBMC_XFORM_GN_GELU, S(1 + l * R + R - 1),
+                             &n.trunk[l * PBMC_MAX_REPEATS + R - 1], invc);
+      RC(pbmc_bicubic_up(&us, F(P.up[l]), B, Hl, Wl, H, W, sl));
+      PBMC_CUDA(cudaEventRecord(ctx->ev_join[l], sl));
+    }
+  }
+  for (int l = 1; l < L; ++l) PBMC_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[l], 0));
+
+  // conv[1] over cat(levels..., inputs) (:1332-1335): the concat is a source list
+  fill_conv(d, n, n.conv1, B, H, W, F(P.h1), S(1 + L * R), nullptr, PBMC_ACT_NONE);
+  if (L + 1 > PBMC_MAX_SRC) return PBMC_ERR_UNSUPPORTED;
+  d.nsrc = L + 1;
+  d.src[0] = make_src(F(P.ping[0][(R - 1) & 1]), CB, PBMC_XFORM_GN_GELU, S(1 + R - 1), &n.trunk[R - 1], 1.0 / (4.0 * H * W));
+  for (int l = 1; l < L; ++l) d.src[l] = make_src(F(P.up[l]), CB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
+  d.src[L] = make_src(inp, P.CIB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
+  RC(conv_enqueue(d, st));
+  // gn[0] + act folded into conv[2]'s load; conv[2] + act (:1336-1340)
+  fill_conv(d, n, n.conv2, B, H, W, F(P.h2), nullptr, nullptr, PBMC_ACT_GELU);
+  d.nsrc = 1;
+  d.src[0] = make_src(F(P.h1), CB, PBMC_XFORM_GN_GELU, S(1 + L * R), &n.conv1, 1.0 / (4.0 * H * W));
+  RC(conv_enqueue(d, st));
+  // conv[3] (:1342) with per-channel sums for the zero-mean (:1343)
+  fill_conv(d, n, n.conv3, B, H, W, F(P.h3), nullptr, chan_sum, PBMC_ACT_NONE);
+  d.nsrc = 1;
+  d.src[0] = make_src(F(P.h2), CB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
+  RC(conv_enqueue(d, st));
+  RC(pbmc_head(F(P.h3), chan_sum, members, n.a_bound, n.head_kind, n.p_pred, u, v, p, uvmax, B, H, W, st));
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_surrogate_forward(pbmc_ctx* ctx, const pbmc_net* net, const float* inp, const pbmc_member* members,
+                                      float* u, float* v, float* p, uint32_t* uvmax, void* workspace,
+                                      size_t workspace_bytes, int B, int H, int W, void* stream) {
+  if (!ctx || !net || !inp || !u || !v || !workspace) return PBMC_ERR_NULL_POINTER;
+  Plan P;
+  RC(make_plan(*net, B, H, W, P));
+  if (workspace_bytes < P.total) return PBMC_ERR_WORKSPACE;
+  if (!aligned16(workspace) || !aligned16(inp)) return PBMC_ERR_MISALIGNED;
+  RC(check_device_ptr(workspace));
+  return surrogate_enqueue(ctx, *net, P, (char*)workspace, inp, members, u, v, p, uvmax, B, H, W, (cudaStream_t)stream);
+}
+
+namespace pbmc {
+__global__ void uvmax_batch_reduce_kernel(uint32_t* uv, int B) {
+  // ADNet's dt is ONE scalar over the whole batch (pytorch_networks_convae.py:556): fold members into slot 0
+  uint32_t m = 0;
+  for (int i = threadIdx.x; i < B; i += 32) m = max(m, uv[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (threadIdx.x == 0) uv[0] = m;
+}
+}  // namespace pbmc
+
+extern "C" int pbmc_rollout(pbmc_ctx* ctx, const pbmc_net* net, const pbmc_member* members, const float* xc,
+                            const float* yc, const float* ycc, const float* xcoef, const float* ycoef, double dx_min,
+                            double cn_max,
+                            int per_member_dt, float* T_seq, int nslots, int first_step, int n_steps, double* dt_seq,
+                            float* u, float* v, float* p, float* V, void* workspace, size_t workspace_bytes, int B, int H,
+                            int W, void* stream) {
+  if (!ctx || !net || !members || !xc || !yc || !ycc || !xcoef || !ycoef || !T_seq || !u || !v || !workspace) return PBMC_ERR_NULL_POINTER;
+  if (nslots < 2 || first_step < 1 || n_steps < 0 || !(dx_min > 0.0)) return PBMC_ERR_BAD_SHAPE;
+  if (net->c_i != 7) return PBMC_ERR_UNSUPPORTED;  // TS builds the 7-channel input (:390-407)
+  Plan P;
+  RC(make_plan(*net, B, H, W, P));
+  if (workspace_bytes < P.total) return PBMC_ERR_WORKSPACE;
+  if (!aligned16(workspace)) return PBMC_ERR_MISALIGNED;
+  RC(check_device_ptr(workspace));
+  RC(check_device_ptr(T_seq));
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  uint32_t* uvmax = reinterpret_cast<uint32_t*>(ws + P.uvmax);
+  const size_t field = (size_t)B * H * W;
+  for (int i = first_step; i < first_step + n_steps; ++i) {
+    const float* Tin = T_seq + (size_t)((i - 1) % nslots) * field;
+    float* Tout = T_seq + (size_t)(i % nslots) * field;
+    const bool last = (i == first_step + n_steps - 1);
+    RC(pbmc_build_input(Tin, xc, yc, ycc, members, reinterpret_cast<float*>(ws + P.inp), last ? V : nullptr, B, H, W, st));
+    RC(surrogate_enqueue(ctx, *net, P, ws, reinterpret_cast<float*>(ws + P.inp), members, u, v, p, uvmax, B, H, W, st));
+    if (!per_member_dt && B > 1) {
+      uvmax_batch_reduce_kernel<<<1, 32, 0, st>>>(uvmax, B);
+      PBMC_CHECK_LAUNCH("uvmax_batch_reduce_kernel");
+    }
+    RC(pbmc_advect_diffuse(Tin, u, v, xcoef, ycoef, members, uvmax, per_member_dt ? 1 : 0, dx_min, cn_max, 0.0, Tout, nullptr,
+                           dt_seq ? dt_seq + (size_t)(i - 1) * B : nullptr, B, H, W, st));
+  }
+  return PBMC_OK;
+}

@@ -1,0 +1,100 @@
+// Shared device/host helpers for libpbmc (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "pbmc.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libpbmc is written for sm_100a (B200) only"
+#endif
+
+namespace pbmc {
+
+// ---------------------------------------------------------------- host-side error plumbing
+void set_last_cuda_error(cudaError_t e, const char* where);
+
+#define PBMC_CHECK_LAUNCH(where)                         \
+  do {                                                   \
+    cudaError_t _e = cudaPeekAtLastError();              \
+    if (_e != cudaSuccess) {                             \
+      ::pbmc::set_last_cuda_error(_e, where);            \
+      return PBMC_ERR_CUDA;                              \
+    }                                                    \
+  } while (0)
+
+#define PBMC_CUDA(call)                                  \
+  do {                                                   \
+    cudaError_t _e = (call);                             \
+    if (_e != cudaSuccess) {                             \
+      ::pbmc::set_last_cuda_error(_e, #call);            \
+      return PBMC_ERR_CUDA;                              \
+    }                                                    \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- device math
+// exact-erf GELU, nn.GELU() default (pytorch_networks_convae.py:751)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// source index for a padded coordinate; returns -1 for a zero-padded tap
+__device__ __forceinline__ int pad_index(int i, int n, int mode) {
+  if (i >= 0 && i < n) return i;
+  if (mode == PBMC_PAD_REPLICATE) return i < 0 ? 0 : n - 1;
+  if (mode == PBMC_PAD_REFLECT) {
+    int r = i < 0 ? -i : 2 * (n - 1) - i;
+    return r < 0 ? 0 : (r >= n ? n - 1 : r);
+  }
+  return -1;
+}
+
+// Per-channel (scale, shift) of a fused GroupNorm: y = x*a + b, from raw (sum, sum^2).
+// torch.nn.GroupNorm semantics: biased variance, eps = 1e-5 (pytorch_networks_convae.py:788).
+__device__ __forceinline__ void gn_coeffs(const double* stats2, double inv_count, float gamma, float beta, float& a,
+                                          float& b) {
+  double mean = stats2[0] * inv_count;
+  double var = stats2[1] * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double rstd = rsqrt(var + 1e-5);
+  double ad = rstd * (double)gamma;
+  a = (float)ad;
+  b = (float)((double)beta - mean * ad);
+}
+
+__device__ __forceinline__ float4 xform4(float4 v, const float* a4, const float* b4, int xform) {
+  if (xform == PBMC_XFORM_NONE) return v;
+  if (xform != PBMC_XFORM_GELU) {
+    v.x = fmaf(v.x, a4[0], b4[0]);
+    v.y = fmaf(v.y, a4[1], b4[1]);
+    v.z = fmaf(v.z, a4[2], b4[2]);
+    v.w = fmaf(v.w, a4[3], b4[3]);
+  }
+  if (xform != PBMC_XFORM_GN) {
+    v.x = gelu_erf(v.x);
+    v.y = gelu_erf(v.y);
+    v.z = gelu_erf(v.z);
+    v.w = gelu_erf(v.w);
+  }
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// non-negative floats order like their bit patterns
+__device__ __forceinline__ void atomic_max_nonneg(uint32_t* addr, float v) { atomicMax(addr, __float_as_uint(v)); }
+
+}  // namespace pbmc

@@ -1,0 +1,261 @@
+// Layout conversion, network-input synthesis, AvgPool2d(2,2) and bicubic up-sampling.
+#include "common.cuh"
+
+namespace pbmc {
+
+// ---------------------------------------------------------------- NCHW <-> blocked
+__global__ void pack_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CB, size_t plane) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  const int cb = blockIdx.y, b = blockIdx.z;
+  float v[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const int c = cb * 4 + l;
+    v[l] = c < C ? __ldg(src + ((size_t)b * C + c) * plane + i) : 0.f;
+  }
+  *reinterpret_cast<float4*>(dst + (((size_t)b * CB + cb) * plane + i) * 4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+__global__ void unpack_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CB, size_t plane) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  const int cb = blockIdx.y, b = blockIdx.z;
+  const float4 v = ldg4(src + (((size_t)b * CB + cb) * plane + i) * 4);
+  const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const int c = cb * 4 + l;
+    if (c < C) dst[((size_t)b * C + c) * plane + i] = a[l];
+  }
+}
+
+// blocked -> NCHW with the producer's GroupNorm(+GELU) applied (FluidLayer.forward tail, :796-797)
+__global__ void finalize_nchw_kernel(const pbmc_src S, float* __restrict__ dst, int C, size_t plane) {
+  const int cb = blockIdx.y, b = blockIdx.z;
+  __shared__ float a4[4], b4[4];
+  if (threadIdx.x < 4) {
+    float a = 1.f, bb = 0.f;
+    if (S.xform == PBMC_XFORM_GN_GELU || S.xform == PBMC_XFORM_GN)
+      gn_coeffs(S.stats + ((size_t)b * S.nblk + cb) * 2, S.inv_count, S.gamma[cb * 4 + threadIdx.x],
+                S.beta[cb * 4 + threadIdx.x], a, bb);
+    a4[threadIdx.x] = a;
+    b4[threadIdx.x] = bb;
+  }
+  __syncthreads();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  float4 v = ldg4(S.ptr + (((size_t)b * S.nblk + cb) * plane + i) * 4);
+  v = xform4(v, a4, b4, S.xform);
+  const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const int c = cb * 4 + l;
+    if (c < C) dst[((size_t)b * C + c) * plane + i] = a[l];
+  }
+}
+
+// ---------------------------------------------------------------- A1: network input
+// TS.forward, pytorch_networks_convae.py:379-407.  log10(clip(exp(z),1e-8,1)) is evaluated as
+// clamp(z*log10(e), -8, 0): identical in exact arithmetic, and free of the exp->log10 round trip.
+__global__ void build_input_kernel(const float* __restrict__ T, const float* __restrict__ xc,
+                                   const float* __restrict__ yc, const float* __restrict__ ycc,
+                                   const pbmc_member* __restrict__ mem, float* __restrict__ inp, float* __restrict__ V,
+                                   size_t plane) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  const int b = blockIdx.y;
+  const pbmc_member m = mem[b];
+  const float t = __ldg(T + (size_t)b * plane + i);
+  const float z = m.ln_fkt * (0.0f - t) + m.ln_fkp * (1.0f - __ldg(ycc + i));
+  const float l10 = fminf(fmaxf(z * 0.43429448190325182765f, -8.0f), 0.0f);
+  float4 c0 = make_float4(__ldg(xc + i) * 0.25f, __ldg(yc + i) * 0.25f, l10 * 0.125f, m.raq_nd);
+  float4 c1 = make_float4(m.fkt_nd, m.fkp_nd, t, 0.f);
+  *reinterpret_cast<float4*>(inp + (((size_t)b * 2 + 0) * plane + i) * 4) = c0;
+  *reinterpret_cast<float4*>(inp + (((size_t)b * 2 + 1) * plane + i) * 4) = c1;
+  if (V != nullptr) V[(size_t)b * plane + i] = fminf(fmaxf(expf(z), 1e-8f), 1.0f);
+}
+
+// ---------------------------------------------------------------- A5: AvgPool2d(2,2), floor
+__global__ void avgpool2_kernel(const pbmc_src S, float* __restrict__ dst, int H, int W, int Ho, int Wo) {
+  const int cb = blockIdx.y, b = blockIdx.z;
+  __shared__ float a4[4], b4[4];
+  if (threadIdx.x < 4) {
+    float a = 1.f, bb = 0.f;
+    if (S.xform == PBMC_XFORM_GN_GELU || S.xform == PBMC_XFORM_GN)
+      gn_coeffs(S.stats + ((size_t)b * S.nblk + cb) * 2, S.inv_count, S.gamma[cb * 4 + threadIdx.x],
+                S.beta[cb * 4 + threadIdx.x], a, bb);
+    a4[threadIdx.x] = a;
+    b4[threadIdx.x] = bb;
+  }
+  __syncthreads();
+  const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (size_t)Ho * Wo) return;
+  const int oy = (int)(o / Wo), ox = (int)(o % Wo);
+  const float* base = S.ptr + ((size_t)b * S.nblk + cb) * (size_t)H * W * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      float4 v = ldg4(base + ((size_t)(2 * oy + dy) * W + 2 * ox + dx) * 4);
+      v = xform4(v, a4, b4, S.xform);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  s.x *= 0.25f; s.y *= 0.25f; s.z *= 0.25f; s.w *= 0.25f;
+  *reinterpret_cast<float4*>(dst + (((size_t)b * S.nblk + cb) * (size_t)Ho * Wo + o) * 4) = s;
+}
+
+// ---------------------------------------------------------------- A5: bicubic up-sampling
+// nn.Upsample(size, mode="bicubic"): align_corners=False, A = -0.75, source index
+// scale*(dst+0.5)-0.5 NOT clamped, the four taps clamped to [0, n-1].
+constexpr int BU_TW = 32, BU_TH = 8;  // output tile; 256 threads, one output pixel (float4) each
+constexpr int BU_MAX_SW = BU_TW + 4, BU_MAX_SH = BU_TH + 4;
+
+__device__ __forceinline__ void cubic_w(float t, float w[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+__device__ __forceinline__ int src_floor(int d, float scale, float& t) {
+  const float s = scale * ((float)d + 0.5f) - 0.5f;
+  const float f = floorf(s);
+  t = s - f;
+  return (int)f;
+}
+
+__global__ void __launch_bounds__(BU_TW* BU_TH) bicubic_kernel(const pbmc_src S, float* __restrict__ dst, int Hs, int Ws,
+                                                                int H, int W, float sy_scale, float sx_scale) {
+  __shared__ float4 tile[BU_MAX_SH][BU_MAX_SW];
+  __shared__ float a4[4], b4[4];
+  const int cb = blockIdx.z % S.nblk, b = blockIdx.z / S.nblk;
+  const int tid = threadIdx.y * BU_TW + threadIdx.x;
+  if (tid < 4) {
+    float a = 1.f, bb = 0.f;
+    if (S.xform == PBMC_XFORM_GN_GELU || S.xform == PBMC_XFORM_GN)
+      gn_coeffs(S.stats + ((size_t)b * S.nblk + cb) * 2, S.inv_count, S.gamma[cb * 4 + tid], S.beta[cb * 4 + tid], a, bb);
+    a4[tid] = a;
+    b4[tid] = bb;
+  }
+  const int ox0 = blockIdx.x * BU_TW, oy0 = blockIdx.y * BU_TH;
+  const int ox1 = min(ox0 + BU_TW, W) - 1, oy1 = min(oy0 + BU_TH, H) - 1;
+  float tdum;
+  // source footprint of this output tile (taps -1..+2 around the floor), clamped like the taps are
+  const int fx0 = max(src_floor(ox0, sx_scale, tdum) - 1, 0), fx1 = min(src_floor(ox1, sx_scale, tdum) + 2, Ws - 1);
+  const int fy0 = max(src_floor(oy0, sy_scale, tdum) - 1, 0), fy1 = min(src_floor(oy1, sy_scale, tdum) + 2, Hs - 1);
+  const int fw = fx1 - fx0 + 1, fh = fy1 - fy0 + 1;  // <= BU_T? + 4 because scale <= 1
+  __syncthreads();
+  const float* base = S.ptr + ((size_t)b * S.nblk + cb) * (size_t)Hs * Ws * 4;
+  for (int e = tid; e < fw * fh; e += BU_TW * BU_TH) {
+    const int r = e / fw, c = e % fw;
+    float4 v = ldg4(base + ((size_t)(fy0 + r) * Ws + fx0 + c) * 4);
+    tile[r][c] = xform4(v, a4, b4, S.xform);
+  }
+  __syncthreads();
+  const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
+  if (ox >= W || oy >= H) return;
+  float tx, ty, wx[4], wy[4];
+  const int ix = src_floor(ox, sx_scale, tx), iy = src_floor(oy, sy_scale, ty);
+  cubic_w(tx, wx);
+  cubic_w(ty, wy);
+  int cx[4], cy[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    cx[k] = min(max(ix - 1 + k, 0), Ws - 1) - fx0;
+    cy[k] = min(max(iy - 1 + k, 0), Hs - 1) - fy0;
+  }
+  // rows first, then columns: same association as oracle/ref_numpy.bicubic_upsample
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int kx = 0; kx < 4; ++kx) {
+    float4 colv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const float4 v = tile[cy[ky]][cx[kx]];
+      colv.x = fmaf(wy[ky], v.x, colv.x); colv.y = fmaf(wy[ky], v.y, colv.y);
+      colv.z = fmaf(wy[ky], v.z, colv.z); colv.w = fmaf(wy[ky], v.w, colv.w);
+    }
+    o.x = fmaf(wx[kx], colv.x, o.x); o.y = fmaf(wx[kx], colv.y, o.y);
+    o.z = fmaf(wx[kx], colv.z, o.z); o.w = fmaf(wx[kx], colv.w, o.w);
+  }
+  *reinterpret_cast<float4*>(dst + (((size_t)b * S.nblk + cb) * (size_t)H * W + (size_t)oy * W + ox) * 4) = o;
+}
+
+}  // namespace pbmc
+
+using namespace pbmc;
+
+extern "C" int pbmc_pack_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream) {
+  if (!src || !dst) return PBMC_ERR_NULL_POINTER;
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return PBMC_ERR_BAD_SHAPE;
+  if (!aligned16(dst)) return PBMC_ERR_MISALIGNED;
+  const size_t plane = (size_t)H * W;
+  dim3 grid((unsigned)((plane + 255) / 256), (C + 3) / 4, B);
+  pack_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, C, (C + 3) / 4, plane);
+  PBMC_CHECK_LAUNCH("pack_nchw_kernel");
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_unpack_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream) {
+  if (!src || !dst) return PBMC_ERR_NULL_POINTER;
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return PBMC_ERR_BAD_SHAPE;
+  if (!aligned16(src)) return PBMC_ERR_MISALIGNED;
+  const size_t plane = (size_t)H * W;
+  dim3 grid((unsigned)((plane + 255) / 256), (C + 3) / 4, B);
+  unpack_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, C, (C + 3) / 4, plane);
+  PBMC_CHECK_LAUNCH("unpack_nchw_kernel");
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_finalize_nchw(const pbmc_src* S, float* dst, int B, int C, int H, int W, void* stream) {
+  if (!S || !S->ptr || !dst) return PBMC_ERR_NULL_POINTER;
+  if ((S->xform == PBMC_XFORM_GN_GELU || S->xform == PBMC_XFORM_GN) && (!S->stats || !S->gamma || !S->beta)) return PBMC_ERR_NULL_POINTER;
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || S->nblk != (C + 3) / 4) return PBMC_ERR_BAD_SHAPE;
+  if (!aligned16(S->ptr)) return PBMC_ERR_MISALIGNED;
+  const size_t plane = (size_t)H * W;
+  dim3 grid((unsigned)((plane + 255) / 256), S->nblk, B);
+  finalize_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*S, dst, C, plane);
+  PBMC_CHECK_LAUNCH("finalize_nchw_kernel");
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_build_input(const float* T, const float* xc, const float* yc, const float* ycc,
+                                const pbmc_member* members, float* inp, float* V, int B, int H, int W, void* stream) {
+  if (!T || !xc || !yc || !ycc || !members || !inp) return PBMC_ERR_NULL_POINTER;
+  if (B <= 0 || H < 3 || W < 3) return PBMC_ERR_BAD_SHAPE;
+  if (!aligned16(inp)) return PBMC_ERR_MISALIGNED;
+  const size_t plane = (size_t)H * W;
+  dim3 grid((unsigned)((plane + 255) / 256), B);
+  build_input_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, xc, yc, ycc, members, inp, V, plane);
+  PBMC_CHECK_LAUNCH("build_input_kernel");
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_avgpool2(const pbmc_src* S, float* dst, int B, int H, int W, void* stream) {
+  if (!S || !S->ptr || !dst) return PBMC_ERR_NULL_POINTER;
+  if ((S->xform == PBMC_XFORM_GN_GELU || S->xform == PBMC_XFORM_GN) && (!S->stats || !S->gamma || !S->beta)) return PBMC_ERR_NULL_POINTER;
+  const int Ho = H / 2, Wo = W / 2;
+  if (B <= 0 || Ho <= 0 || Wo <= 0 || S->nblk <= 0) return PBMC_ERR_BAD_SHAPE;
+  if (!aligned16(S->ptr) || !aligned16(dst)) return PBMC_ERR_MISALIGNED;
+  dim3 grid((unsigned)(((size_t)Ho * Wo + 255) / 256), S->nblk, B);
+  avgpool2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*S, dst, H, W, Ho, Wo);
+  PBMC_CHECK_LAUNCH("avgpool2_kernel");
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_bicubic_up(const pbmc_src* S, float* dst, int B, int Hs, int Ws, int H, int W, void* stream) {
+  if (!S || !S->ptr || !dst) return PBMC_ERR_NULL_POINTER;
+  if ((S->xform == PBMC_XFORM_GN_GELU || S->xform == PBMC_XFORM_GN) && (!S->stats || !S->gamma || !S->beta)) return PBMC_ERR_NULL_POINTER;
+  if (B <= 0 || Hs <= 0 || Ws <= 0 || H < Hs || W < Ws || S->nblk <= 0) return PBMC_ERR_BAD_SHAPE;  // up-sampling only
+  if (!aligned16(S->ptr) || !aligned16(dst)) return PBMC_ERR_MISALIGNED;
+  dim3 grid(cdiv(W, BU_TW), cdiv(H, BU_TH), B * S->nblk);
+  if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
+  bicubic_kernel<<<grid, dim3(BU_TW, BU_TH), 0, (cudaStream_t)stream>>>(*S, dst, Hs, Ws, H, W, (float)Hs / (float)H,
+                                                                       (float)Ws / (float)W);
+  PBMC_CHECK_LAUNCH("bicubic_kernel");
+  return PBMC_OK;
+}

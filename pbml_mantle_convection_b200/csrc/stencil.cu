@@ -1,0 +1,391 @@
+// A8/A9: explicit advection-diffusion update of T with the CFL time step, one HBM pass.
+//   ADNet.forward          pytorch_networks_convae.py:522-568
+//     forced wall coords   :532-535      one-sided differences :537-545 (FD kernels :183-214)
+//     upwind advection     :547-548      non-uniform central diffusion :550-552
+//     dt                   :554-559      update + replicate pad + wall rows :561-567
+//   TS boundary rows/cols  :468-471      (idempotent on top of ADNet's own BCs)
+// Algorithmic traffic: read T,u,v + write T' = 16 B per cell (fp32).  The CFL reduction
+// max|u|,|v| of the interior is produced in the same pass (warp shuffle -> block -> one
+// atomicMax per CTA), so a following step (or sweep) never needs a separate reduction pass.
+#include "common.cuh"
+
+namespace pbmc {
+
+constexpr int ST_BX = 32, ST_BY = 8, ST_RPT = 4;  // block threads, rows per thread
+constexpr int ST_TH = ST_BY * ST_RPT;             // 32-row tile
+
+struct StencilParams {
+  const float* T; const float* u; const float* v; const float* xcoef; const float* ycoef;
+  const pbmc_member* mem; const uint32_t* uvmax_in; uint32_t* uvmax_out; float* T_out; double* dt_out;
+  double dx_min, cn_max, dt_fixed;
+  int member_stride, H, W;
+};
+
+__device__ __forceinline__ double cfl_dt(double uvm, double dx_min, double cn_max) {
+  // :557-559 verbatim (dt_diffuse reduces to dx_min^2/4)
+  const double dt_adv = 0.5 * cn_max * dx_min / uvm;
+  const double dt_dif = 0.5 * ((dx_min * dx_min) * (dx_min * dx_min)) / (dx_min * dx_min + dx_min * dx_min);
+  return fmin(dt_adv, dt_dif);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(ST_BX* ST_BY) stencil_kernel(const StencilParams p) {
+  constexpr int TW = ST_BX * VEC;
+  constexpr int PITCH = TW + 8;  // body at [4, 4+TW), halos at 3 and 4+TW; rows stay 16B aligned
+  __shared__ __align__(16) float Ts[ST_TH + 2][PITCH];
+  __shared__ float idxl[TW], idxr[TW], idxc[TW];  // 1/dx_left, 1/dx_right, 1/(0.5 dx_r + 0.5 dx_l) per column
+  __shared__ float idyt[ST_TH], idyb[ST_TH], idyc[ST_TH];
+  __shared__ float dt_s;
+  __shared__ float red[ST_BY];
+
+  const int H = p.H, W = p.W, b = blockIdx.z;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * ST_BX + tx;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * ST_TH;
+  const size_t plane = (size_t)H * W;
+  const float* Tb = p.T + (size_t)b * plane;
+  const float* ub = p.u + (size_t)b * plane;
+  const float* vb = p.v + (size_t)b * plane;
+
+  // ---- issue the u,v loads first: they stay in flight while the T tile is staged
+  float uu[ST_RPT][VEC], vv[ST_RPT][VEC];
+  const int gx = x0 + tx * VEC;
+#pragma unroll
+  for (int r = 0; r < ST_RPT; ++r) {
+    const int gy = y0 + ty + r * ST_BY;
+    const bool in = gy > 0 && gy < H - 1 && gx < W;
+    if (VEC == 4) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+      if (in) {
+        a = __ldcs(reinterpret_cast<const float4*>(ub + (size_t)gy * W + gx));
+        c = __ldcs(reinterpret_cast<const float4*>(vb + (size_t)gy * W + gx));
+      }
+      uu[r][0] = a.x; uu[r][VEC > 1 ? 1 : 0] = a.y; uu[r][VEC > 2 ? 2 : 0] = a.z; uu[r][VEC > 3 ? 3 : 0] = a.w;
+      vv[r][0] = c.x; vv[r][VEC > 1 ? 1 : 0] = c.y; vv[r][VEC > 2 ? 2 : 0] = c.z; vv[r][VEC > 3 ? 3 : 0] = c.w;
+    } else {
+      uu[r][0] = in ? __ldcs(ub + (size_t)gy * W + gx) : 0.f;
+      vv[r][0] = in ? __ldcs(vb + (size_t)gy * W + gx) : 0.f;
+    }
+  }
+
+  // ---- T tile with a one-cell halo
+  if (VEC == 4) {
+    for (int e = tid; e < (ST_TH + 2) * ST_BX; e += ST_BX * ST_BY) {
+      const int r = e / ST_BX, c4 = e % ST_BX;
+      const int gy = y0 + r - 1, gxx = x0 + c4 * 4;
+      if (gy >= 0 && gy < H && gxx < W)
+        *reinterpret_cast<float4*>(&Ts[r][4 + c4 * 4]) = __ldg(reinterpret_cast<const float4*>(Tb + (size_t)gy * W + gxx));
+    }
+  } else {
+    for (int e = tid; e < (ST_TH + 2) * TW; e += ST_BX * ST_BY) {
+      const int r = e / TW, c = e % TW;
+      const int gy = y0 + r - 1, gxx = x0 + c;
+      if (gy >= 0 && gy < H && gxx < W) Ts[r][4 + c] = __ldg(Tb + (size_t)gy * W + gxx);
+    }
+  }
+  if (tid < 2 * (ST_TH + 2)) {
+    const int r = tid >> 1, side = tid & 1;
+    const int gy = y0 + r - 1, gxx = side ? x0 + TW : x0 - 1;
+    if (gy >= 0 && gy < H && gxx >= 0 && gxx < W) Ts[r][side ? 4 + TW : 3] = __ldg(Tb + (size_t)gy * W + gxx);
+  }
+  // ---- inverse spacings, precomputed in double by pbmc_stencil_coefs: [3][n] = 1/d_minus, 1/d_plus, 1/(0.5 d_plus + 0.5 d_minus)
+  for (int c = tid; c < TW; c += ST_BX * ST_BY) {
+    const int j = x0 + c;
+    if (j > 0 && j < W - 1) {
+      idxl[c] = __ldg(p.xcoef + j); idxr[c] = __ldg(p.xcoef + W + j); idxc[c] = __ldg(p.xcoef + 2 * W + j);
+    }
+  }
+  for (int r = tid; r < ST_TH; r += ST_BX * ST_BY) {
+    const int i = y0 + r;
+    if (i > 0 && i < H - 1) {
+      idyt[r] = __ldg(p.ycoef + i); idyb[r] = __ldg(p.ycoef + H + i); idyc[r] = __ldg(p.ycoef + 2 * H + i);
+    }
+  }
+  if (tid == 0) {
+    double dt = p.dt_fixed;
+    if (!(dt > 0.0)) dt = cfl_dt((double)__uint_as_float(p.uvmax_in[(size_t)b * p.member_stride]), p.dx_min, p.cn_max);
+    dt_s = (float)dt;
+    if (p.dt_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0) p.dt_out[b] = dt;
+  }
+  __syncthreads();
+
+  const float dt = dt_s;
+  const float raq = p.mem ? p.mem[b].raq : 0.f;
+  float m = 0.f;
+  float* To = p.T_out + (size_t)b * plane;
+#pragma unroll
+  for (int r = 0; r < ST_RPT; ++r) {
+    const int lr = ty + r * ST_BY;  // local row in [0, ST_TH)
+    const int gy = y0 + lr;
+    if (gy >= H || gx >= W) continue;
+    float o[VEC];
+    if (gy == 0) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o[k] = 1.0f;  // hot bottom wall (:566, :468)
+    } else if (gy == H - 1) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o[k] = 0.0f;  // cold top wall (:567, :469)
+    } else {
+      const float iyt = idyt[lr], iyb = idyb[lr], iyc = idyc[lr];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const int c = tx * VEC + k, j = x0 + c;
+        o[k] = 0.f;
+        if (j > 0 && j < W - 1) {
+          const float Tc = Ts[lr + 1][4 + c];
+          const float Tl = (Tc - Ts[lr + 1][3 + c]) * idxl[c];
+          const float Tr = (Ts[lr + 1][5 + c] - Tc) * idxr[c];
+          const float Tt = (Tc - Ts[lr][4 + c]) * iyt;
+          const float Tbm = (Ts[lr + 2][4 + c] - Tc) * iyb;
+          const float u_ = uu[r][k], v_ = vv[r][k];
+          const float Tx = u_ > 0.f ? Tl : (u_ < 0.f ? Tr : 0.f);
+          const float Ty = v_ > 0.f ? Tt : (v_ < 0.f ? Tbm : 0.f);
+          const float lap = (Tr - Tl) * idxc[c] + (Tbm - Tt) * iyc;
+          o[k] = Tc + dt * (-u_ * Tx - v_ * Ty + lap + raq);
+          m = fmaxf(m, fmaxf(fabsf(u_), fabsf(v_)));
+        }
+      }
+      // side columns copy their interior neighbour (replicate pad :565, :470-471)
+      if (VEC == 4) {
+        if (gx == 0) o[0] = o[VEC > 1 ? 1 : 0];
+        if (gx + VEC == W) o[VEC - 1] = o[VEC > 1 ? VEC - 2 : 0];
+      }
+    }
+    if (VEC == 4) {
+      __stcs(reinterpret_cast<float4*>(To + (size_t)gy * W + gx),
+             make_float4(o[0], o[VEC > 1 ? 1 : 0], o[VEC > 2 ? 2 : 0], o[VEC > 3 ? 3 : 0]));
+    } else {
+      const int j = gx;
+      if (j > 0 && j < W - 1) {
+        To[(size_t)gy * W + j] = o[0];
+        if (gy > 0 && gy < H - 1) {
+          if (j == 1) To[(size_t)gy * W] = o[0];
+          if (j == W - 2) To[(size_t)gy * W + W - 1] = o[0];
+        }
+      } else if (gy == 0 || gy == H - 1) {
+        To[(size_t)gy * W + j] = o[0];
+      }
+    }
+  }
+  if (p.uvmax_out != nullptr) {
+    m = warp_max(m);
+    if (tx == 0) red[ty] = m;
+    __syncthreads();
+    if (tid < ST_BY) {
+      float t = red[tid];
+#pragma unroll
+      for (int o2 = ST_BY / 2; o2 > 0; o2 >>= 1) t = fmaxf(t, __shfl_xor_sync((1u << ST_BY) - 1u, t, o2));
+      if (tid == 0) atomic_max_nonneg(p.uvmax_out + (size_t)b * p.member_stride, t);
+    }
+  }
+}
+
+// ---- stand-alone interior max|u|,|v| (only when no producer supplied it)
+__global__ void __launch_bounds__(256) uvmax_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                                                    uint32_t* __restrict__ out, int member_stride, int H, int W) {
+  const int b = blockIdx.y;
+  const size_t plane = (size_t)H * W;
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / W), c = (int)(i % W);
+    if (r > 0 && r < H - 1 && c > 0 && c < W - 1)
+      m = fmaxf(m, fmaxf(fabsf(__ldg(u + (size_t)b * plane + i)), fabsf(__ldg(v + (size_t)b * plane + i))));
+  }
+  __shared__ float red[8];
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffu, t, o));
+    if (threadIdx.x == 0) atomic_max_nonneg(out + (size_t)b * member_stride, t);
+  }
+}
+
+// ---- general form: coordinates (and optionally RaQ) given as fields, exactly ADNet's inputs tensor
+__global__ void __launch_bounds__(256) stencil_fields_kernel(const float* __restrict__ T, const float* __restrict__ u,
+                                                             const float* __restrict__ v, const double* __restrict__ xc,
+                                                             const double* __restrict__ yc, size_t coord_stride,
+                                                             const float* __restrict__ raq_field, const pbmc_member* mem,
+                                                             const uint32_t* uvmax_in, int member_stride,
+                                                             const double* dx_min_dev, double cn_max,
+                                                             const double* dt_fixed_dev, float* __restrict__ T_out,
+                                                             double* dt_out, int H, int W) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+  __shared__ float dt_s;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    double dt = dt_fixed_dev ? *dt_fixed_dev : 0.0;
+    if (!(dt > 0.0)) dt = cfl_dt((double)__uint_as_float(uvmax_in[(size_t)b * member_stride]), *dx_min_dev, cn_max);
+    dt_s = (float)dt;
+    if (dt_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0) dt_out[b] = dt;
+  }
+  __syncthreads();
+  if (i >= H || j >= W) return;
+  const size_t plane = (size_t)H * W;
+  const float* Tb = T + (size_t)b * plane;
+  const double* xb = xc + (size_t)b * coord_stride;
+  const double* yb = yc + (size_t)b * coord_stride;
+  float* To = T_out + (size_t)b * plane;
+  if (i == 0) { To[j] = 1.f; return; }
+  if (i == H - 1) { To[(size_t)i * W + j] = 0.f; return; }
+  if (j == 0 || j == W - 1) return;  // written by the neighbouring interior cell
+  // spacings in double: differences of O(1) coordinates lose ~1e-5 relative accuracy in float
+  auto X = [&](int ii, int jj) { return jj == 0 ? 0.0 : (jj == W - 1 ? 4.0 : __ldg(xb + (size_t)ii * W + jj)); };
+  auto Y = [&](int ii, int jj) { return ii == 0 ? 0.0 : (ii == H - 1 ? 1.0 : __ldg(yb + (size_t)ii * W + jj)); };
+  const float dxl = (float)(X(i, j) - X(i, j - 1)), dxr = (float)(X(i, j + 1) - X(i, j));
+  const float dyt = (float)(Y(i, j) - Y(i - 1, j)), dyb = (float)(Y(i + 1, j) - Y(i, j));
+  const size_t c = (size_t)i * W + j;
+  const float Tc = Tb[c];
+  const float Tl = (Tc - Tb[c - 1]) / dxl, Tr = (Tb[c + 1] - Tc) / dxr;
+  const float Tt = (Tc - Tb[c - W]) / dyt, Tbm = (Tb[c + W] - Tc) / dyb;
+  const float u_ = u[(size_t)b * plane + c], v_ = v[(size_t)b * plane + c];
+  const float Tx = u_ > 0.f ? Tl : (u_ < 0.f ? Tr : 0.f);
+  const float Ty = v_ > 0.f ? Tt : (v_ < 0.f ? Tbm : 0.f);
+  const float lap = (Tr - Tl) / (0.5f * dxr + 0.5f * dxl) + (Tbm - Tt) / (0.5f * dyb + 0.5f * dyt);
+  const float raq = raq_field ? __ldg(raq_field + (size_t)b * plane + c) : (mem ? mem[b].raq : 0.f);
+  const float o = Tc + dt_s * (-u_ * Tx - v_ * Ty + lap + raq);
+  To[c] = o;
+  if (j == 1) To[(size_t)i * W] = o;
+  if (j == W - 2) To[(size_t)i * W + W - 1] = o;
+}
+
+// ---- inverse spacings of one coordinate axis, from double coordinates with forced wall values (:532-545)
+__global__ void stencil_coefs_kernel(const double* __restrict__ c, int n, double lo, double hi, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f, b = 0.f, d = 0.f;
+  if (i > 0 && i < n - 1) {
+    const double cm = (i - 1 == 0) ? lo : c[i - 1], cp = (i + 1 == n - 1) ? hi : c[i + 1], ci = c[i];
+    const double dm = ci - cm, dp = cp - ci;
+    a = (float)(1.0 / dm); b = (float)(1.0 / dp); d = (float)(1.0 / (0.5 * dp + 0.5 * dm));
+  }
+  out[i] = a; out[n + i] = b; out[2 * n + i] = d;
+}
+
+// ---- A10: advect_wi_gaia.py:624-629
+__global__ void clamp_T_kernel(float* __restrict__ T, int core_cool, int H, int W) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+  if (i >= H || j >= W) return;
+  float* Tb = T + (size_t)b * H * W;
+  const int js = j == 0 ? 1 : (j == W - 1 ? W - 2 : j);
+  float t = Tb[(size_t)i * W + js];
+  if (i == 0 && !core_cool) t = 1.f;
+  if (i == H - 1) t = 0.f;
+  t = fminf(fmaxf(t, 0.f), 2.f);
+  Tb[(size_t)i * W + j] = t;
+}
+
+// ---- A11: row means (profile) and mean-T in double
+__global__ void __launch_bounds__(256) row_mean_kernel(const float* __restrict__ T, double* __restrict__ prof, int H, int W) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  const float* row = T + ((size_t)b * H + i) * W;
+  double s = 0.0;
+  for (int j = threadIdx.x; j < W; j += 256) s += (double)__ldg(row + j);
+  __shared__ double red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    prof[(size_t)b * H + i] = t / (double)W;
+  }
+}
+__global__ void __launch_bounds__(256) prof_mean_kernel(const double* __restrict__ prof, double* __restrict__ meanT, int H) {
+  const int b = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < H; i += 256) s += prof[(size_t)b * H + i];
+  __shared__ double red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    meanT[b] = t / (double)H;
+  }
+}
+
+}  // namespace pbmc
+
+using namespace pbmc;
+
+extern "C" int pbmc_stencil_coefs(const double* coord, int n, double wall_lo, double wall_hi, float* coef, void* stream) {
+  if (!coord || !coef) return PBMC_ERR_NULL_POINTER;
+  if (n < 3) return PBMC_ERR_BAD_SHAPE;
+  stencil_coefs_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(coord, n, wall_lo, wall_hi, coef);
+  PBMC_CHECK_LAUNCH("stencil_coefs_kernel");
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_advect_diffuse(const float* T, const float* u, const float* v, const float* x, const float* y,
+                                   const pbmc_member* members, const uint32_t* uvmax_in, int member_stride,
+                                   double dx_min, double cn_max, double dt_fixed, float* T_out, uint32_t* uvmax_out,
+                                   double* dt_out, int B, int H, int W, void* stream) {
+  if (!T || !u || !v || !x || !y || !T_out) return PBMC_ERR_NULL_POINTER;
+  if (!(dt_fixed > 0.0) && !uvmax_in) return PBMC_ERR_NULL_POINTER;
+  if (B <= 0 || H < 3 || W < 3 || (member_stride != 0 && member_stride != 1)) return PBMC_ERR_BAD_SHAPE;
+  if (T == T_out) return PBMC_ERR_UNSUPPORTED;  // out-of-place only (neighbours are read)
+  StencilParams p{T, u, v, x, y, members, uvmax_in, uvmax_out, T_out, dt_out, dx_min, cn_max, dt_fixed, member_stride, H, W};
+  const bool vec = (W % 4 == 0) && aligned16(T) && aligned16(u) && aligned16(v) && aligned16(T_out);
+  const int TW = vec ? ST_BX * 4 : ST_BX;
+  dim3 grid(cdiv(W, TW), cdiv(H, ST_TH), B);
+  if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
+  if (vec)
+    stencil_kernel<4><<<grid, dim3(ST_BX, ST_BY), 0, (cudaStream_t)stream>>>(p);
+  else
+    stencil_kernel<1><<<grid, dim3(ST_BX, ST_BY), 0, (cudaStream_t)stream>>>(p);
+  PBMC_CHECK_LAUNCH("stencil_kernel");
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_uvmax(const float* u, const float* v, uint32_t* uvmax, int member_stride, int B, int H, int W,
+                          void* stream) {
+  if (!u || !v || !uvmax) return PBMC_ERR_NULL_POINTER;
+  if (B <= 0 || H < 3 || W < 3 || (member_stride != 0 && member_stride != 1)) return PBMC_ERR_BAD_SHAPE;
+  const size_t plane = (size_t)H * W;
+  const unsigned nb = (unsigned)min((size_t)1184, (plane + 255) / 256);
+  uvmax_kernel<<<dim3(nb, B), 256, 0, (cudaStream_t)stream>>>(u, v, uvmax, member_stride, H, W);
+  PBMC_CHECK_LAUNCH("uvmax_kernel");
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_advect_diffuse_fields(const float* T, const float* u, const float* v, const double* xc,
+                                          const double* yc, size_t coord_batch_stride, const float* raq_field,
+                                          const pbmc_member* members, const uint32_t* uvmax_in, int member_stride,
+                                          const double* dx_min_dev, double cn_max, const double* dt_fixed_dev,
+                                          float* T_out, double* dt_out, int B, int H, int W, void* stream) {
+  if (!T || !u || !v || !xc || !yc || !T_out) return PBMC_ERR_NULL_POINTER;
+  if (!dt_fixed_dev && (!uvmax_in || !dx_min_dev)) return PBMC_ERR_NULL_POINTER;
+  if (B <= 0 || H < 3 || W < 3 || (member_stride != 0 && member_stride != 1)) return PBMC_ERR_BAD_SHAPE;
+  if (coord_batch_stride != 0 && coord_batch_stride != (size_t)H * W) return PBMC_ERR_BAD_SHAPE;
+  if (T == T_out) return PBMC_ERR_UNSUPPORTED;
+  dim3 grid(cdiv(W, 32), cdiv(H, 8), B);
+  if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
+  stencil_fields_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(T, u, v, xc, yc, coord_batch_stride, raq_field,
+                                                                       members, uvmax_in, member_stride, dx_min_dev,
+                                                                       cn_max, dt_fixed_dev, T_out, dt_out, H, W);
+  PBMC_CHECK_LAUNCH("stencil_fields_kernel");
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_clamp_T(float* T, int core_cool, int B, int H, int W, void* stream) {
+  if (!T) return PBMC_ERR_NULL_POINTER;
+  if (B <= 0 || H < 3 || W < 3) return PBMC_ERR_BAD_SHAPE;
+  dim3 grid(cdiv(W, 32), cdiv(H, 8), B);
+  clamp_T_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(T, core_cool, H, W);
+  PBMC_CHECK_LAUNCH("clamp_T_kernel");
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_diagnostics(const float* T, double* prof, double* meanT, int B, int H, int W, void* stream) {
+  if (!T || !prof || !meanT) return PBMC_ERR_NULL_POINTER;
+  if (B <= 0 || H <= 0 || W <= 0 || H > 65535 * 16) return PBMC_ERR_BAD_SHAPE;
+  row_mean_kernel<<<dim3(H, B), 256, 0, (cudaStream_t)stream>>>(T, prof, H, W);
+  PBMC_CHECK_LAUNCH("row_mean_kernel");
+  prof_mean_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(prof, meanT, H);
+  PBMC_CHECK_LAUNCH("prof_mean_kernel");
+  return PBMC_OK;
+}

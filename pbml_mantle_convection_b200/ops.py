@@ -1,0 +1,266 @@
+"""Tensor-level wrappers over the C ABI (one Python function per `pbmc_*` operator).
+
+These are the building blocks the drop-in modules use for their stand-alone `forward`s and
+that the `-m gpu` parity tests call directly.  All tensors are float32 CUDA tensors owned by
+PyTorch; the wrappers only allocate outputs and pass pointers + the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.PbmcError("this operator has no CPU implementation; pass CUDA tensors")
+
+
+def nblk(c):
+    return (int(c) + 3) // 4
+
+
+# ------------------------------------------------------------------ weights
+def expand_symmetric(w_unique: torch.Tensor, c_out: int) -> torch.Tensor:
+    """Full filter bank of a SymmetricConv2d with symmetry {'h': h} (symmetric_layers_torch.py:118-138):
+    [unique..., x-mirrored copies of the first h/2]."""
+    n_mirror = c_out - w_unique.shape[0]
+    if n_mirror == 0:
+        return w_unique
+    return torch.cat([w_unique, torch.flip(w_unique[:n_mirror], (3,))], 0)
+
+
+def pack_conv_weight(w_full: torch.Tensor, src_channels) -> torch.Tensor:
+    """[Co, Ci, k, k] -> float32 [ceil(Co/16)][cin_blks][k*k][4][16] (layout in include/pbmc.h).
+    `src_channels`: channels contributed by each conv source, in concat order; each source is
+    padded to a multiple of 4 input lanes (zero weights)."""
+    Co, Ci, k, _ = w_full.shape
+    assert sum(src_channels) == Ci, (src_channels, Ci)
+    parts, c0 = [], 0
+    for c in src_channels:
+        wpart = w_full[:, c0:c0 + c]
+        pad = nblk(c) * 4 - c
+        if pad:
+            wpart = torch.cat([wpart, wpart.new_zeros(Co, pad, k, k)], 1)
+        parts.append(wpart)
+        c0 += c
+    w = torch.cat(parts, 1).float()
+    cg = (Co + 15) // 16
+    if cg * 16 != Co:
+        w = torch.cat([w, w.new_zeros(cg * 16 - Co, w.shape[1], k, k)], 0)
+    cb = w.shape[1] // 4
+    w = w.reshape(cg, 16, cb, 4, k * k).permute(0, 2, 4, 3, 1).contiguous()  # [cg][cb][tap][ci][co]
+    return w
+
+
+def pad_vec(v, c: int, device, fill=0.0) -> torch.Tensor:
+    """[c] -> float32 [ceil(c/4)*4] on `device` (v=None: all `fill`)."""
+    out = torch.full((nblk(c) * 4,), fill, dtype=torch.float32, device=device)
+    if v is not None:
+        out[:c] = v.detach().to(device, torch.float32).reshape(-1)
+    return out
+
+
+# ------------------------------------------------------------------ layout
+def pack_nchw(x: torch.Tensor) -> torch.Tensor:
+    _chk_cuda(x)
+    x = x.contiguous().float()
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, nblk(Cc), H, W, 4, dtype=torch.float32, device=x.device)
+    L.check(L.load().pbmc_pack_nchw(L.ptr(x), L.ptr(out), B, Cc, H, W, L.stream_ptr(x.device)), "pbmc_pack_nchw")
+    return out
+
+
+def unpack_nchw(xb: torch.Tensor, Cc: int) -> torch.Tensor:
+    _chk_cuda(xb)
+    B, CB, H, W, _ = xb.shape
+    out = torch.empty(B, Cc, H, W, dtype=torch.float32, device=xb.device)
+    L.check(L.load().pbmc_unpack_nchw(L.ptr(xb), L.ptr(out), B, Cc, H, W, L.stream_ptr(xb.device)), "pbmc_unpack_nchw")
+    return out
+
+
+class Source:
+    """A conv/pool/upsample input: blocked tensor + the producer's fused GroupNorm(+GELU)."""
+
+    def __init__(self, t, xform=L.XFORM_NONE, stats=None, gamma=None, beta=None, channels_per_group=4):
+        self.t, self.xform, self.stats, self.gamma, self.beta = t, xform, stats, gamma, beta
+        B, CB, H, W, _ = t.shape
+        self.nblk = CB
+        self.inv_count = 1.0 / (channels_per_group * H * W) if xform in (L.XFORM_GN_GELU, L.XFORM_GN) else 0.0
+
+    def c(self):
+        return L.make_src(self.t, self.nblk, self.xform, self.stats, self.gamma, self.beta, self.inv_count)
+
+
+def finalize_nchw(src: Source, Cc: int) -> torch.Tensor:
+    B, CB, H, W, _ = src.t.shape
+    out = torch.empty(B, Cc, H, W, dtype=torch.float32, device=src.t.device)
+    s = src.c()
+    L.check(L.load().pbmc_finalize_nchw(C.byref(s), L.ptr(out), B, Cc, H, W, L.stream_ptr(out.device)), "pbmc_finalize_nchw")
+    return out
+
+
+# ------------------------------------------------------------------ conv
+def conv_fwd(sources, wpk, bias, cout, ksize, pad_mode, epi_act=L.ACT_NONE, want_stats=False, want_chan_sum=False,
+             impl="auto", wpk_umma=None, out=None, stats=None, csum=None):
+    """Returns (out_blocked, stats|None, chan_sum|None).  `out`/`stats`/`csum` may be preallocated
+    (statistics ACCUMULATE into the given buffers, as in the C ABI)."""
+    t0 = sources[0].t
+    B, _, H, W, _ = t0.shape
+    dev = t0.device
+    cob = nblk(cout)
+    if out is None:
+        out = torch.empty(B, cob, H, W, 4, dtype=torch.float32, device=dev)
+    if stats is None and want_stats:
+        stats = torch.zeros(B, cob, 2, dtype=torch.float64, device=dev)
+    if csum is None and want_chan_sum:
+        csum = torch.zeros(B, cob * 4, dtype=torch.float64, device=dev)
+    d = L.ConvDesc()
+    d.nsrc = len(sources)
+    for i, s in enumerate(sources):
+        d.src[i] = s.c()
+    d.B, d.H, d.W, d.cout, d.ksize = B, H, W, int(cout), int(ksize)
+    d.pad_mode = L.PAD[pad_mode] if isinstance(pad_mode, str) else int(pad_mode)
+    d.epi_act, d.impl = int(epi_act), L.CONV_IMPL[impl]
+    d.wpk, d.wpk_umma, d.bias, d.out = L.ptr(wpk), L.ptr(wpk_umma), L.ptr(bias), L.ptr(out)
+    d.out_stats, d.out_chan_sum = L.ptr(stats), L.ptr(csum)
+    L.check(L.load().pbmc_conv_fwd(C.byref(d), L.stream_ptr(dev)), "pbmc_conv_fwd")
+    return out, stats, csum
+
+
+# ------------------------------------------------------------------ pyramid
+def avgpool2(src: Source) -> torch.Tensor:
+    B, CB, H, W, _ = src.t.shape
+    out = torch.empty(B, CB, H // 2, W // 2, 4, dtype=torch.float32, device=src.t.device)
+    s = src.c()
+    L.check(L.load().pbmc_avgpool2(C.byref(s), L.ptr(out), B, H, W, L.stream_ptr(out.device)), "pbmc_avgpool2")
+    return out
+
+
+def bicubic_up(src: Source, H: int, W: int) -> torch.Tensor:
+    B, CB, Hs, Ws, _ = src.t.shape
+    out = torch.empty(B, CB, H, W, 4, dtype=torch.float32, device=src.t.device)
+    s = src.c()
+    L.check(L.load().pbmc_bicubic_up(C.byref(s), L.ptr(out), B, Hs, Ws, H, W, L.stream_ptr(out.device)), "pbmc_bicubic_up")
+    return out
+
+
+# ------------------------------------------------------------------ members
+def member_values(raq, fkt, fkp):
+    """Host-side per-run constants (advect_wi_gaia.py:443-460, pytorch_networks_convae.py:343-350), in double."""
+    raq, fkt, fkp = float(raq), float(fkt), float(fkp)
+    raq_nd = (raq - 0.12624371) / (9.70723344 - 0.12624371)
+    fkt_nd = (math.log10(fkt) - 6.00352841978384) / (9.888820429862925 - 6.00352841978384)
+    fkp_nd = (math.log10(fkp) - 0.005251646002323797) / (1.9927988938926755 - 0.005251646002323797)
+    scaler = math.exp(raq / 10 * 1.80167667 + math.log(fkt) * 0.4330392 + math.log(fkp) * -0.46052953) * 5
+    return [raq_nd, fkt_nd, fkp_nd, math.log(fkt), math.log(fkp), raq, scaler, 0.0]
+
+
+def make_members(params, device, nd_override=None) -> torch.Tensor:
+    """params: iterable of (raq, fkt, fkp).  Returns a float32 [B, 8] tensor laid out as pbmc_member[B].
+    nd_override: optional iterable of (raq_nd, fkt_nd, fkp_nd) when the caller supplies its own
+    normalised values (TS.forward takes them as arguments)."""
+    rows = [member_values(*p) for p in params]
+    if nd_override is not None:
+        for r, nd in zip(rows, nd_override):
+            r[0], r[1], r[2] = float(nd[0]), float(nd[1]), float(nd[2])
+    return torch.tensor(rows, dtype=torch.float64).float().to(device).contiguous()
+
+
+# ------------------------------------------------------------------ input / head / stencil
+def build_input(T, xc, yc, ycc, members, want_V=False):
+    """T [B,H,W]; xc,yc,ycc [H,W]; members [B,8] -> (inp blocked [B,2,H,W,4], V|None)."""
+    _chk_cuda(T, xc, yc, ycc, members)
+    B, H, W = T.shape
+    inp = torch.empty(B, 2, H, W, 4, dtype=torch.float32, device=T.device)
+    V = torch.empty(B, H, W, dtype=torch.float32, device=T.device) if want_V else None
+    L.check(L.load().pbmc_build_input(L.ptr(T), L.ptr(xc), L.ptr(yc), L.ptr(ycc), L.ptr(members), L.ptr(inp), L.ptr(V), B,
+                                      H, W, L.stream_ptr(T.device)), "pbmc_build_input")
+    return inp, V
+
+
+def head(y_blocked, chan_sum, members, a_bound, head_kind, p_pred, want_uvmax=True):
+    B, _, H, W, _ = y_blocked.shape
+    dev = y_blocked.device
+    u = torch.empty(B, H, W, dtype=torch.float32, device=dev)
+    v = torch.empty_like(u)
+    p = torch.empty_like(u) if p_pred else None
+    uvmax = torch.zeros(B, dtype=torch.int32, device=dev) if want_uvmax else None
+    L.check(L.load().pbmc_head(L.ptr(y_blocked), L.ptr(chan_sum), L.ptr(members), float(a_bound), int(head_kind),
+                               int(bool(p_pred)), L.ptr(u), L.ptr(v), L.ptr(p), L.ptr(uvmax), B, H, W, L.stream_ptr(dev)),
+            "pbmc_head")
+    return u, v, p, uvmax
+
+
+def uvmax_reduce(u, v, batch_global=False):
+    B, H, W = u.shape
+    out = torch.zeros(B, dtype=torch.int32, device=u.device)
+    L.check(L.load().pbmc_uvmax(L.ptr(u), L.ptr(v), L.ptr(out), 0 if batch_global else 1, B, H, W, L.stream_ptr(u.device)),
+            "pbmc_uvmax")
+    return out
+
+
+def stencil_coefs(coord64, wall_lo, wall_hi):
+    """1-D cell coordinates (float64 CUDA tensor [n]) -> float32 [3, n] inverse spacings
+    (1/d_minus, 1/d_plus, 1/(0.5 d_plus + 0.5 d_minus)) with ADNet's forced wall values."""
+    _chk_cuda(coord64)
+    coord64 = coord64.contiguous().double()
+    n = coord64.numel()
+    out = torch.empty(3, n, dtype=torch.float32, device=coord64.device)
+    L.check(L.load().pbmc_stencil_coefs(L.ptr(coord64), n, float(wall_lo), float(wall_hi), L.ptr(out),
+                                        L.stream_ptr(coord64.device)), "pbmc_stencil_coefs")
+    return out
+
+
+def advect_diffuse(T, u, v, xcoef, ycoef, members, uvmax, dx_min, cn_max, per_member_dt=True, dt_fixed=0.0,
+                   want_uvmax_out=False, T_out=None, dt_out=None, uv_out=None):
+    """Fast separable-grid step.  xcoef [3,W], ycoef [3,H] from stencil_coefs.
+    Returns (T_out [B,H,W], dt [B] float64, uvmax_out|None)."""
+    _chk_cuda(T, u, v, xcoef, ycoef)
+    assert xcoef.shape == (3, T.shape[2]) and ycoef.shape == (3, T.shape[1])
+    B, H, W = T.shape
+    dev = T.device
+    T_out = torch.empty_like(T) if T_out is None else T_out
+    dt_out = torch.empty(B, dtype=torch.float64, device=dev) if dt_out is None else dt_out
+    if uv_out is None and want_uvmax_out:
+        uv_out = torch.zeros(B, dtype=torch.int32, device=dev)
+    L.check(L.load().pbmc_advect_diffuse(L.ptr(T), L.ptr(u), L.ptr(v), L.ptr(xcoef), L.ptr(ycoef), L.ptr(members), L.ptr(uvmax),
+                                         1 if per_member_dt else 0, float(dx_min), float(cn_max), float(dt_fixed),
+                                         L.ptr(T_out), L.ptr(uv_out), L.ptr(dt_out), B, H, W, L.stream_ptr(dev)),
+            "pbmc_advect_diffuse")
+    return T_out, dt_out, uv_out
+
+
+def advect_diffuse_fields(T, u, v, xc, yc, raq_field, members, uvmax, dx_min_dev, cn_max, per_member_dt=False,
+                          dt_fixed_dev=None):
+    """General form (coordinates as float64 fields, RaQ optionally a field; ADNet.forward semantics)."""
+    B, H, W = T.shape
+    assert xc.dtype == torch.float64 and yc.dtype == torch.float64
+    dev = T.device
+    T_out = torch.empty_like(T)
+    dt_out = torch.empty(B, dtype=torch.float64, device=dev)
+    stride = 0 if xc.dim() == 2 or xc.shape[0] == 1 else H * W
+    L.check(L.load().pbmc_advect_diffuse_fields(L.ptr(T), L.ptr(u), L.ptr(v), L.ptr(xc), L.ptr(yc), stride, L.ptr(raq_field),
+                                                L.ptr(members), L.ptr(uvmax), 1 if per_member_dt else 0,
+                                                L.ptr(dx_min_dev), float(cn_max), L.ptr(dt_fixed_dev), L.ptr(T_out),
+                                                L.ptr(dt_out), B, H, W, L.stream_ptr(dev)), "pbmc_advect_diffuse_fields")
+    return T_out, dt_out
+
+
+def clamp_T(T, core_cool=False):
+    B, H, W = T.shape
+    L.check(L.load().pbmc_clamp_T(L.ptr(T), int(bool(core_cool)), B, H, W, L.stream_ptr(T.device)), "pbmc_clamp_T")
+    return T
+
+
+def diagnostics(T):
+    """T [B,H,W] float32 -> (mean_T [B], profile [B,H]) float64 on device."""
+    B, H, W = T.shape
+    prof = torch.empty(B, H, dtype=torch.float64, device=T.device)
+    mean = torch.empty(B, dtype=torch.float64, device=T.device)
+    L.check(L.load().pbmc_diagnostics(L.ptr(T), L.ptr(prof), L.ptr(mean), B, H, W, L.stream_ptr(T.device)), "pbmc_diagnostics")
+    return mean, prof

@@ -1,0 +1,408 @@
+"""Drop-in modules for the surrogate time-stepping path (reference: pytorch_networks_convae.py).
+
+Same class names, constructor signatures, `state_dict` layout and call signatures as the
+reference's `FluidLayer` (:702-799), `BoundaryLearnedConvolution2D` (:802-1065),
+`NewFluidNet` (:1068-1388), `FluidNet` (:1392-1697), `ADNet` (:478-568) and `TS` (:266-475);
+the `forward` bodies enqueue hand-written sm_100a kernels through the C ABI (libpbmc.so).
+
+Differences a user can observe:
+  * CUDA only.  A CPU tensor / missing library raises -- there is no fallback path.
+  * Arithmetic is float32 (tensor-core variants selectable per network); inputs of any float
+    dtype are accepted and outputs come back in the input dtype, so `.double()` models and
+    float64 state (advect_wi_gaia.py:348,430,468) keep working.
+  * The grid size is taken from the input; the reference's hard-coded 128x506
+    (:414-417, :1222-1229) is not inherited.
+  * Inference only (the rollout runs under torch.no_grad(), advect_wi_gaia.py:589).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .engine import Grid, RolloutState, SurrogateEngine
+from .symmetric_layers_torch import SymmetricConv2d, conv_module_forward, full_weight
+
+_ACTS = {"selu": nn.SELU, "tanh": nn.Tanh, "elu": nn.ELU, "silu": nn.SiLU, "relu": nn.ReLU, "gelu": nn.GELU}
+
+
+def count_parameters(model):
+    """pytorch_networks_convae.py:105-115."""
+    return sum(p.numel() for p in model.parameters() if p.requires_grad)
+
+
+def _make_act(act_fn):
+    if act_fn == "sine":
+        raise NotImplementedError("act_fn='sine' is not part of the rollout path")
+    return _ACTS[act_fn]()
+
+
+def _sym_counts(c_o):
+    # pytorch_networks_convae.py:755-757
+    return {"h": int(c_o / 4) if c_o > 4 else int(c_o / 2), "v": 0, "hv": 0}
+
+
+def _require_gelu(mod):
+    if not isinstance(mod.act, nn.GELU):
+        raise NotImplementedError("the B200 path fuses exact-erf GELU (act_fn='gelu', advect_wi_gaia.py:247); "
+                                  f"{type(mod.act).__name__} is not implemented")
+
+
+class BoundaryLearnedConvolution2D(nn.Module):
+    """Nine bias-free 'valid' convolutions (interior, 4 edges, 4 corners) stitched together
+    plus a learnable bias (reference :802-1065).  NB the reference places the strip computed
+    from the LAST input rows at output row 0 (`cat([bottom, x, top], dim=2)`, :1060)."""
+
+    _REGIONS = ("conv", "conv_top_left", "conv_top_right", "conv_bottom_left", "conv_bottom_right", "conv_top",
+                "conv_bottom", "conv_left", "conv_right")
+
+    def __init__(self, c_i, c_o, k, stride=1, use_symm=False):
+        super().__init__()
+        self.c_i, self.c_o, self.k = c_i, c_o, k
+        for name in self._REGIONS:
+            if use_symm:
+                conv = SymmetricConv2d(c_i, c_o, k, bias=False, padding="valid", symmetry=_sym_counts(c_o))
+            else:
+                conv = nn.Conv2d(in_channels=c_i, out_channels=c_o, kernel_size=k, padding="valid", bias=False)
+            setattr(self, name, conv)
+        self.learnable_bias = nn.Parameter(torch.zeros(1, c_o, 1, 1))
+
+    def forward(self, x, bc_x=1, bc_y=1):
+        k = self.k
+        pad_x = k + 1 + (bc_x - 1) if k == 5 else k + (bc_x - 1)
+        pad_y = k + 1 + (bc_y - 1) if k == 5 else k + (bc_y - 1)
+        run = lambda name, t: conv_module_forward(getattr(self, name), t.contiguous())
+        first_r, last_r = x[:, :, :pad_y], x[:, :, -pad_y:]
+        from_first = torch.cat([run("conv_top_left", first_r[..., :pad_x]), run("conv_top", first_r),
+                                run("conv_top_right", first_r[..., -pad_x:])], 3)
+        from_last = torch.cat([run("conv_bottom_left", last_r[..., :pad_x]), run("conv_bottom", last_r),
+                               run("conv_bottom_right", last_r[..., -pad_x:])], 3)
+        mid = torch.cat([run("conv_left", x[..., :pad_x]), run("conv", x), run("conv_right", x[..., -pad_x:])], 3)
+        out = torch.cat([from_last, mid, from_first], 2)  # row order as in the reference (:1060)
+        return out + self.learnable_bias.to(out.dtype)
+
+
+class FluidLayer(nn.Module):
+    """conv -> GroupNorm(4 channels per group) -> activation -> Dropout (reference :702-799)."""
+
+    def __init__(self, c_i: int, c_o: int, act_fn: str = "selu", r_p="zeros", use_symm=False, dilation=1, f=3,
+                 drop_rate=0.0):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        self.r_p = "constant" if r_p == "zeros" else r_p
+        self.act = _make_act(act_fn)
+        self.dropout = torch.nn.Dropout(drop_rate)
+        if r_p == "learned":
+            self.layers.append(BoundaryLearnedConvolution2D(c_i, c_o, k=f, use_symm=use_symm))
+        elif use_symm:
+            self.layers.append(SymmetricConv2d(c_i, c_o, kernel_size=f, padding="same", dilation=dilation,
+                                               padding_mode=r_p, symmetry=_sym_counts(c_o)))
+        else:
+            self.layers.append(nn.Conv2d(c_i, c_o, kernel_size=f, padding="same", dilation=dilation, padding_mode=r_p))
+        self.layers.append(torch.nn.GroupNorm(int(c_o / min(4, c_o)), c_o))
+
+    def forward(self, inputs, bc_x=1, bc_y=1):
+        _require_gelu(self)
+        if self.dropout.p != 0.0 and self.training:
+            raise NotImplementedError("dropout>0 in training mode is outside the inference path")
+        conv, gn = self.layers[0], self.layers[1]
+        c_o = gn.num_channels
+        if c_o > 4 and c_o % 4 != 0:
+            raise NotImplementedError("GroupNorm groups must coincide with 4-channel blocks (c_o % 4 == 0)")
+        dev = inputs.device
+        if self.r_p == "learned":
+            y = conv(inputs, bc_x=bc_x, bc_y=bc_y)
+            yb = ops.pack_nchw(y)
+            # statistics of the stitched tensor: one more pass through the conv-free reduction
+            stats = _stats_of_blocked(yb, c_o)
+        else:
+            from .symmetric_layers_torch import _check_conv_supported
+            _check_conv_supported(conv)
+            k = conv.kernel_size[0]
+            w = full_weight(conv).detach().to(dev, torch.float32)
+            wpk = ops.pack_conv_weight(w, [conv.in_channels])
+            bias = ops.pad_vec(conv.bias, c_o, dev)
+            yb, stats, _ = ops.conv_fwd([ops.Source(ops.pack_nchw(inputs))], wpk, bias, c_o, k, conv.padding_mode,
+                                        want_stats=True, impl="ffma")
+        src = ops.Source(yb, L.XFORM_GN_GELU, stats, ops.pad_vec(gn.weight, c_o, dev, 1.0), ops.pad_vec(gn.bias, c_o, dev),
+                         channels_per_group=min(4, c_o))
+        return ops.finalize_nchw(src, c_o).to(inputs.dtype)
+
+
+def _stats_of_blocked(yb, c_o):
+    """(sum, sum^2) per (sample, 4-channel block) of a blocked tensor, float64 (host-side helper
+    for the stitched learned-boundary output; tiny reduction, stays on the device)."""
+    y64 = yb.double()
+    return torch.stack([y64.sum(dim=(2, 3, 4)), (y64 * y64).sum(dim=(2, 3, 4))], -1).contiguous()
+
+
+class _FluidNetBase(nn.Module):
+    """Shared constructor of NewFluidNet / FluidNet (reference :1123-1313 / :1447-1637)."""
+
+    _HEAD_PADDING_CURL = (1, 1)
+
+    def __init__(self, levels: int, c_i: int, c_h: int, c_o: int, device, act_fn: str = "selu", r_p="zeros",
+                 loss_type="mae", use_symm=False, dilation=1, a_bound=4.0, use_cosine=False, repeats=3, use_skip=False,
+                 f=3, p_pred=True, spectral_conv=False, blurr=False, drop_rate=0.0, factor=2):
+        super().__init__()
+        if spectral_conv:
+            raise NotImplementedError("spectral_conv=True is outside the rollout path (advect_wi_gaia.py:253)")
+        if blurr:
+            raise NotImplementedError("blurr=True is outside the rollout path (advect_wi_gaia.py:255)")
+        if factor != 2:
+            raise NotImplementedError("pooling factor 2 is the only one used (advect_wi_gaia.py:307)")
+        self.conv = nn.ModuleList()
+        self.gn = nn.ModuleList()
+        self.unpool = nn.ModuleList()
+        self.levels, self.loss_type, self.a_bound = levels, loss_type, a_bound
+        self.use_cosine, self.repeats, self.use_skip, self.p_pred = use_cosine, repeats, use_skip, p_pred
+        self.c_h, self.c_i, self.c_o = c_h, c_i, c_o
+        self.blurrer = None
+        self.r_p = "constant" if r_p == "zeros" else r_p
+        self.act = _make_act(act_fn)
+        self.conv.append(FluidLayer(c_i, c_h, act_fn, r_p, use_symm, dilation, f=f, drop_rate=drop_rate))
+        self.pool = nn.AvgPool2d((factor, factor), stride=factor)
+        for _ in range(1, levels):
+            # kept for structural parity; the kernels up-sample to the INPUT's size, whatever it is
+            self.unpool.append(nn.Upsample(size=(128, 506), mode="bicubic"))
+        self.convs = nn.ModuleList()
+        for _l in range(levels):
+            self.convs.append(nn.ModuleList(
+                [FluidLayer(c_h, c_h, act_fn, r_p, use_symm, dilation, f=f, drop_rate=drop_rate) for _ in range(repeats)]))
+        head_pad = self._HEAD_PADDING_CURL if loss_type == "curl" else (1, 1)
+        if self.r_p != "learned":
+            self.conv.append(nn.Conv2d(c_h * levels + c_i, c_h, kernel_size=3, padding=head_pad, dilation=dilation,
+                                       padding_mode=r_p, stride=1))
+        else:
+            self.conv.append(BoundaryLearnedConvolution2D(c_h * levels + c_i, c_h, k=f, use_symm=use_symm))
+        self.gn.append(torch.nn.GroupNorm(int(c_h / 4), c_h))
+        for co in (c_h, c_o):
+            if self.r_p != "learned":
+                self.conv.append(nn.Conv2d(c_h, co, kernel_size=3, padding=(1, 1), dilation=1, padding_mode=r_p, stride=1))
+            else:
+                self.conv.append(BoundaryLearnedConvolution2D(c_h, co, k=f, use_symm=use_symm))
+        self._engines = {}
+        self.conv_impl = "auto"  # "auto" | "ffma" | "umma_3xtf32" | "umma_bf16"
+
+    # nn.Module bookkeeping: engines hold device buffers, never parameters
+    def _engine(self, device) -> SurrogateEngine:
+        key = str(device)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = self._engines[key] = SurrogateEngine(self, device)
+        if eng.conv_impl != self.conv_impl:
+            eng.set_conv_impl(self.conv_impl)
+        return eng
+
+    def __getstate__(self):  # engines are not picklable / deep-copyable
+        d = dict(self.__dict__)
+        d["_engines"] = {}
+        return d
+
+    def _r_p_name(self):
+        return "zeros" if self.r_p == "constant" else self.r_p
+
+    def _check_fused(self, inputs):
+        _require_gelu(self)
+        if not inputs.is_cuda:
+            raise L.PbmcError("NewFluidNet/FluidNet run on CUDA only: there is no CPU implementation of this path")
+        if inputs.dim() != 4 or inputs.shape[1] != self.c_i:
+            raise ValueError(f"expected inputs [B,{self.c_i},H,W], got {tuple(inputs.shape)}")
+        if self.training and any(m.dropout.p != 0.0 for m in self.modules() if isinstance(m, FluidLayer)):
+            raise NotImplementedError("dropout>0 in training mode is outside the inference path")
+
+
+class NewFluidNet(_FluidNetBase):
+    """Multi-level conv surrogate T-features -> (u, v, p) (reference :1068-1388)."""
+
+    def forward(self, inputs):
+        self._check_fused(inputs)
+        if self.r_p == "learned":
+            return _forward_learned(self, inputs, head_bc=1, wall_bcs=True)
+        eng = self._engine(inputs.device)
+        eng.net_module = self
+        u, v, p, _ = eng.forward_blocked(ops.pack_nchw(inputs))
+        return _shape_outputs(self, u, v, p, inputs.dtype)
+
+
+def _shape_outputs(net, u, v, p, dtype):
+    u, v = u.to(dtype), v.to(dtype)
+    if p is not None:
+        p = p.to(dtype)
+        if net.loss_type != "curl":
+            p = p[:, None]  # reference returns y[:, 2:3] for the mae head (:1349)
+    return u, v, p
+
+
+class FluidNet(_FluidNetBase):
+    """Variant whose head conv enlarges the field by one ring and which returns the raw curl
+    without wall BCs (reference :1392-1697).  Like the reference it only runs with
+    r_p='learned' and loss_type='curl' (:1659-1661)."""
+
+    _HEAD_PADDING_CURL = (2, 2)
+
+    def forward(self, inputs):
+        self._check_fused(inputs)
+        if self.r_p != "learned" or self.loss_type != "curl":
+            raise TypeError("FluidNet.forward needs r_p='learned' and loss_type='curl' (the reference skips conv[1] "
+                            "otherwise and fails, pytorch_networks_convae.py:1659-1661)")
+        return _forward_learned(self, inputs, head_bc=2, wall_bcs=False)
+
+
+def _forward_learned(net, inputs, head_bc, wall_bcs):
+    """Learned-boundary networks: every layer runs through the
+    module-level kernels (9-region conv, fused GN/GELU, pool, bicubic); not yet one DAG."""
+    B, _, H, W = inputs.shape
+    dev = inputs.device
+    x_in = net.conv[0](inputs)
+    feats = []
+    pooled = ops.pack_nchw(x_in)
+    for l in range(net.levels):
+        if l > 0:
+            pooled = ops.avgpool2(ops.Source(pooled))
+        y1 = ops.unpack_nchw(pooled, net.c_h)
+        for r in range(net.repeats):
+            y1 = net.convs[l][r](y1)
+        if l > 0:
+            y1 = ops.unpack_nchw(ops.bicubic_up(ops.Source(ops.pack_nchw(y1)), H, W), net.c_h)
+        feats.append(y1.float())
+    y = torch.cat(feats + [inputs.float()], 1)
+    y = net.conv[1](y, bc_x=head_bc, bc_y=head_bc)
+    c_h = net.c_h
+    yb = ops.pack_nchw(y)
+    src = ops.Source(yb, L.XFORM_GN_GELU, _stats_of_blocked(yb, c_h), ops.pad_vec(net.gn[0].weight, c_h, dev, 1.0),
+                     ops.pad_vec(net.gn[0].bias, c_h, dev))
+    y = ops.finalize_nchw(src, c_h)
+    y = ops.finalize_nchw(ops.Source(ops.pack_nchw(net.conv[2](y)), L.XFORM_GELU), c_h)
+    y = net.conv[3](y)
+    Hh, Wh = y.shape[-2:]
+    yb = ops.pack_nchw(y)
+    csum = yb.double().sum(dim=(2, 3)).reshape(B, -1).contiguous()
+    if wall_bcs:
+        u, v, p, _ = ops.head(yb, csum, None, net.a_bound, L.HEAD_CURL if net.loss_type == "curl" else L.HEAD_MAE,
+                              net.p_pred, want_uvmax=False)
+        return _shape_outputs(net, u, v, p, inputs.dtype)
+    # FluidNet: plain central differences of the enlarged stream function, no BCs (:1694-1697)
+    ym = y - y.mean(dim=(2, 3), keepdim=True)
+    a = ym[:, 0] * net.a_bound
+    p = ym[:, 1] if net.p_pred else None
+    u = 0.5 * (a[:, 2:, 1:-1] - a[:, :-2, 1:-1])
+    v = -0.5 * (a[:, 1:-1, 2:] - a[:, 1:-1, :-2])
+    return u.to(inputs.dtype), v.to(inputs.dtype), (p.to(inputs.dtype) if p is not None else None)
+
+
+class ADNet(nn.Module):
+    """Explicit upwind-advection / central-diffusion update with the CFL time step
+    (reference :478-568).  `forward(inputs[B,6,H,W], dt=None, T_prev=None) -> (T[B,1,H,W], dt)`;
+    channels = (u, v, T, RaQ, x, y).  As in the reference, dt is ONE scalar over the batch (:556)
+    and the wall coordinates of `inputs` are overwritten in place (:532-535)."""
+
+    def __init__(self, device, r_p="zeros", CN_max=0.1):
+        super().__init__()
+        self.device = device
+        self.CN_max = CN_max
+
+    def forward(self, inputs, dt=None, T_prev=None):
+        if not inputs.is_cuda:
+            raise L.PbmcError("ADNet runs on CUDA only: there is no CPU implementation of this path")
+        B, _, H, W = inputs.shape
+        dtype = inputs.dtype
+        inputs[:, 4, :, 0] = 0.0
+        inputs[:, 4, :, -1] = 4.0
+        inputs[:, 5, 0, :] = 0.0
+        inputs[:, 5, -1, :] = 1.0
+        f32 = lambda t: t.contiguous().float()
+        u, v = f32(inputs[:, 0]), f32(inputs[:, 1])
+        T = f32(inputs[:, 2] if T_prev is None else T_prev.reshape(B, H, W))
+        raq = f32(inputs[:, 3])
+        xc, yc = inputs[:, 4].contiguous().double(), inputs[:, 5].contiguous().double()
+        dx_min = (inputs[:, 4, 1:-1, 1:-1] - inputs[:, 4, 1:-1, :-2]).double().amin().reshape(1).contiguous()  # :555
+        dt_dev = None
+        uvmax = None
+        if dt is None:
+            uvmax = ops.uvmax_reduce(u, v, batch_global=True)
+        else:
+            dt_dev = torch.as_tensor(dt, dtype=torch.float64, device=inputs.device).reshape(1).contiguous()
+        T_out, dt_out = ops.advect_diffuse_fields(T, u, v, xc, yc, raq, None, uvmax, dx_min, self.CN_max,
+                                                  per_member_dt=False, dt_fixed_dev=dt_dev)
+        dt_ret = dt if dt is not None else dt_out[0].to(dtype)
+        return T_out[:, None].to(dtype), dt_ret
+
+
+class TS(nn.Module):
+    """Evaluation wrapper that advances T by `ts` surrogate steps (reference :266-475).
+    Same constructor and 15-argument `forward`; returns `(x, dts, u, v, p, V)` exactly like the
+    reference: `x[i]` / `dts[i]` for every step, and the last step's fields."""
+
+    def __init__(self, stokes, ad, device, ts=8, advection_scheme=2, scale=True, p_pred=True, net="fluidnet"):
+        super().__init__()
+        self.stokes, self.ad, self.ts, self.device = stokes, ad, ts, device
+        self.advection_scheme, self.scale, self.p_pred, self.net = advection_scheme, scale, p_pred, net
+        self._grid_key, self._grid = None, None
+
+    def _get_grid(self, xc, yc, ycc, dev):
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in (xc, yc, ycc))
+        if key != self._grid_key:
+            self._grid, self._grid_key = Grid(xc, yc, ycc, dev), key
+        return self._grid
+
+    @torch.no_grad()
+    def forward(self, T_prev, sdf, sdf2, ycc, raq_nd, fkt_nd, fkp_nd, raq, fkt, fkp, xc, yc, u_prev=None, v_prev=None,
+                dt=None):
+        if self.net == "unet":
+            raise NotImplementedError("net='unet' (SURVEY.md section 8f N4) is outside the accelerated path")
+        if self.net not in ("newfluidnet", "fluidnet"):
+            raise ValueError(self.net)
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise L.PbmcError("TS runs on CUDA only: there is no CPU implementation of this path")
+        stokes = self.stokes
+        dtype = T_prev.dtype
+        B = T_prev.shape[0] if T_prev.dim() == 4 else 1
+        H, W = T_prev.shape[-2:]
+        grid = self._get_grid(xc, yc, ycc, dev)
+        fl = lambda t: float(t)
+        members = ops.make_members([(fl(raq), fl(fkt), fl(fkp))] * B, dev, nd_override=[(fl(raq_nd), fl(fkt_nd), fl(fkp_nd))] * B)
+        T0 = T_prev.to(dev)
+        x, dts = {0: T0}, {}
+        advect = self.ad is not None and self.net == "newfluidnet"
+        fused = isinstance(stokes, NewFluidNet) and stokes.r_p != "learned" and grid.separable
+        cn_max = self.ad.CN_max if advect else 0.0
+        n = self.ts
+        if fused and advect:
+            # whole loop device-resident: one C call enqueues ts steps (batch-global dt like ADNet, :556)
+            eng = stokes._engine(dev)
+            stokes._check_fused(T0.new_empty(1, stokes.c_i, 1, 1))
+            st = RolloutState(grid, members, B, n + 1, n, cn_max, per_member_dt=False, p_pred=stokes.p_pred, device=dev)
+            st.T_seq[0].copy_(T0.reshape(B, H, W))
+            eng.rollout(st, 1, n)
+            for i in range(1, n + 1):
+                x[i] = st.T_seq[i][:, None].to(dtype)
+                dts[i] = st.dt_seq[i - 1, 0].to(dtype)
+            u, v, p, V = st.u, st.v, st.p, st.V
+        else:
+            Tc = T0.reshape(B, H, W).float().contiguous()
+            u = v = p = V = None
+            for i in range(1, n + 1):
+                inp, V = ops.build_input(Tc, grid.xc, grid.yc, grid.ycc, members, want_V=True)
+                uu, vv, pp = stokes(ops.unpack_nchw(inp, 7))
+                s = members[:, 6].reshape(B, 1, 1)
+                u, v, p = (uu.float() * s).contiguous(), (vv.float() * s).contiguous(), pp
+                if advect:
+                    uvmax = ops.uvmax_reduce(u, v, batch_global=True)
+                    if grid.separable:
+                        Tc, dt_i, _ = ops.advect_diffuse(Tc, u, v, grid.xcoef, grid.ycoef, members, uvmax, grid.dx_min,
+                                                         cn_max, per_member_dt=False)
+                    else:
+                        Tc, dt_i = ops.advect_diffuse_fields(Tc, u, v, grid.xc64, grid.yc64, None, members, uvmax,
+                                                             grid.dx_min_dev, cn_max, per_member_dt=False)
+                    x[i] = Tc[:, None].to(dtype)
+                    dts[i] = dt_i[0].to(dtype)
+        u = u.reshape(-1, 1, u.shape[-2], u.shape[-1]).to(dtype)
+        v = v.reshape(-1, 1, v.shape[-2], v.shape[-1]).to(dtype)
+        if self.p_pred and p is not None:
+            p = p.reshape(-1, 1, p.shape[-2], p.shape[-1]).to(dtype)
+        elif p is not None:
+            p = p.to(dtype)
+        return x, dts, u, v, p, V[:, None].to(dtype)

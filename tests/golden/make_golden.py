@@ -282,3 +282,19 @@ if __name__ == "__main__":
     golden_rollout("roll128", RN.NetSpec(), 128, 128, keep=(1, 10, 100), n_steps=100)
     golden_rollout("roll64x96", RN.NetSpec(levels=4), 64, 96, keep=(1, 10), n_steps=10)
     golden_ts_unmodified()
+
+
+def golden_mlp_weights():
+    """The reference's MLP asset (numpy arrays only) re-saved as .npz so calc_mlp_profile can be
+    checked on machines without /root/reference."""
+    import pickle
+
+    mlp = pickle.load(open(os.path.join(REF, "mlp_[128, 128, 128, 128, 128].pkl"), "rb"))
+    out = {}
+    for i, (W, b) in enumerate(mlp):
+        out[f"W{i}"], out[f"b{i}"] = np.asarray(W), np.asarray(b)
+    np.savez_compressed(os.path.join(HERE, "mlp_profile_weights.npz"), **out)
+
+
+if __name__ == "__main__":
+    golden_mlp_weights()

@@ -1,0 +1,232 @@
+"""Network / rollout parity on the GPU through the drop-in module API (which calls the C ABI).
+
+Tolerance for one float32 forward ("parity metric caveat"): the reference's
+OWN float32 forward differs from its float64 forward by `ref_fp32_noise` (stored with the
+golden vectors; 3.7e-5 / 7.2e-5 / 1.4e-6 rel-L2 for u / v / p at 128^2), so the bound is
+    rel_L2(new_fp32, ref_fp64) <= max(1e-5, 1.5 * rel_L2(ref_fp32, ref_fp64))     per field.
+Rollout diagnostics (mean-T, T(y) profile) must agree within 1e-4 after 100 steps (north_star).
+"""
+import numpy as np
+import pytest
+import torch
+
+import pbml_mantle_convection_b200 as P
+from oracle import ref_numpy as RN
+from oracle import ref_torch as RT
+from pbml_mantle_convection_b200 import _lib as L
+from tests._util import VARIANTS, load, load_weights, relerr, spec_from_variant, split_weights
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+PARAMS = (6.79733173, 475523342.0, 2.58574662)
+
+
+def make_net(spec, weights, impl="auto", cls=P.NewFluidNet):
+    net = cls(spec.levels, spec.c_i, spec.c_h, spec.c_o, DEV, act_fn="gelu", r_p=spec.r_p, loss_type=spec.loss_type,
+              use_symm=spec.use_symm, a_bound=spec.a_bound, repeats=spec.repeats, f=spec.f, p_pred=spec.p_pred).double()
+    net.load_state_dict({k: torch.tensor(v) for k, v in weights.items()})
+    net.conv_impl = impl
+    return net.to(DEV).eval()
+
+
+def fwd_bound(noise):
+    return np.maximum(1e-5, 1.5 * np.asarray(noise))
+
+
+@pytest.mark.parametrize("tag", VARIANTS)
+def test_variants_forward(tag):
+    """zeros / reflect / replicate padding, symmetric and plain filters, odd sizes, mae head, k=5."""
+    g = load(tag)
+    spec = spec_from_variant(g)
+    net = make_net(spec, split_weights(g), impl="ffma")
+    inp = torch.tensor(g["inp"], device=DEV)  # float64 in, float64 out (module is .double() like the reference)
+    u, v, p = net(inp)
+    assert u.dtype == torch.float64 and tuple(u.shape) == g["u"].shape
+    assert relerr(u.cpu().numpy(), g["u"]) < 3e-4 and relerr(v.cpu().numpy(), g["v"]) < 3e-4
+    if "p" in g:
+        assert tuple(p.shape) == g["p"].shape and relerr(p.cpu().numpy(), g["p"]) < 3e-5
+    else:
+        assert p is None
+
+
+def test_forward_128_against_reference_golden():
+    g = load("roll128")
+    spec = RN.NetSpec()
+    net = make_net(spec, load_weights("roll128"), impl="ffma")
+    inp, _ = RN.build_input(g["T0"][None, None], g["xc"], g["yc"], g["yc"], *PARAMS)
+    u, v, p = net(torch.tensor(inp, device=DEV))
+    s = RN.velocity_scaler(*PARAMS)
+    errs = np.array([relerr(u[0].cpu().numpy() * s, g["u1"]), relerr(v[0].cpu().numpy() * s, g["v1"]),
+                     relerr(p[0].cpu().numpy(), g["p1"])])
+    print("rel-L2 (u,v,p) new fp32 vs reference fp64:", errs, " reference fp32 noise:", g["ref_fp32_noise"])
+    assert np.all(errs <= fwd_bound(g["ref_fp32_noise"])), (errs, g["ref_fp32_noise"])
+
+
+def _ts_call(ts, T0, xc, yc, params=PARAMS, dtype=torch.float64):
+    H, W = T0.shape[-2:]
+    t = lambda a: torch.tensor(a, dtype=dtype)
+    nd = RN.nondim_params(*params)
+    return ts(t(T0).view(-1, 1, H, W), None, None, t(yc).view(1, 1, H, W), t(nd[0]), t(nd[1]), t(nd[2]), t(params[0]),
+              t(params[1]), t(params[2]), t(xc).view(1, 1, H, W), t(yc).view(1, 1, H, W))
+
+
+def test_TS_dropin_unmodified_reference_128x506():
+    """Same call as advect_wi_gaia.py:590-593 (CPU float64 tensors in), against the UNMODIFIED reference TS(ts=5)."""
+    g = load("ts128x506")
+    net = make_net(RN.NetSpec(), load_weights("ts128x506"), impl="ffma")
+    ts = P.TS(net, P.ADNet(DEV, CN_max=0.99), DEV, ts=5, scale=True, p_pred=True, net="newfluidnet")
+    x, dts, u, v, p, V = _ts_call(ts, g["T0"], g["xc"], g["yc"])
+    assert sorted(x.keys()) == [0, 1, 2, 3, 4, 5] and sorted(dts.keys()) == [1, 2, 3, 4, 5]
+    assert tuple(x[5].shape) == (1, 1, 128, 506) and x[5].dtype == torch.float64 and dts[1].dim() == 0
+    assert tuple(u.shape) == (1, 1, 128, 506) and tuple(p.shape) == (1, 1, 128, 506) and tuple(V.shape) == (1, 1, 128, 506)
+    assert np.abs(x[1][0, 0].cpu().numpy() - g["T1"]).max() < 2e-5
+    assert np.abs(x[5][0, 0].cpu().numpy() - g["T5"]).max() < 5e-5
+    got_dts = np.array([float(dts[i]) for i in range(1, 6)])
+    assert np.allclose(got_dts, g["dts"], rtol=3e-4)
+    assert relerr(u[0, 0].cpu().numpy(), g["u5"]) < 3e-4 and relerr(p[0, 0].cpu().numpy(), g["p5"]) < 3e-5
+    assert np.abs(V[0, 0].cpu().numpy() - g["V5"]).max() < 2e-6
+
+
+def test_rollout_100_steps_diagnostics():
+    """BASELINE config 1 (128x128, 100 steps): T fields and mean-T / profile diagnostics vs the reference."""
+    g = load("roll128")
+    net = make_net(RN.NetSpec(), load_weights("roll128"), impl="ffma")
+    ens = P.EnsembleRollout(net, 128, 128, [PARAMS], DEV, cn_max=0.99)
+    ens.set_T(g["T0"][None])
+    snaps = {}
+    done = 0
+    for upto in (1, 10, 100):
+        ens.step(upto - done)
+        done = upto
+        snaps[upto] = ens.T[0].cpu().numpy().astype(np.float64)
+    for i, tol in ((1, 2e-5), (10, 5e-5), (100, 3e-4)):
+        assert np.abs(snaps[i] - g[f"T{i}"]).max() < tol, i
+    mean, prof, dprof = ens.diagnostics()
+    assert abs(mean[0].item() - float(g["meanT"])) < 1e-4
+    assert np.abs(prof[0].cpu().numpy() - g["Tprof"]).max() < 1e-4
+    scale = np.abs(g["dTprof"]).max()
+    assert np.abs(dprof[0].cpu().numpy() - g["dTprof"]).max() < 1e-3 * scale
+    assert abs(ens.time[0].item() - g["dts"].sum()) < 3e-4 * g["dts"].sum()
+
+
+def test_graph_replay_equals_eager():
+    spec = RN.NetSpec(levels=4)
+    w = load_weights("roll64x96")
+    g = load("roll64x96")
+    net = make_net(spec, w, impl="ffma")
+    outs = []
+    for mode in ("eager", "graph2", "graph5"):
+        ens = P.EnsembleRollout(net, 64, 96, [PARAMS], DEV)
+        ens.set_T(g["T0"][None])
+        if mode == "eager":
+            ens.step(10)
+        else:
+            ens.run(10, steps_per_graph=int(mode[5:]))
+        outs.append((ens.T.clone(), ens.time.clone()))
+    assert np.abs(outs[0][0].cpu().numpy()[0] - g["T10"]).max() < 5e-5
+    for T, t in outs[1:]:
+        # identical kernels and order; only the GroupNorm atomics may reorder (double) => ~1e-7
+        assert (T - outs[0][0]).abs().max().item() < 2e-6
+        assert abs(t[0].item() - outs[0][1][0].item()) < 1e-6 * outs[0][1][0].item()
+
+
+def test_ensemble_members_are_independent():
+    """B members with different (Ra, gamma, beta, T0) == B separate B=1 rollouts (per-member dt)."""
+    spec = RN.NetSpec(levels=4)
+    net = make_net(spec, load_weights("roll64x96"), impl="ffma")
+    prm = [PARAMS, (0.9, 3.0e6, 1.5), (9.1, 5.0e9, 60.0)]
+    H, W = 64, 96
+    T0 = np.stack([RN.synthetic_T0(H, W, seed=1 + m) for m in range(3)])
+    ens = P.EnsembleRollout(net, H, W, prm, DEV)
+    ens.set_T(T0)
+    ens.step(4)
+    for m in range(3):
+        one = P.EnsembleRollout(net, H, W, [prm[m]], DEV)
+        one.set_T(T0[m:m + 1])
+        one.step(4)
+        assert (one.T[0] - ens.T[m]).abs().max().item() < 2e-6
+        assert abs(one.time[0].item() - ens.time[m].item()) <= 1e-6 * one.time[0].item()
+    # and against the float64 oracle for one non-default member
+    W64 = RT.prepare_weights(load_weights("roll64x96"), spec)
+    xc, yc = RN.synthetic_grid(H, W)
+    Tr, dts, *_ = RT.rollout(W64, spec, torch.tensor(T0[1])[None, None], torch.tensor(xc), torch.tensor(yc), *prm[1], 4)
+    assert np.abs(ens.T[1].cpu().numpy() - Tr[0, 0].numpy()).max() < 5e-5
+    assert abs(ens.time[1].item() - sum(dts)) < 3e-4 * sum(dts)
+
+
+def test_full_size_512_against_cpu_port():
+    """BASELINE config 2 grid (512x512): one forward + 3 steps against the ATen-CPU float64 port."""
+    spec = RN.NetSpec()
+    w = load_weights("roll128")
+    net = make_net(spec, w, impl="ffma")
+    H = W = 512
+    xc, yc = RN.synthetic_grid(H, W)
+    T0 = RN.synthetic_T0(H, W, seed=1)
+    W64 = RT.prepare_weights(w, spec)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    Tr, dts, ur, vr, pr, Vr, _ = RT.rollout(W64, spec, torch.tensor(T0)[None, None], torch.tensor(xc), torch.tensor(yc),
+                                            *PARAMS, 3)
+    ens = P.EnsembleRollout(net, H, W, [PARAMS], DEV)
+    ens.set_T(T0[None])
+    ens.run(3)
+    u, v, p, V = ens.fields()
+    assert relerr(u[0].cpu().numpy(), ur[0].numpy()) < 3e-4 and relerr(v[0].cpu().numpy(), vr[0].numpy()) < 3e-4
+    assert relerr(p[0].cpu().numpy(), pr[0].numpy()) < 3e-5
+    assert np.abs(ens.T[0].cpu().numpy() - Tr[0, 0].numpy()).max() < 5e-5
+    assert abs(ens.time[0].item() - sum(dts)) < 3e-4 * sum(dts)
+
+
+def test_module_level_layers():
+    """Stand-alone FluidLayer / SymmetricConv2d / BoundaryLearnedConvolution2D / ADNet forwards."""
+    g = load("ops")
+    for tag, k, ci, co, symm in (("blc3", 3, 5, 8, False), ("blc5", 5, 4, 8, False), ("blc3s", 3, 6, 16, True)):
+        m = P.BoundaryLearnedConvolution2D(ci, co, k, use_symm=symm).double()
+        m.load_state_dict({kk: torch.tensor(v) for kk, v in split_weights(g, tag + "_w::").items()})
+        m = m.to(DEV)
+        y = m(torch.tensor(g[tag + "_x"], device=DEV))
+        assert tuple(y.shape) == g[tag + "_y"].shape and relerr(y.cpu().numpy(), g[tag + "_y"]) < 3e-6
+        if tag == "blc3":
+            y2 = m(torch.tensor(g[tag + "_x"], device=DEV), bc_x=2, bc_y=2)
+            assert tuple(y2.shape) == g["blc3_y_bc2"].shape and relerr(y2.cpu().numpy(), g["blc3_y_bc2"]) < 3e-6
+    # ADNet drop-in: inputs [B,6,H,W] float64, batch-global dt, in-place wall coordinates
+    u, v, T = g["ad_u"], g["ad_v"], g["ad_T"]
+    B, _, H, W = u.shape
+    xc = np.broadcast_to(g["ad_xc"], (B, 1, H, W))
+    yc = np.broadcast_to(g["ad_yc"], (B, 1, H, W))
+    inp = torch.tensor(np.concatenate([u, v, T, np.full_like(u, float(g["ad_raq"])), xc, yc], 1), device=DEV)
+    ad = P.ADNet(DEV, CN_max=0.99)
+    Tn, dt = ad(inp)
+    assert tuple(Tn.shape) == (B, 1, H, W) and Tn.dtype == torch.float64
+    assert abs(float(dt) - float(g["ad_dt"])) < 1e-6 * float(g["ad_dt"])
+    assert np.abs(Tn.cpu().numpy() - g["ad_Tn"]).max() < 2e-5
+    assert inp[0, 4, 3, -1].item() == 4.0 and inp[0, 5, -1, 3].item() == 1.0  # reference side effect, :532-535
+    Tn2, dt2 = ad(inp, dt=torch.tensor(1e-4, dtype=torch.float64))
+    assert np.abs(Tn2.cpu().numpy() - g["ad_Tn_fixed_dt"]).max() < 2e-4
+    # FluidLayer stand-alone == conv + GN + GELU (numpy oracle)
+    torch.manual_seed(1)
+    fl = P.FluidLayer(7, 16, "gelu", "replicate", True, 1, f=3).double().to(DEV)
+    x = torch.randn(2, 7, 18, 27, dtype=torch.float64, device=DEV)
+    sd = {k: t.detach().cpu().numpy() for k, t in fl.state_dict().items()}
+    ref = RN.fluid_layer(x.cpu().numpy(), sd, "", 16, RN.NetSpec())
+    assert relerr(fl(x).cpu().numpy(), ref) < 5e-6
+
+
+def test_learned_boundary_network_runs_and_matches_oracle_layers():
+    """SURVEY.md section 8f N1 (secondary config), small: learned 9-region convs, k=5, c_o=1, through NewFluidNet."""
+    torch.manual_seed(2)
+    net = P.NewFluidNet(2, 7, 8, 1, DEV, act_fn="gelu", r_p="learned", loss_type="curl", use_symm=False, a_bound=10,
+                        repeats=1, f=5, p_pred=False).double().to(DEV).eval()
+    x = torch.randn(1, 7, 24, 32, dtype=torch.float64, device=DEV)
+    u, v, p = net(x)
+    assert p is None and tuple(u.shape) == (1, 24, 32) and torch.isfinite(u).all() and torch.isfinite(v).all()
+    # first layer against the numpy oracle of the 9-region conv + GN + GELU
+    sd = {k: t.detach().cpu().numpy() for k, t in net.state_dict().items()}
+    y = RN.boundary_learned_conv(x.cpu().numpy(), sd, "conv.0.layers.0.", 5, 8)
+    ref = RN.gelu(RN.group_norm(y, sd["conv.0.layers.1.weight"], sd["conv.0.layers.1.bias"], 2))
+    assert relerr(net.conv[0](x).cpu().numpy(), ref) < 5e-6
+
+
+def test_no_silent_fallback_on_gpu_box():
+    with pytest.raises(L.PbmcError):
+        P.NewFluidNet(2, 7, 16, 2, DEV, act_fn="gelu", r_p="replicate", loss_type="curl", use_symm=True,
+                      repeats=1)(torch.zeros(1, 7, 16, 16))  # CPU tensor on a CUDA model: refuse, do not fall back

@@ -1,0 +1,345 @@
+"""Operator-level parity on the GPU: every C-ABI kernel against the numpy oracle on the same
+seeded inputs (float64 oracle, float32 kernels; tolerances are relative L2 unless noted)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_numpy as RN
+from pbml_mantle_convection_b200 import _lib as L
+from pbml_mantle_convection_b200 import ops
+from tests._util import load, relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(a):
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float32, device=DEV)
+
+
+def c64(a):
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)
+
+
+def xco(xc):
+    return ops.stencil_coefs(c64(xc[0]), 0.0, 4.0)
+
+
+def yco(yc):
+    return ops.stencil_coefs(c64(yc[:, 0]), 0.0, 1.0)
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+def test_library_is_loaded_from_tree():
+    lib = L.load()
+    assert lib.pbmc_version() == 1 and L.LIB_PATH.endswith("pbml_mantle_convection_b200/libpbmc.so")
+
+
+@pytest.mark.parametrize("shape", [(1, 7, 16, 16), (2, 16, 33, 50), (3, 1, 5, 7), (1, 103, 20, 24)])
+def test_pack_unpack_roundtrip(shape):
+    x = rng(0).standard_normal(shape).astype(np.float32)
+    xb = ops.pack_nchw(cu(x))
+    B, C, H, W = shape
+    assert tuple(xb.shape) == (B, (C + 3) // 4, H, W, 4)
+    ref = np.zeros((B, (C + 3) // 4 * 4, H, W), np.float32)
+    ref[:, :C] = x
+    ref = ref.reshape(B, -1, 4, H, W).transpose(0, 1, 3, 4, 2)
+    assert np.array_equal(xb.cpu().numpy(), ref)
+    assert np.array_equal(ops.unpack_nchw(xb, C).cpu().numpy(), x)
+
+
+CONV_CASES = [
+    # (B, Ci, Co, H, W, k, pad)
+    (1, 16, 16, 40, 70, 3, "replicate"),
+    (2, 16, 16, 8, 64, 3, "zeros"),
+    (1, 16, 16, 37, 129, 3, "reflect"),
+    (2, 7, 16, 19, 23, 3, "replicate"),
+    (1, 16, 2, 24, 40, 3, "replicate"),
+    (1, 8, 8, 17, 31, 3, "zeros"),
+    (1, 16, 16, 21, 66, 5, "zeros"),
+    (1, 16, 1, 12, 30, 5, "reflect"),
+    (1, 32, 32, 16, 20, 3, "replicate"),
+    (1, 16, 16, 3, 3, 3, "replicate"),
+    (1, 16, 16, 1, 5, 3, "zeros"),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_plain(case):
+    B, Ci, Co, H, W, k, pad = case
+    r = rng(1)
+    x = r.standard_normal((B, Ci, H, W))
+    w = r.standard_normal((Co, Ci, k, k)) / np.sqrt(Ci * k * k)
+    b = r.standard_normal(Co)
+    ref = RN.conv2d_same(x, w, b, pad)
+    wpk = ops.pack_conv_weight(cu(w), [Ci])
+    out, stats, csum = ops.conv_fwd([ops.Source(ops.pack_nchw(cu(x)))], wpk, ops.pad_vec(cu(b), Co, DEV), Co, k, pad,
+                                    want_stats=True, want_chan_sum=True, impl="ffma")
+    y = ops.unpack_nchw(out, Co).cpu().numpy()
+    assert relerr(y, ref) < 2e-6
+    # statistics: per (sample, 4-channel block) sum and sum of squares, per-channel sums
+    cb = (Co + 3) // 4
+    refp = np.zeros((B, cb * 4, H, W))
+    refp[:, :Co] = ref
+    rs = refp.reshape(B, cb, -1)
+    st = stats.cpu().numpy()
+    assert np.allclose(st[..., 0], rs.sum(-1), rtol=1e-5, atol=1e-4 * np.sqrt(rs.shape[-1]))
+    assert np.allclose(st[..., 1], (rs**2).sum(-1), rtol=1e-5)
+    assert np.allclose(csum.cpu().numpy(), refp.sum((2, 3)), rtol=1e-5, atol=1e-4 * np.sqrt(H * W))
+
+
+def test_conv_gelu_epilogue():
+    r = rng(2)
+    x, w, b = r.standard_normal((1, 16, 20, 30)), r.standard_normal((16, 16, 3, 3)) / 12, r.standard_normal(16)
+    ref = RN.gelu(RN.conv2d_same(x, w, b, "replicate"))
+    out, _, _ = ops.conv_fwd([ops.Source(ops.pack_nchw(cu(x)))], ops.pack_conv_weight(cu(w), [16]), ops.pad_vec(cu(b), 16, DEV),
+                             16, 3, "replicate", epi_act=L.ACT_GELU, impl="ffma")
+    assert relerr(ops.unpack_nchw(out, 16).cpu().numpy(), ref) < 2e-6
+
+
+def test_fluid_layer_chain_with_fused_groupnorm_and_concat():
+    """conv -> [GN+GELU fused into the next load] -> conv over a 3-source concat (one plain source)."""
+    r = rng(3)
+    B, H, W = 2, 26, 45
+    x0 = r.standard_normal((B, 16, H, W))
+    xin = r.standard_normal((B, 7, H, W))
+    w1, b1 = r.standard_normal((16, 16, 3, 3)) / 12, r.standard_normal(16)
+    g1, be1 = 1 + 0.2 * r.standard_normal(16), 0.2 * r.standard_normal(16)
+    w2, b2 = r.standard_normal((16, 39, 3, 3)) / 18, r.standard_normal(16)
+    y1 = RN.conv2d_same(x0, w1, b1, "replicate")
+    a1 = RN.gelu(RN.group_norm(y1, g1, be1, 4))
+    ref = RN.conv2d_same(np.concatenate([a1, x0, xin], 1), w2, b2, "replicate")
+
+    x0b, xinb = ops.pack_nchw(cu(x0)), ops.pack_nchw(cu(xin))
+    y1b, st1, _ = ops.conv_fwd([ops.Source(x0b)], ops.pack_conv_weight(cu(w1), [16]), ops.pad_vec(cu(b1), 16, DEV), 16, 3,
+                               "replicate", want_stats=True, impl="ffma")
+    srcs = [ops.Source(y1b, L.XFORM_GN_GELU, st1, cu(g1), cu(be1)), ops.Source(x0b), ops.Source(xinb)]
+    out, _, _ = ops.conv_fwd(srcs, ops.pack_conv_weight(cu(w2), [16, 16, 7]), ops.pad_vec(cu(b2), 16, DEV), 16, 3,
+                             "replicate", impl="ffma")
+    assert relerr(ops.unpack_nchw(out, 16).cpu().numpy(), ref) < 5e-6
+    # stand-alone finalize == GN + GELU
+    fin = ops.finalize_nchw(ops.Source(y1b, L.XFORM_GN_GELU, st1, cu(g1), cu(be1)), 16).cpu().numpy()
+    assert relerr(fin, a1) < 3e-6
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (15, 31), (50, 77), (2, 3)])
+def test_avgpool_floor(H, W):
+    x = rng(4).standard_normal((2, 16, H, W))
+    out = ops.avgpool2(ops.Source(ops.pack_nchw(cu(x))))
+    assert tuple(out.shape) == (2, 4, H // 2, W // 2, 4)
+    assert relerr(ops.unpack_nchw(out, 16).cpu().numpy(), RN.avg_pool2(x)) < 1e-6
+
+
+def test_avgpool_with_fused_groupnorm():
+    r = rng(5)
+    x = r.standard_normal((2, 16, 20, 34)) * 3 + 1
+    g, be = 1 + 0.2 * r.standard_normal(16), 0.2 * r.standard_normal(16)
+    ref = RN.avg_pool2(RN.gelu(RN.group_norm(x, g, be, 4)))
+    xb = ops.pack_nchw(cu(x))
+    st = torch.stack([xb.double().sum((2, 3, 4)), (xb.double() ** 2).sum((2, 3, 4))], -1).contiguous()
+    out = ops.avgpool2(ops.Source(xb, L.XFORM_GN_GELU, st, cu(g), cu(be)))
+    assert relerr(ops.unpack_nchw(out, 16).cpu().numpy(), ref) < 3e-6
+
+
+@pytest.mark.parametrize("hs,ws,H,W", [(15, 31, 50, 77), (64, 64, 128, 128), (4, 15, 128, 506), (8, 8, 8, 8), (1, 1, 9, 9),
+                                       (63, 126, 128, 506)])
+def test_bicubic(hs, ws, H, W):
+    x = rng(6).standard_normal((1, 8, hs, ws))
+    out = ops.bicubic_up(ops.Source(ops.pack_nchw(cu(x))), H, W)
+    y = ops.unpack_nchw(out, 8).cpu().numpy()
+    assert relerr(y, RN.bicubic_upsample(x, (H, W))) < 3e-6
+
+
+def test_bicubic_matches_golden_torch():
+    g = load("ops")
+    out = ops.bicubic_up(ops.Source(ops.pack_nchw(cu(g["bic_x"]))), 50, 77)
+    assert relerr(ops.unpack_nchw(out, 3).cpu().numpy(), g["bic_y"]) < 3e-6
+    pl = ops.avgpool2(ops.Source(ops.pack_nchw(cu(g["bic_x"]))))
+    assert relerr(ops.unpack_nchw(pl, 3).cpu().numpy(), g["pool_y"]) < 1e-6
+
+
+def test_build_input():
+    H, W, B = 40, 56, 3
+    xc, yc = RN.synthetic_grid(H, W)
+    prm = [(6.79733173, 475523342.0, 2.58574662), (0.5, 1.2e6, 1.1), (9.0, 7e9, 90.0)]
+    T = np.stack([RN.synthetic_T0(H, W, seed=s) for s in range(B)])
+    T[1] *= 1.7  # exercise the clip(V, 1e-8, 1) branches
+    members = ops.make_members(prm, DEV)
+    inp, V = ops.build_input(cu(T), cu(xc), cu(yc), cu(yc), members, want_V=True)
+    got = ops.unpack_nchw(inp, 7).cpu().numpy()
+    for b in range(B):
+        ref, Vr = RN.build_input(T[b][None, None], xc, yc, yc, *prm[b])
+        assert np.abs(got[b] - ref[0]).max() < 3e-6
+        assert np.abs(V[b].cpu().numpy() - Vr[0, 0]).max() < 2e-6
+    assert np.all(inp[:, 1, :, :, 3].cpu().numpy() == 0)
+
+
+@pytest.mark.parametrize("H,W", [(20, 28), (33, 65), (3, 3)])
+def test_head_curl(H, W):
+    r = rng(7)
+    B = 2
+    y = r.standard_normal((B, 2, H, W))
+    spec = RN.NetSpec()
+    u_ref, v_ref, p_ref = RN.curl_head(y.copy(), spec)
+    prm = [(6.79733173, 475523342.0, 2.58574662), (1.0, 1e7, 2.0)]
+    members = ops.make_members(prm, DEV)
+    yb = ops.pack_nchw(cu(y))
+    csum = torch.tensor(np.pad(y.sum((2, 3)), ((0, 0), (0, 2))), dtype=torch.float64, device=DEV)
+    u, v, p, uvmax = ops.head(yb, csum, members, spec.a_bound, L.HEAD_CURL, True)
+    for b in range(B):
+        s = RN.velocity_scaler(*prm[b])
+        assert np.abs(u[b].cpu().numpy() - u_ref[b] * s).max() <= 2e-6 * np.abs(u_ref[b] * s).max() + 1e-30
+        assert np.abs(v[b].cpu().numpy() - v_ref[b] * s).max() <= 2e-6 * np.abs(v_ref[b] * s).max() + 1e-30
+        assert np.abs(p[b].cpu().numpy() - p_ref[b]).max() < 1e-5
+        if H > 2 and W > 2:
+            m = max(np.abs(u_ref[b, 1:-1, 1:-1]).max(), np.abs(v_ref[b, 1:-1, 1:-1]).max()) * s
+            got = uvmax[b:b + 1].view(torch.float32).item()
+            assert abs(got - m) <= 2e-6 * m
+    # wall structure is exact
+    un = u.cpu().numpy()
+    assert np.all(un[:, 1:-1, 0] == -un[:, 1:-1, 1])
+    assert np.all(un[:, 0, 0] == 0) and np.all(v.cpu().numpy()[:, -1, -1] == 0)
+
+
+def test_head_mae():
+    r = rng(8)
+    y = r.standard_normal((2, 3, 12, 20))
+    yb = ops.pack_nchw(cu(y))
+    csum = torch.tensor(np.pad(y.sum((2, 3)), ((0, 0), (0, 1))), dtype=torch.float64, device=DEV)
+    u, v, p, _ = ops.head(yb, csum, None, 10.0, L.HEAD_MAE, True, want_uvmax=False)
+    ym = y - y.mean((2, 3), keepdims=True)
+    assert np.abs(u.cpu().numpy() - ym[:, 0]).max() < 1e-5 and np.abs(p.cpu().numpy() - ym[:, 2]).max() < 1e-5
+
+
+def _adnet_case(H, W, B, seed, scale=50.0):
+    r = rng(seed)
+    xc, yc = RN.synthetic_grid(H, W)
+    u = r.standard_normal((B, H, W)) * scale
+    v = r.standard_normal((B, H, W)) * scale
+    u[0, min(5, H - 2), min(5, W - 2)] = 0.0
+    T = r.random((B, H, W))
+    return xc, yc, u, v, T
+
+
+@pytest.mark.parametrize("H,W,B", [(40, 56, 2), (33, 65, 1), (128, 506, 1), (3, 3, 1), (64, 512, 2), (35, 130, 1)])
+def test_stencil_vs_oracle(H, W, B):
+    """fast separable kernel (vector path when W % 4 == 0) incl. the fused CFL reduction."""
+    xc, yc, u, v, T = _adnet_case(H, W, B, 9)
+    raq = 3.5
+    members = ops.make_members([(raq, 1e7, 2.0)] * B, DEV)
+    uvmax = ops.uvmax_reduce(cu(u), cu(v), batch_global=True)
+    xf = xc.copy()
+    xf[:, 0], xf[:, -1] = 0, 4
+    dx_min = (xf[1:-1, 1:-1] - xf[1:-1, :-2]).min() if W > 2 else 1.0
+    Tn, dt, uv_out = ops.advect_diffuse(cu(T), cu(u), cu(v), xco(xc), yco(yc), members, uvmax, dx_min, 0.99,
+                                        per_member_dt=False, want_uvmax_out=True)
+    # oracle in float64 on the float32-rounded inputs (isolates kernel arithmetic from input rounding)
+    f = lambda a: a.astype(np.float32).astype(np.float64)
+    Tr, dtr = RN.adnet_forward(f(u), f(v), f(T), np.float64(np.float32(raq)), xc, yc, 0.99)
+    Tr = RN.apply_T_bcs(Tr)
+    assert abs(dt[0].item() - dtr) <= 1e-6 * dtr
+    got = Tn.cpu().numpy()
+    # upwind switches at u == 0 exactly, inputs are identical => same branch everywhere
+    assert np.abs(got - Tr).max() < 5e-6 * max(1.0, np.abs(Tr).max())
+    m = max(np.abs(f(u)[:, 1:-1, 1:-1]).max(), np.abs(f(v)[:, 1:-1, 1:-1]).max())
+    assert uv_out.view(torch.float32)[0].item() == pytest.approx(m, rel=1e-7)
+    # wall structure
+    assert np.all(got[:, 0, :] == 1) and np.all(got[:, -1, :] == 0)
+    assert np.all(got[:, 1:-1, 0] == got[:, 1:-1, 1]) and np.all(got[:, 1:-1, -1] == got[:, 1:-1, -2])
+
+
+def test_stencil_golden_reference():
+    """against vectors produced by the reference's ADNet itself (B=2, batch-global dt; fixed dt)."""
+    g = load("ops")
+    u, v, T = g["ad_u"][:, 0], g["ad_v"][:, 0], g["ad_T"][:, 0]
+    xc, yc = g["ad_xc"], g["ad_yc"]
+    members = ops.make_members([(float(g["ad_raq"]), 1e7, 2.0)] * 2, DEV)
+    uvmax = ops.uvmax_reduce(cu(u), cu(v), batch_global=True)
+    xf = xc.copy()
+    xf[:, 0], xf[:, -1] = 0, 4
+    dx_min = (xf[1:-1, 1:-1] - xf[1:-1, :-2]).min()
+    Tn, dt, _ = ops.advect_diffuse(cu(T), cu(u), cu(v), xco(xc), yco(yc), members, uvmax, dx_min, 0.99,
+                                   per_member_dt=False)
+    assert abs(dt[0].item() - float(g["ad_dt"])) < 1e-6 * float(g["ad_dt"])
+    assert np.abs(Tn.cpu().numpy() - g["ad_Tn"][:, 0]).max() < 2e-5  # float32 inputs: |u| dt/dx ~ 0.5 => ~1e-6 expected
+    Tn2, dt2, _ = ops.advect_diffuse(cu(T), cu(u), cu(v), xco(xc), yco(yc), members, None, dx_min, 0.99,
+                                     per_member_dt=False, dt_fixed=1e-4)
+    assert dt2[0].item() == 1e-4
+    assert np.abs(Tn2.cpu().numpy() - g["ad_Tn_fixed_dt"][:, 0]).max() < 2e-4
+    # general-fields kernel gives the same answer
+    dxm = torch.tensor([dx_min], dtype=torch.float64, device=DEV)
+    Tn3, dt3 = ops.advect_diffuse_fields(cu(T), cu(u), cu(v), c64(xc), c64(yc), None, members, uvmax, dxm, 0.99)
+    assert np.abs(Tn3.cpu().numpy() - Tn.cpu().numpy()).max() < 2e-6 and dt3[0].item() == dt[0].item()
+
+
+def test_stencil_per_member_dt():
+    H, W, B = 32, 64, 3
+    xc, yc, u, v, T = _adnet_case(H, W, B, 10)
+    u[1] *= 10
+    v[2] *= 0.01
+    u[2] *= 0.01
+    members = ops.make_members([(1.0, 1e7, 2.0), (2.0, 1e7, 2.0), (3.0, 1e7, 2.0)], DEV)
+    uvmax = ops.uvmax_reduce(cu(u), cu(v), batch_global=False)
+    xf = xc.copy()
+    xf[:, 0], xf[:, -1] = 0, 4
+    dx_min = (xf[1:-1, 1:-1] - xf[1:-1, :-2]).min()
+    Tn, dt, _ = ops.advect_diffuse(cu(T), cu(u), cu(v), xco(xc), yco(yc), members, uvmax, dx_min, 0.99,
+                                   per_member_dt=True)
+    f = lambda a: a.astype(np.float32).astype(np.float64)
+    for b in range(B):
+        Tr, dtr = RN.adnet_forward(f(u[b:b + 1]), f(v[b:b + 1]), f(T[b:b + 1]), float(b + 1), xc, yc, 0.99)
+        assert abs(dt[b].item() - dtr) <= 1e-6 * dtr
+        assert np.abs(Tn[b].cpu().numpy() - RN.apply_T_bcs(Tr)[0]).max() < 5e-6
+
+
+def test_stencil_large_grid_properties():
+    """BASELINE config 3 size (8192^2): properties that need no oracle run -- zero velocity
+    and linear T(y) on the non-uniform grid is a fixed point of the diffusion operator; wall
+    rows/columns exact; CFL reduction equals torch's own max."""
+    H = W = 8192
+    xc, yc = RN.synthetic_grid(H, W)
+    y1 = cu(yc[:, 0])
+    T = (1.0 - y1)[None, :, None].expand(1, H, W).contiguous()
+    z = torch.zeros(1, H, W, device=DEV)
+    members = ops.make_members([(0.0, 1e7, 2.0)], DEV)
+    uv = torch.zeros(1, dtype=torch.int32, device=DEV)
+    dx_min = 2.0 / (W - 2)
+    Tn, dt, _ = ops.advect_diffuse(T, z, z, xco(xc), yco(yc), members, uv, dx_min, 0.99)
+    assert dt[0].item() == pytest.approx(0.25 * dx_min**2, rel=1e-12)  # diffusive limit when max|u| = 0
+    assert (Tn[0, 1:-1, 1:-1] - T[0, 1:-1, 1:-1]).abs().max().item() < 1e-6
+    assert torch.all(Tn[0, 0] == 1) and torch.all(Tn[0, -1] == 0)
+    u = torch.randn(1, H, W, device=DEV) * 1e3
+    v = torch.randn(1, H, W, device=DEV) * 1e3
+    Tn2, dt2, uvo = ops.advect_diffuse(T, u, v, xco(xc), yco(yc), members, ops.uvmax_reduce(u, v), dx_min, 0.99,
+                                       want_uvmax_out=True)
+    m = max(u[0, 1:-1, 1:-1].abs().max().item(), v[0, 1:-1, 1:-1].abs().max().item())
+    assert uvo.view(torch.float32)[0].item() == m
+    assert dt2[0].item() == pytest.approx(0.5 * 0.99 * dx_min / m, rel=1e-6)
+    assert torch.all(Tn2[0, 1:-1, 0] == Tn2[0, 1:-1, 1]) and torch.isfinite(Tn2).all()
+
+
+def test_clamp_and_diagnostics():
+    r = rng(11)
+    T = r.standard_normal((2, 30, 44)) * 2
+    t = cu(T)
+    ops.clamp_T(t)
+    ref = T.astype(np.float32).copy()
+    ref[:, 0, :], ref[:, -1, :] = 1, 0
+    ref[:, :, 0], ref[:, :, -1] = ref[:, :, 1], ref[:, :, -2]
+    ref = np.clip(ref, 0, 2)
+    assert np.array_equal(t.cpu().numpy(), ref)
+    mean, prof = ops.diagnostics(t)
+    assert np.allclose(prof.cpu().numpy(), ref.astype(np.float64).mean(-1), rtol=1e-12)
+    assert np.allclose(mean.cpu().numpy(), ref.astype(np.float64).mean((1, 2)), rtol=1e-12)
+
+
+def test_error_codes_on_device():
+    x = torch.zeros(1, 1, 8, 8, 4, device=DEV)
+    with pytest.raises(L.PbmcError, match="unsupported"):
+        ops.conv_fwd([ops.Source(x)], torch.zeros(1, 1, 49, 4, 16, device=DEV), torch.zeros(4, device=DEV), 4, 7, "zeros")
+    with pytest.raises(L.PbmcError):  # reflect needs size > pad
+        ops.conv_fwd([ops.Source(torch.zeros(1, 1, 1, 8, 4, device=DEV))], torch.zeros(1, 1, 9, 4, 16, device=DEV),
+                     torch.zeros(4, device=DEV), 4, 3, "reflect")
