@@ -80,7 +80,7 @@ class BoundaryLearnedConvolution2D(nn.Module):
                                run("conv_bottom_right", last_r[..., -pad_x:])], 3)
         mid = torch.cat([run("conv_left", x[..., :pad_x]), run("conv", x), run("conv_right", x[..., -pad_x:])], 3)
         out = torch.cat([from_last, mid, from_first], 2)  # row order as in the reference (:1060)
-        return out + self.learnable_bias.to(out.dtype)
+        return out + self.learnable_bias.detach().to(out.dtype)
 
 
 class FluidLayer(nn.Module):
