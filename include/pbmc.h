@@ -47,9 +47,11 @@ enum { PBMC_PAD_ZEROS = 0, PBMC_PAD_REPLICATE = 1, PBMC_PAD_REFLECT = 2 };
 enum { PBMC_XFORM_NONE = 0, PBMC_XFORM_GN_GELU = 1, PBMC_XFORM_GN = 2, PBMC_XFORM_GELU = 3 };
 enum { PBMC_ACT_NONE = 0, PBMC_ACT_GELU = 1 };
 enum { PBMC_HEAD_CURL = 0, PBMC_HEAD_MAE = 1 };
-/* conv implementation selector: FFMA = fp32 CUDA cores; UMMA_3XTF32 = tcgen05 tensor
- * cores with a 3-term TF32 split (fp32-grade accuracy); UMMA_BF16 = tcgen05 bf16 operands. */
-enum { PBMC_CONV_AUTO = 0, PBMC_CONV_FFMA = 1, PBMC_CONV_UMMA_3XTF32 = 2, PBMC_CONV_UMMA_BF16 = 3 };
+/* conv implementation selector: FFMA = fp32 CUDA cores; UMMA_* = tcgen05 tensor cores:
+ * 3XTF32 / F16X2 split every operand into hi + lo (tf32 resp. fp16) and issue 3 passes --
+ * fp32-grade accuracy; BF16 = single pass with bf16 operands (looser, stated bound).
+ * AUTO = UMMA_F16X2 where the shape is supported, else FFMA. */
+enum { PBMC_CONV_AUTO = 0, PBMC_CONV_FFMA = 1, PBMC_CONV_UMMA_3XTF32 = 2, PBMC_CONV_UMMA_BF16 = 3, PBMC_CONV_UMMA_F16X2 = 4 };
 
 const char* pbmc_error_string(int status);
 int pbmc_version(void);

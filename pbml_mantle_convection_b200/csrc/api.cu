@@ -89,9 +89,9 @@ static int conv_enqueue(const pbmc_conv_desc& d, cudaStream_t st) {
   int rc = validate_conv(d);
   if (rc != PBMC_OK) return rc;
   int impl = d.impl;
-  if (impl == PBMC_CONV_AUTO) impl = (d.wpk_umma && conv_umma_supported(d)) ? PBMC_CONV_UMMA_3XTF32 : PBMC_CONV_FFMA;
+  if (impl == PBMC_CONV_AUTO) impl = (d.wpk_umma && conv_umma_supported(d)) ? PBMC_CONV_UMMA_F16X2 : PBMC_CONV_FFMA;
   if (impl == PBMC_CONV_FFMA) return conv_ffma_dispatch(d, st);
-  if (impl == PBMC_CONV_UMMA_3XTF32 || impl == PBMC_CONV_UMMA_BF16) {
+  if (impl == PBMC_CONV_UMMA_3XTF32 || impl == PBMC_CONV_UMMA_BF16 || impl == PBMC_CONV_UMMA_F16X2) {
     if (!d.wpk_umma || !conv_umma_supported(d)) return PBMC_ERR_UNSUPPORTED;
     pbmc_conv_desc e = d;
     e.impl = impl;

@@ -24,7 +24,8 @@ class _PackedLayer:
         self.beta = ops.pad_vec(beta, cout, dev, 0.0) if beta is not None else None
         self.cin_blks = sum(ops.nblk(c) for c in src_channels)
         self.cout, self.ksize = cout, k
-        self.wpk_umma = None
+        self.wpk_umma = (ops.pack_conv_weight_umma(w_full.to(dev), src_channels)
+                         if ops.umma_supported(cout, src_channels) else None)
 
     def c(self):
         s = L.Layer()

@@ -57,6 +57,49 @@ def pack_conv_weight(w_full: torch.Tensor, src_channels) -> torch.Tensor:
     return w
 
 
+def tf32_round(x: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest (ties away) float32 -> tf32 (10-bit mantissa), result still float32 -- cvt.rna.tf32.f32."""
+    bits = x.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & -8192).view(torch.float32)
+
+
+def umma_supported(cout: int, src_channels) -> bool:
+    """Shapes the tcgen05 conv kernel takes (csrc/conv_umma.cu): <= 16 outputs, every source an even number of 4-channel blocks."""
+    return cout <= 16 and all(nblk(c) % 2 == 0 for c in src_channels)
+
+
+def pack_conv_weight_umma(w_full: torch.Tensor, src_channels) -> torch.Tensor:
+    """[Co<=16, Ci, k, k] -> uint8 buffer holding the three K-major B-operand images of csrc/conv_umma.cu:
+         tf32 : float32  [2 (hi, lo)][cin_blks  ][k*k][16 c_out][4 c_in]   hi = tf32(w),  lo = w - hi
+         fp16 : float16  [2 (hi, lo)][cin_blks/2][k*k][16 c_out][8 c_in]   hi = fp16(w),  lo = fp16(w - hi)
+         bf16 : bfloat16 [1         ][cin_blks/2][k*k][16 c_out][8 c_in]
+       back to back (offsets are multiples of 256 B)."""
+    Co, Ci, k, _ = w_full.shape
+    assert Co <= 16 and sum(src_channels) == Ci
+    parts, c0 = [], 0
+    for c in src_channels:
+        wpart = w_full[:, c0:c0 + c]
+        pad = nblk(c) * 4 - c
+        if pad:
+            wpart = torch.cat([wpart, wpart.new_zeros(Co, pad, k, k)], 1)
+        parts.append(wpart)
+        c0 += c
+    w = torch.cat(parts, 1).float()
+    if Co < 16:
+        w = torch.cat([w, w.new_zeros(16 - Co, w.shape[1], k, k)], 0)
+    cb = w.shape[1] // 4
+    assert cb % 2 == 0
+    w4 = w.reshape(16, cb, 4, k * k).permute(1, 3, 0, 2).contiguous()  # [cb][tap][co][4]
+    hi = tf32_round(w4)
+    img_tf32 = torch.stack([hi, w4 - hi], 0).contiguous()
+    w8 = w.reshape(16, cb // 2, 8, k * k).permute(1, 3, 0, 2).contiguous()  # [cb/2][tap][co][8]
+    h16 = w8.half()
+    img_f16 = torch.stack([h16, (w8 - h16.float()).half()], 0).contiguous()
+    img_bf16 = w8.bfloat16().contiguous()
+    as_bytes = lambda t: t.view(torch.uint8).reshape(-1)
+    return torch.cat([as_bytes(img_tf32), as_bytes(img_f16), as_bytes(img_bf16)]).contiguous()
+
+
 def pad_vec(v, c: int, device, fill=0.0) -> torch.Tensor:
     """[c] -> float32 [ceil(c/4)*4] on `device` (v=None: all `fill`)."""
     out = torch.full((nblk(c) * 4,), fill, dtype=torch.float32, device=device)

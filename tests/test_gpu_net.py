@@ -33,12 +33,16 @@ def fwd_bound(noise):
     return np.maximum(1e-5, 1.5 * np.asarray(noise))
 
 
+IMPLS = ["ffma", "umma_3xtf32", "umma_f16x2"]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("tag", VARIANTS)
-def test_variants_forward(tag):
+def test_variants_forward(tag, impl):
     """zeros / reflect / replicate padding, symmetric and plain filters, odd sizes, mae head, k=5."""
     g = load(tag)
     spec = spec_from_variant(g)
-    net = make_net(spec, split_weights(g), impl="ffma")
+    net = make_net(spec, split_weights(g), impl=impl)
     inp = torch.tensor(g["inp"], device=DEV)  # float64 in, float64 out (module is .double() like the reference)
     u, v, p = net(inp)
     assert u.dtype == torch.float64 and tuple(u.shape) == g["u"].shape
@@ -49,17 +53,37 @@ def test_variants_forward(tag):
         assert p is None
 
 
-def test_forward_128_against_reference_golden():
+@pytest.mark.parametrize("impl", IMPLS)
+def test_forward_128_against_reference_golden(impl):
     g = load("roll128")
     spec = RN.NetSpec()
-    net = make_net(spec, load_weights("roll128"), impl="ffma")
+    net = make_net(spec, load_weights("roll128"), impl=impl)
     inp, _ = RN.build_input(g["T0"][None, None], g["xc"], g["yc"], g["yc"], *PARAMS)
     u, v, p = net(torch.tensor(inp, device=DEV))
     s = RN.velocity_scaler(*PARAMS)
     errs = np.array([relerr(u[0].cpu().numpy() * s, g["u1"]), relerr(v[0].cpu().numpy() * s, g["v1"]),
                      relerr(p[0].cpu().numpy(), g["p1"])])
-    print("rel-L2 (u,v,p) new fp32 vs reference fp64:", errs, " reference fp32 noise:", g["ref_fp32_noise"])
+    print(f"[{impl}] rel-L2 (u,v,p) new fp32 vs reference fp64:", errs, " reference fp32 noise:", g["ref_fp32_noise"])
     assert np.all(errs <= fwd_bound(g["ref_fp32_noise"])), (errs, g["ref_fp32_noise"])
+
+
+def test_forward_128_bf16_variant_bound():
+    """bf16-operand conv variant (north_star: "bf16 conv variants get their own stated looser bound").
+    Stated bound for one forward at 128^2: rel-L2(p) <= 2e-2, rel-L2(u) <= 0.5, rel-L2(v) <= 0.8.
+    The velocity bound is loose BY NATURE: u, v are finite differences of the stream function, which
+    amplifies the relative error of the net output by ~|a|/|delta a| ~ 600 (the reference's own fp32
+    run already shows 3.7e-5 / 7.2e-5 from a 5.8e-7 output error).  Operands with 8 mantissa bits
+    (measured 1.7e-3 per conv) are therefore adequate for p but not for the curl head; the
+    tensor-core path that meets the fp32 parity bound is the fp16 hi+lo split (umma_f16x2)."""
+    g = load("roll128")
+    net = make_net(RN.NetSpec(), load_weights("roll128"), impl="umma_bf16")
+    inp, _ = RN.build_input(g["T0"][None, None], g["xc"], g["yc"], g["yc"], *PARAMS)
+    u, v, p = net(torch.tensor(inp, device=DEV))
+    s = RN.velocity_scaler(*PARAMS)
+    errs = np.array([relerr(u[0].cpu().numpy() * s, g["u1"]), relerr(v[0].cpu().numpy() * s, g["v1"]),
+                     relerr(p[0].cpu().numpy(), g["p1"])])
+    print("[umma_bf16] rel-L2 (u,v,p) vs reference fp64:", errs)
+    assert errs[0] < 0.5 and errs[1] < 0.8 and errs[2] < 2e-2
 
 
 def _ts_call(ts, T0, xc, yc, params=PARAMS, dtype=torch.float64):
@@ -73,7 +97,7 @@ def _ts_call(ts, T0, xc, yc, params=PARAMS, dtype=torch.float64):
 def test_TS_dropin_unmodified_reference_128x506():
     """Same call as advect_wi_gaia.py:590-593 (CPU float64 tensors in), against the UNMODIFIED reference TS(ts=5)."""
     g = load("ts128x506")
-    net = make_net(RN.NetSpec(), load_weights("ts128x506"), impl="ffma")
+    net = make_net(RN.NetSpec(), load_weights("ts128x506"), impl="auto")
     ts = P.TS(net, P.ADNet(DEV, CN_max=0.99), DEV, ts=5, scale=True, p_pred=True, net="newfluidnet")
     x, dts, u, v, p, V = _ts_call(ts, g["T0"], g["xc"], g["yc"])
     assert sorted(x.keys()) == [0, 1, 2, 3, 4, 5] and sorted(dts.keys()) == [1, 2, 3, 4, 5]
@@ -87,10 +111,11 @@ def test_TS_dropin_unmodified_reference_128x506():
     assert np.abs(V[0, 0].cpu().numpy() - g["V5"]).max() < 2e-5  # float32 exp of z ~ -20..0
 
 
-def test_rollout_100_steps_diagnostics():
+@pytest.mark.parametrize("impl", IMPLS)
+def test_rollout_100_steps_diagnostics(impl):
     """BASELINE config 1 (128x128, 100 steps): T fields and mean-T / profile diagnostics vs the reference."""
     g = load("roll128")
-    net = make_net(RN.NetSpec(), load_weights("roll128"), impl="ffma")
+    net = make_net(RN.NetSpec(), load_weights("roll128"), impl=impl)
     ens = P.EnsembleRollout(net, 128, 128, [PARAMS], DEV, cn_max=0.99)
     ens.set_T(g["T0"][None])
     snaps = {}
@@ -158,7 +183,7 @@ def test_full_size_512_against_cpu_port():
     """BASELINE config 2 grid (512x512): one forward + 3 steps against the ATen-CPU float64 port."""
     spec = RN.NetSpec()
     w = load_weights("roll128")
-    net = make_net(spec, w, impl="ffma")
+    net = make_net(spec, w, impl="auto")
     H = W = 512
     xc, yc = RN.synthetic_grid(H, W)
     T0 = RN.synthetic_T0(H, W, seed=1)

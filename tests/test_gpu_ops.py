@@ -91,6 +91,53 @@ def test_conv_plain(case):
     assert np.allclose(csum.cpu().numpy(), refp.sum((2, 3)), rtol=1e-5, atol=1e-4 * np.sqrt(H * W))
 
 
+UMMA_CASES = [
+    (1, 16, 16, 40, 70, 3, "replicate"),
+    (2, 16, 16, 15, 64, 3, "zeros"),
+    (1, 16, 16, 37, 129, 3, "reflect"),
+    (2, 7, 16, 19, 23, 3, "replicate"),
+    (1, 16, 2, 24, 40, 3, "replicate"),
+    (1, 8, 8, 17, 31, 3, "zeros"),
+    (1, 16, 16, 21, 66, 5, "zeros"),
+    (1, 16, 1, 12, 30, 5, "reflect"),
+    (1, 32, 16, 16, 20, 3, "replicate"),
+    (1, 16, 16, 3, 3, 3, "replicate"),
+    (1, 16, 16, 1, 5, 3, "zeros"),
+    (1, 16, 16, 128, 128, 3, "replicate"),
+]
+
+
+@pytest.mark.parametrize("impl,tol", [("umma_3xtf32", 3e-6), ("umma_f16x2", 3e-6), ("umma_bf16", 1e-2)])
+@pytest.mark.parametrize("case", UMMA_CASES)
+def test_conv_umma(case, impl, tol):
+    """tcgen05 implicit-GEMM conv: the hi+lo split modes are fp32-grade against the float64 oracle;
+    the single-pass bf16 mode carries its own (stated) bound: 2^-9 per operand -> <= 1e-2 rel-L2."""
+    B, Ci, Co, H, W, k, pad = case
+    r = rng(21)
+    x = r.standard_normal((B, Ci, H, W))
+    w = r.standard_normal((Co, Ci, k, k)) / np.sqrt(Ci * k * k)
+    b = r.standard_normal(Co)
+    ref = RN.conv2d_same(x, w, b, pad)
+    wpk, wum = ops.pack_conv_weight(cu(w), [Ci]), ops.pack_conv_weight_umma(cu(w), [Ci])
+    out, stats, csum = ops.conv_fwd([ops.Source(ops.pack_nchw(cu(x)))], wpk, ops.pad_vec(cu(b), Co, DEV), Co, k, pad,
+                                    want_stats=True, want_chan_sum=True, impl=impl, wpk_umma=wum)
+    y = ops.unpack_nchw(out, Co).cpu().numpy()
+    assert relerr(y, ref) < tol, relerr(y, ref)
+    if impl == "umma_bf16":
+        ref = y.astype(np.float64)  # statistics are checked against the kernel's own output
+    cb = (Co + 3) // 4
+    refp = np.zeros((B, cb * 4, H, W))
+    refp[:, :Co] = ref
+    rs = refp.reshape(B, cb, -1)
+    st = stats.cpu().numpy()
+    assert np.allclose(st[..., 0], rs.sum(-1), rtol=1e-5, atol=1e-4 * np.sqrt(rs.shape[-1]))
+    assert np.allclose(st[..., 1], (rs**2).sum(-1), rtol=1e-5)
+    assert np.allclose(csum.cpu().numpy(), refp.sum((2, 3)), rtol=1e-5, atol=1e-4 * np.sqrt(H * W))
+    # lanes of the padded output channels stay exactly zero-biased (weights are zero there)
+    if Co % 4:
+        assert np.all(out[:, -1, :, :, Co % 4:].cpu().numpy() == 0)
+
+
 def test_conv_gelu_epilogue():
     r = rng(2)
     x, w, b = r.standard_normal((1, 16, 20, 30)), r.standard_normal((16, 16, 3, 3)) / 12, r.standard_normal(16)
@@ -100,7 +147,8 @@ def test_conv_gelu_epilogue():
     assert relerr(ops.unpack_nchw(out, 16).cpu().numpy(), ref) < 2e-6
 
 
-def test_fluid_layer_chain_with_fused_groupnorm_and_concat():
+@pytest.mark.parametrize("impl", ["ffma", "umma_3xtf32", "umma_f16x2"])
+def test_fluid_layer_chain_with_fused_groupnorm_and_concat(impl):
     """conv -> [GN+GELU fused into the next load] -> conv over a 3-source concat (one plain source)."""
     r = rng(3)
     B, H, W = 2, 26, 45
@@ -115,10 +163,10 @@ def test_fluid_layer_chain_with_fused_groupnorm_and_concat():
 
     x0b, xinb = ops.pack_nchw(cu(x0)), ops.pack_nchw(cu(xin))
     y1b, st1, _ = ops.conv_fwd([ops.Source(x0b)], ops.pack_conv_weight(cu(w1), [16]), ops.pad_vec(cu(b1), 16, DEV), 16, 3,
-                               "replicate", want_stats=True, impl="ffma")
+                               "replicate", want_stats=True, impl=impl, wpk_umma=ops.pack_conv_weight_umma(cu(w1), [16]))
     srcs = [ops.Source(y1b, L.XFORM_GN_GELU, st1, cu(g1), cu(be1)), ops.Source(x0b), ops.Source(xinb)]
     out, _, _ = ops.conv_fwd(srcs, ops.pack_conv_weight(cu(w2), [16, 16, 7]), ops.pad_vec(cu(b2), 16, DEV), 16, 3,
-                             "replicate", impl="ffma")
+                             "replicate", impl=impl, wpk_umma=ops.pack_conv_weight_umma(cu(w2), [16, 16, 7]))
     assert relerr(ops.unpack_nchw(out, 16).cpu().numpy(), ref) < 5e-6
     # stand-alone finalize == GN + GELU
     fin = ops.finalize_nchw(ops.Source(y1b, L.XFORM_GN_GELU, st1, cu(g1), cu(be1)), 16).cpu().numpy()
