@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBMC_VERSION 1
+#define PBMC_VERSION 2
 #define PBMC_MAX_SRC 8
 #define PBMC_MAX_LEVELS 8
 #define PBMC_MAX_REPEATS 8
@@ -50,8 +50,11 @@ enum { PBMC_HEAD_CURL = 0, PBMC_HEAD_MAE = 1 };
 /* conv implementation selector: FFMA = fp32 CUDA cores; UMMA_* = tcgen05 tensor cores:
  * 3XTF32 / F16X2 split every operand into hi + lo (tf32 resp. fp16) and issue 3 passes --
  * fp32-grade accuracy; BF16 = single pass with bf16 operands (looser, stated bound).
- * AUTO = UMMA_F16X2 where the shape is supported, else FFMA. */
-enum { PBMC_CONV_AUTO = 0, PBMC_CONV_FFMA = 1, PBMC_CONV_UMMA_3XTF32 = 2, PBMC_CONV_UMMA_BF16 = 3, PBMC_CONV_UMMA_F16X2 = 4 };
+ * ROW_* = the row-streaming warp-specialised tcgen05 kernel (csrc/conv_row.cu; vertical taps folded
+ * into the MMA's N dimension), F16X2 = fp16 hi+lo 3-pass (fp32-grade), BF16 = single bf16 pass.
+ * AUTO = ROW_F16X2 where the shape is supported, else UMMA_F16X2, else FFMA. */
+enum { PBMC_CONV_AUTO = 0, PBMC_CONV_FFMA = 1, PBMC_CONV_UMMA_3XTF32 = 2, PBMC_CONV_UMMA_BF16 = 3, PBMC_CONV_UMMA_F16X2 = 4,
+       PBMC_CONV_ROW_F16X2 = 5, PBMC_CONV_ROW_BF16 = 6 };
 
 const char* pbmc_error_string(int status);
 int pbmc_version(void);
@@ -121,6 +124,7 @@ typedef struct {
   int reserved;
   const float* wpk;
   const void* wpk_umma;  /* tensor-core operand image of the same weights (NULL => FFMA only) */
+  const void* wpk_row;   /* operand image for the row-streaming tensor-core kernel (NULL => not available) */
   const float* bias;     /* [ceil(cout/4)*4], zero padded */
   float* out;            /* [B][ceil(cout/4)][H][W][4] */
   double* out_stats;     /* [B][ceil(cout/4)][2] or NULL */
@@ -191,6 +195,7 @@ int pbmc_diagnostics(const float* T, double* prof, double* meanT, int B, int H, 
 typedef struct {
   const float* wpk;
   const void* wpk_umma;
+  const void* wpk_row;
   const float* bias;
   const float* gamma; /* GroupNorm affine applied to THIS layer's output by its consumers (NULL: none) */
   const float* beta;

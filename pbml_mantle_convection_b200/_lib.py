@@ -19,7 +19,8 @@ PAD = {"zeros": 0, "constant": 0, "replicate": 1, "reflect": 2}
 XFORM_NONE, XFORM_GN_GELU, XFORM_GN, XFORM_GELU = 0, 1, 2, 3
 ACT_NONE, ACT_GELU = 0, 1
 HEAD_CURL, HEAD_MAE = 0, 1
-CONV_IMPL = {"auto": 0, "ffma": 1, "umma_3xtf32": 2, "umma_bf16": 3, "umma_f16x2": 4}
+CONV_IMPL = {"auto": 0, "ffma": 1, "umma_3xtf32": 2, "umma_bf16": 3, "umma_f16x2": 4,
+             "row_f16x2": 5, "row_bf16": 6}
 
 
 class Member(C.Structure):
@@ -35,12 +36,13 @@ class Src(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [("src", Src * MAX_SRC), ("nsrc", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
                 ("cout", C.c_int), ("ksize", C.c_int), ("pad_mode", C.c_int), ("epi_act", C.c_int), ("impl", C.c_int),
-                ("reserved", C.c_int), ("wpk", C.c_void_p), ("wpk_umma", C.c_void_p), ("bias", C.c_void_p),
-                ("out", C.c_void_p), ("out_stats", C.c_void_p), ("out_chan_sum", C.c_void_p)]
+                ("reserved", C.c_int), ("wpk", C.c_void_p), ("wpk_umma", C.c_void_p), ("wpk_row", C.c_void_p),
+                ("bias", C.c_void_p), ("out", C.c_void_p), ("out_stats", C.c_void_p), ("out_chan_sum", C.c_void_p)]
 
 
 class Layer(C.Structure):
-    _fields_ = [("wpk", C.c_void_p), ("wpk_umma", C.c_void_p), ("bias", C.c_void_p), ("gamma", C.c_void_p),
+    _fields_ = [("wpk", C.c_void_p), ("wpk_umma", C.c_void_p), ("wpk_row", C.c_void_p), ("bias", C.c_void_p),
+                ("gamma", C.c_void_p),
                 ("beta", C.c_void_p), ("cin_blks", C.c_int), ("cout", C.c_int), ("ksize", C.c_int), ("reserved", C.c_int)]
 
 

@@ -18,6 +18,8 @@ void set_last_cuda_error(cudaError_t e, const char* where) {
 int conv_ffma_dispatch(const pbmc_conv_desc& d, cudaStream_t st);
 int conv_umma_dispatch(const pbmc_conv_desc& d, cudaStream_t st);  // conv_umma.cu
 bool conv_umma_supported(const pbmc_conv_desc& d);
+int conv_row_dispatch(const pbmc_conv_desc& d, cudaStream_t st);  // conv_row.cu
+bool conv_row_supported(const pbmc_conv_desc& d);
 
 }  // namespace pbmc
 
@@ -89,7 +91,16 @@ static int conv_enqueue(const pbmc_conv_desc& d, cudaStream_t st) {
   int rc = validate_conv(d);
   if (rc != PBMC_OK) return rc;
   int impl = d.impl;
-  if (impl == PBMC_CONV_AUTO) impl = (d.wpk_umma && conv_umma_supported(d)) ? PBMC_CONV_UMMA_F16X2 : PBMC_CONV_FFMA;
+  if (impl == PBMC_CONV_AUTO)
+    impl = (d.wpk_row && conv_row_supported(d))     ? PBMC_CONV_ROW_F16X2
+           : (d.wpk_umma && conv_umma_supported(d)) ? PBMC_CONV_UMMA_F16X2
+                                                    : PBMC_CONV_FFMA;
+  if (impl == PBMC_CONV_ROW_F16X2 || impl == PBMC_CONV_ROW_BF16) {
+    if (!d.wpk_row || !conv_row_supported(d)) return PBMC_ERR_UNSUPPORTED;
+    pbmc_conv_desc e = d;
+    e.impl = impl;
+    return conv_row_dispatch(e, st);
+  }
   if (impl == PBMC_CONV_FFMA) return conv_ffma_dispatch(d, st);
   if (impl == PBMC_CONV_UMMA_3XTF32 || impl == PBMC_CONV_UMMA_BF16 || impl == PBMC_CONV_UMMA_F16X2) {
     if (!d.wpk_umma || !conv_umma_supported(d)) return PBMC_ERR_UNSUPPORTED;
@@ -193,7 +204,7 @@ inline void fill_conv(pbmc_conv_desc& d, const pbmc_net& n, const pbmc_layer& L,
   memset(&d, 0, sizeof(d));
   d.B = B; d.H = H; d.W = W;
   d.cout = L.cout; d.ksize = L.ksize; d.pad_mode = n.pad_mode; d.epi_act = epi_act; d.impl = n.conv_impl;
-  d.wpk = L.wpk; d.wpk_umma = L.wpk_umma; d.bias = L.bias; d.out = out; d.out_stats = ostats; d.out_chan_sum = ochan;
+  d.wpk = L.wpk; d.wpk_umma = L.wpk_umma; d.wpk_row = L.wpk_row; d.bias = L.bias; d.out = out; d.out_stats = ostats; d.out_chan_sum = ochan;
 }
 }  // namespace
 

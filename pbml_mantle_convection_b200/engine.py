@@ -26,10 +26,13 @@ class _PackedLayer:
         self.cout, self.ksize = cout, k
         self.wpk_umma = (ops.pack_conv_weight_umma(w_full.to(dev), src_channels)
                          if ops.umma_supported(cout, src_channels) else None)
+        self.wpk_row = (ops.pack_conv_weight_row(w_full.to(dev), src_channels)
+                        if ops.row_supported(cout, k, src_channels) else None)
 
     def c(self):
         s = L.Layer()
         s.wpk, s.wpk_umma, s.bias = L.ptr(self.wpk), L.ptr(self.wpk_umma), L.ptr(self.bias)
+        s.wpk_row = L.ptr(self.wpk_row)
         s.gamma, s.beta = L.ptr(self.gamma), L.ptr(self.beta)
         s.cin_blks, s.cout, s.ksize = self.cin_blks, self.cout, self.ksize
         return s

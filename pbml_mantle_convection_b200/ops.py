@@ -100,6 +100,47 @@ def pack_conv_weight_umma(w_full: torch.Tensor, src_channels) -> torch.Tensor:
     return torch.cat([as_bytes(img_tf32), as_bytes(img_f16), as_bytes(img_bf16)]).contiguous()
 
 
+def row_supported(cout: int, ksize: int, src_channels) -> bool:
+    """Shapes the row-streaming tcgen05 kernel takes (csrc/conv_row.cu): k in {3, 5}, <= 16 outputs, and
+    the whole filter bank resident in shared memory next to the 4-stage input ring."""
+    if cout > 16 or ksize not in (3, 5):
+        return False
+    groups = sum((nblk(c) + 3) // 4 for c in src_channels)
+    n = ksize * 16
+    plane = (128 + ksize - 1 + 7) // 8 * 8
+    smem = 2176 + groups * ksize * 2 * (2 * n * 16) + 4 * (2 * 2 * plane * 16) + sum(nblk(c) * 4 for c in src_channels) * 8
+    return groups <= 24 and smem <= 227 * 1024
+
+
+def pack_conv_weight_row(w_full: torch.Tensor, src_channels) -> torch.Tensor:
+    """[Co<=16, Ci, k, k] -> uint8 buffer with the two K-major B-operand images of csrc/conv_row.cu:
+         fp16 : [group][dx][2 (hi, lo)][2 K-chunks][N = k*16 rows (dy, c_out)][8 c_in]   hi = fp16(w), lo = fp16(w - hi)
+         bf16 : [group][dx][1         ][2 K-chunks][N rows][8 c_in]
+       back to back.  A group is 16 input channels of ONE source (each source is zero-padded to a
+       multiple of 16 channels), in concat order; the vertical tap dy rides in the MMA's N dimension."""
+    Co, Ci, k, _ = w_full.shape
+    assert Co <= 16 and sum(src_channels) == Ci
+    parts, c0 = [], 0
+    for c in src_channels:
+        wpart = w_full[:, c0:c0 + c]
+        pad = (nblk(c) + 3) // 4 * 16 - c
+        if pad:
+            wpart = torch.cat([wpart, wpart.new_zeros(Co, pad, k, k)], 1)
+        parts.append(wpart)
+        c0 += c
+    w = torch.cat(parts, 1).float()
+    if Co < 16:
+        w = torch.cat([w, w.new_zeros(16 - Co, w.shape[1], k, k)], 0)
+    G = w.shape[1] // 16
+    # (co, g, chunk, e, dy, dx) -> (g, dx, chunk, dy, co, e)
+    w6 = w.reshape(16, G, 2, 8, k, k).permute(1, 5, 2, 4, 0, 3).contiguous()
+    h16 = w6.half()
+    img_f16 = torch.stack([h16, (w6 - h16.float()).half()], 2).contiguous()  # (g, dx, part, chunk, dy, co, e)
+    img_bf16 = w6.bfloat16().contiguous()
+    as_bytes = lambda t: t.view(torch.uint8).reshape(-1)
+    return torch.cat([as_bytes(img_f16), as_bytes(img_bf16)]).contiguous()
+
+
 def pad_vec(v, c: int, device, fill=0.0) -> torch.Tensor:
     """[c] -> float32 [ceil(c/4)*4] on `device` (v=None: all `fill`)."""
     out = torch.full((nblk(c) * 4,), fill, dtype=torch.float32, device=device)
@@ -149,7 +190,7 @@ def finalize_nchw(src: Source, Cc: int) -> torch.Tensor:
 
 # ------------------------------------------------------------------ conv
 def conv_fwd(sources, wpk, bias, cout, ksize, pad_mode, epi_act=L.ACT_NONE, want_stats=False, want_chan_sum=False,
-             impl="auto", wpk_umma=None, out=None, stats=None, csum=None):
+             impl="auto", wpk_umma=None, out=None, stats=None, csum=None, wpk_row=None):
     """Returns (out_blocked, stats|None, chan_sum|None).  `out`/`stats`/`csum` may be preallocated
     (statistics ACCUMULATE into the given buffers, as in the C ABI)."""
     t0 = sources[0].t
@@ -170,6 +211,7 @@ def conv_fwd(sources, wpk, bias, cout, ksize, pad_mode, epi_act=L.ACT_NONE, want
     d.pad_mode = L.PAD[pad_mode] if isinstance(pad_mode, str) else int(pad_mode)
     d.epi_act, d.impl = int(epi_act), L.CONV_IMPL[impl]
     d.wpk, d.wpk_umma, d.bias, d.out = L.ptr(wpk), L.ptr(wpk_umma), L.ptr(bias), L.ptr(out)
+    d.wpk_row = L.ptr(wpk_row)
     d.out_stats, d.out_chan_sum = L.ptr(stats), L.ptr(csum)
     L.check(L.load().pbmc_conv_fwd(C.byref(d), L.stream_ptr(dev)), "pbmc_conv_fwd")
     return out, stats, csum

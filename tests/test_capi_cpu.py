@@ -40,7 +40,7 @@ def test_struct_sizes(lib):
 
 
 def test_version_and_errors(lib):
-    assert lib.pbmc_version() == 1
+    assert lib.pbmc_version() == 2
     assert lib.pbmc_error_string(0) == b"ok"
     assert b"workspace" in lib.pbmc_error_string(-5)
 

@@ -33,7 +33,7 @@ def fwd_bound(noise):
     return np.maximum(1e-5, 1.5 * np.asarray(noise))
 
 
-IMPLS = ["ffma", "umma_3xtf32", "umma_f16x2"]
+IMPLS = ["ffma", "umma_3xtf32", "umma_f16x2", "row_f16x2"]
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -67,7 +67,8 @@ def test_forward_128_against_reference_golden(impl):
     assert np.all(errs <= fwd_bound(g["ref_fp32_noise"])), (errs, g["ref_fp32_noise"])
 
 
-def test_forward_128_bf16_variant_bound():
+@pytest.mark.parametrize("impl", ["umma_bf16", "row_bf16"])
+def test_forward_128_bf16_variant_bound(impl):
     """bf16-operand conv variant (north_star: "bf16 conv variants get their own stated looser bound").
     Stated bound for one forward at 128^2: rel-L2(p) <= 2e-2, rel-L2(u) <= 0.5, rel-L2(v) <= 0.8.
     The velocity bound is loose BY NATURE: u, v are finite differences of the stream function, which
@@ -76,13 +77,13 @@ def test_forward_128_bf16_variant_bound():
     (measured 1.7e-3 per conv) are therefore adequate for p but not for the curl head; the
     tensor-core path that meets the fp32 parity bound is the fp16 hi+lo split (umma_f16x2)."""
     g = load("roll128")
-    net = make_net(RN.NetSpec(), load_weights("roll128"), impl="umma_bf16")
+    net = make_net(RN.NetSpec(), load_weights("roll128"), impl=impl)
     inp, _ = RN.build_input(g["T0"][None, None], g["xc"], g["yc"], g["yc"], *PARAMS)
     u, v, p = net(torch.tensor(inp, device=DEV))
     s = RN.velocity_scaler(*PARAMS)
     errs = np.array([relerr(u[0].cpu().numpy() * s, g["u1"]), relerr(v[0].cpu().numpy() * s, g["v1"]),
                      relerr(p[0].cpu().numpy(), g["p1"])])
-    print("[umma_bf16] rel-L2 (u,v,p) vs reference fp64:", errs)
+    print(f"[{impl}] rel-L2 (u,v,p) vs reference fp64:", errs)
     assert errs[0] < 0.5 and errs[1] < 0.8 and errs[2] < 2e-2
 
 

@@ -35,7 +35,7 @@ def rng(seed):
 
 def test_library_is_loaded_from_tree():
     lib = L.load()
-    assert lib.pbmc_version() == 1 and L.LIB_PATH.endswith("pbml_mantle_convection_b200/libpbmc.so")
+    assert lib.pbmc_version() == 2 and L.LIB_PATH.endswith("pbml_mantle_convection_b200/libpbmc.so")
 
 
 @pytest.mark.parametrize("shape", [(1, 7, 16, 16), (2, 16, 33, 50), (3, 1, 5, 7), (1, 103, 20, 24)])
@@ -138,6 +138,65 @@ def test_conv_umma(case, impl, tol):
         assert np.all(out[:, -1, :, :, Co % 4:].cpu().numpy() == 0)
 
 
+ROW_CASES = UMMA_CASES + [
+    (1, 4, 16, 9, 140, 3, "replicate"),      # one 4-channel block; two column strips
+    (1, 12, 16, 30, 300, 3, "reflect"),      # three blocks; three strips, partial last strip
+    (2, 40, 16, 70, 130, 3, "zeros"),        # three K groups, last one half full; many rows per CTA
+    (1, 16, 16, 200, 256, 3, "replicate"),   # exact strips, accumulator ring wraps many times
+    (1, 16, 16, 64, 128, 5, "replicate"),
+]
+
+
+@pytest.mark.parametrize("impl,tol", [("row_f16x2", 3e-6), ("row_bf16", 1e-2)])
+@pytest.mark.parametrize("case", ROW_CASES)
+def test_conv_row(case, impl, tol):
+    """Row-streaming warp-specialised tcgen05 conv (csrc/conv_row.cu): fp16 hi+lo split is fp32-grade
+    against the float64 oracle; the single-pass bf16 mode carries its own stated bound."""
+    B, Ci, Co, H, W, k, pad = case
+    r = rng(23)
+    x = r.standard_normal((B, Ci, H, W))
+    w = r.standard_normal((Co, Ci, k, k)) / np.sqrt(Ci * k * k)
+    b = r.standard_normal(Co)
+    ref = RN.conv2d_same(x, w, b, pad)
+    assert ops.row_supported(Co, k, [Ci])
+    wpk, wrow = ops.pack_conv_weight(cu(w), [Ci]), ops.pack_conv_weight_row(cu(w), [Ci])
+    out, stats, csum = ops.conv_fwd([ops.Source(ops.pack_nchw(cu(x)))], wpk, ops.pad_vec(cu(b), Co, DEV), Co, k, pad,
+                                    want_stats=True, want_chan_sum=True, impl=impl, wpk_row=wrow)
+    y = ops.unpack_nchw(out, Co).cpu().numpy()
+    assert relerr(y, ref) < tol, relerr(y, ref)
+    if impl == "row_bf16":
+        ref = y.astype(np.float64)
+    cb = (Co + 3) // 4
+    refp = np.zeros((B, cb * 4, H, W))
+    refp[:, :Co] = ref
+    rs = refp.reshape(B, cb, -1)
+    st = stats.cpu().numpy()
+    assert np.allclose(st[..., 0], rs.sum(-1), rtol=1e-5, atol=1e-4 * np.sqrt(rs.shape[-1]))
+    assert np.allclose(st[..., 1], (rs**2).sum(-1), rtol=1e-5)
+    assert np.allclose(csum.cpu().numpy(), refp.sum((2, 3)), rtol=1e-5, atol=1e-4 * np.sqrt(H * W))
+    if Co % 4:
+        assert np.all(out[:, -1, :, :, Co % 4:].cpu().numpy() == 0)
+
+
+@pytest.mark.parametrize("rpc", [1, 2, 5, 64])
+def test_conv_row_any_rows_per_cta(rpc, monkeypatch):
+    """The strip decomposition (rows per CTA) is a scheduling choice: results must not depend on it."""
+    import os, subprocess, sys
+    code = (
+        "import numpy as np, torch\n"
+        "from oracle import ref_numpy as RN\n"
+        "from pbml_mantle_convection_b200 import ops\n"
+        "r=np.random.default_rng(5); x=r.standard_normal((1,16,37,150)); w=r.standard_normal((16,16,3,3))/12; b=r.standard_normal(16)\n"
+        "cu=lambda a: torch.tensor(np.ascontiguousarray(a),dtype=torch.float32,device='cuda:0')\n"
+        "o,_,_=ops.conv_fwd([ops.Source(ops.pack_nchw(cu(x)))],ops.pack_conv_weight(cu(w),[16]),ops.pad_vec(cu(b),16,'cuda:0'),16,3,'replicate',impl='row_f16x2',wpk_row=ops.pack_conv_weight_row(cu(w),[16]))\n"
+        "y=ops.unpack_nchw(o,16).cpu().numpy(); ref=RN.conv2d_same(x,w,b,'replicate')\n"
+        "e=np.linalg.norm(y-ref)/np.linalg.norm(ref); print(e); assert e<3e-6\n")
+    env = dict(os.environ, PBMC_ROW_RPC=str(rpc))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+
+
 def test_conv_gelu_epilogue():
     r = rng(2)
     x, w, b = r.standard_normal((1, 16, 20, 30)), r.standard_normal((16, 16, 3, 3)) / 12, r.standard_normal(16)
@@ -147,7 +206,7 @@ def test_conv_gelu_epilogue():
     assert relerr(ops.unpack_nchw(out, 16).cpu().numpy(), ref) < 2e-6
 
 
-@pytest.mark.parametrize("impl", ["ffma", "umma_3xtf32", "umma_f16x2"])
+@pytest.mark.parametrize("impl", ["ffma", "umma_3xtf32", "umma_f16x2", "row_f16x2"])
 def test_fluid_layer_chain_with_fused_groupnorm_and_concat(impl):
     """conv -> [GN+GELU fused into the next load] -> conv over a 3-source concat (one plain source)."""
     r = rng(3)
@@ -163,10 +222,12 @@ def test_fluid_layer_chain_with_fused_groupnorm_and_concat(impl):
 
     x0b, xinb = ops.pack_nchw(cu(x0)), ops.pack_nchw(cu(xin))
     y1b, st1, _ = ops.conv_fwd([ops.Source(x0b)], ops.pack_conv_weight(cu(w1), [16]), ops.pad_vec(cu(b1), 16, DEV), 16, 3,
-                               "replicate", want_stats=True, impl=impl, wpk_umma=ops.pack_conv_weight_umma(cu(w1), [16]))
+                               "replicate", want_stats=True, impl=impl, wpk_umma=ops.pack_conv_weight_umma(cu(w1), [16]),
+                               wpk_row=ops.pack_conv_weight_row(cu(w1), [16]))
     srcs = [ops.Source(y1b, L.XFORM_GN_GELU, st1, cu(g1), cu(be1)), ops.Source(x0b), ops.Source(xinb)]
     out, _, _ = ops.conv_fwd(srcs, ops.pack_conv_weight(cu(w2), [16, 16, 7]), ops.pad_vec(cu(b2), 16, DEV), 16, 3,
-                             "replicate", impl=impl, wpk_umma=ops.pack_conv_weight_umma(cu(w2), [16, 16, 7]))
+                             "replicate", impl=impl, wpk_umma=ops.pack_conv_weight_umma(cu(w2), [16, 16, 7]),
+                             wpk_row=ops.pack_conv_weight_row(cu(w2), [16, 16, 7]))
     assert relerr(ops.unpack_nchw(out, 16).cpu().numpy(), ref) < 5e-6
     # stand-alone finalize == GN + GELU
     fin = ops.finalize_nchw(ops.Source(y1b, L.XFORM_GN_GELU, st1, cu(g1), cu(be1)), 16).cpu().numpy()
