@@ -32,7 +32,7 @@ def _digest():
     for f in files:
         with open(f, "rb") as fh:
             h.update(f.encode() + b"\0" + fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + os.environ.get("PBMC_EXTRA_NVCC_FLAGS", "")).encode())
     return h.hexdigest()
 
 
@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("PBMC_EXTRA_NVCC_FLAGS", "").split()
     objs = []
     procs = []
     for s in SOURCES:

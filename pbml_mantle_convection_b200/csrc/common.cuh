@@ -37,8 +37,27 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- device math
-// exact-erf GELU, nn.GELU() default (pytorch_networks_convae.py:751)
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact-erf GELU, nn.GELU() default (pytorch_networks_convae.py:751): x * Phi(x).
+// Branch-free evaluation: Phi(-t) = 2^q(t) for t = |x| with q a degree-9 minimax fit of log2(Phi(-t)) on
+// [0, 6.6] (absolute error of Phi < 3e-9 before rounding; x * Phi(-6.6) < 2e-10, so clamping t is exact in
+// fp32), Phi(x) = 1 - Phi(-x) for x > 0.  14 instructions instead of erff's two selected polynomials;
+// fp32 result within 1 ulp-of-|x| of the float64 value (tools/fit_gelu.py regenerates and checks the fit).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float t = fminf(fabsf(x), 6.6f);
+  float q = 4.4101555806984697e-07f;
+  q = fmaf(q, t, -8.559724437379595e-06f);
+  q = fmaf(q, t, 6.932390970346009e-05f);
+  q = fmaf(q, t, -0.00026762983147764706f);
+  q = fmaf(q, t, -1.2973447695787885e-05f);
+  q = fmaf(q, t, 0.006957729551776724f);
+  q = fmaf(q, t, -0.05244853666847913f);
+  q = fmaf(q, t, -0.4592179744839059f);
+  q = fmaf(q, t, -1.1511046056807646f);
+  q = fmaf(q, t, -0.9999999933766083f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return x * (x > 0.f ? 1.0f - e : e);
+}
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 

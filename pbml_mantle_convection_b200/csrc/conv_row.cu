@@ -19,11 +19,12 @@
 // i.e. k TMEM loads from the SAME lane -- no shuffles, no junk lanes, no halo columns in M.
 // D_r live in a TMEM ring of ND accumulators (N columns each).
 //
-// Warp roles (14 warps):  0-3 epilogue (TMEM lane quarter == warp),  4-11 producers (two groups of
-// 128 threads, one thread per position, alternate stages, register prefetch of the next stage),
-// 12 MMA issuer (one elected lane) + TMEM allocator,  13 halo producer (the k-1 extra positions).
+// Warp roles:  0-7 epilogue (two sets of 4 warps on alternate output rows; TMEM lane quarter = warp & 3),
+// 8 .. 8+4*NPG-1 producers (NPG groups of 128 threads, one thread per position plus the k-1 halo positions,
+// round-robin over stages, loads two stages ahead), last warp = MMA issuer (one elected lane) + TMEM allocator.
 // Pipelines: a_full/a_empty (producers <-> MMA, NSTAGE smem stages; one stage = one input row of one
-// 16-channel group), d_full/d_empty (MMA <-> epilogue, ND accumulators).
+// 16-channel group), d_full/d_empty (MMA <-> epilogue, ND accumulators; D_r is released by the k output
+// rows that read it).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -31,9 +32,10 @@
 
 namespace pbmc {
 
-constexpr int CR_MMA_WARP = 12;
-constexpr int CR_HALO_WARP = 13;
-constexpr int CR_THREADS = 14 * 32;
+constexpr int CR_EPI_WARPS = 8;                        // two sets of 4 (alternate output rows)
+constexpr int CR_NPG = 3;                              // producer groups (4 warps = 128 positions each)
+constexpr int CR_MMA_WARP = CR_EPI_WARPS + 4 * CR_NPG;  // warps 0-7 epilogue, 8 .. 8+4*NPG-1 producers, then the MMA issuer
+constexpr int CR_THREADS = (CR_MMA_WARP + 1) * 32;
 constexpr int CR_MAXG = 24;
 constexpr int CR_SMEM_HDR = 2176;
 
@@ -49,6 +51,8 @@ struct ConvRowParams {
   float* out;
   double* out_stats;
   double* out_chan_sum;
+  int dbg_dx;  // developer experiment: byte offset per dx tap (16 = correct)
+  unsigned long long* trace;  // developer timeline (PBMC_ROW_TRACE builds only), else NULL
 };
 
 struct RowGroup {
@@ -67,8 +71,10 @@ struct RowGeom {
   static constexpr int PLANE = (PWS + 7) / 8 * 8;   // positions per K-chunk plane (16 B each)
   static constexpr int PART_BYTES = 2 * PLANE * 16;  // two K chunks (8 channels each)
   static constexpr int STAGE_BYTES = PARTS * PART_BYTES;
-  static constexpr int NSTAGE = 4;
-  static constexpr int ND = KS == 3 ? 5 : 6;
+  static constexpr int NSTAGE = 8;
+  // accumulator ring: the MMA warp may run ND - KS rows ahead of the epilogue (measured with tools/probe:
+  // dependent accumulation into the same TMEM columns costs nothing, one N = 48 MMA is ~44 clk)
+  static constexpr int ND = KS == 3 ? 10 : 6;
   static constexpr uint32_t TMEM_COLS = ND * N <= 256 ? 256 : 512;
   static constexpr int B_TILE = 2 * N * 16;  // one (group, dx, part) operand: [2 chunks][N rows][16 B]
   static constexpr int B_GROUP = KS * PARTS * B_TILE;
@@ -76,6 +82,27 @@ struct RowGeom {
   static_assert(ND >= KS + 1, "the MMA must be able to run ahead of the epilogue");
 };
 
+#ifdef PBMC_ROW_TRACE
+#define CR_TR(slot)                                                                              \
+  do {                                                                                           \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (slot) < 4096) \
+      p.trace[(slot)] = clock64();                                                               \
+  } while (0)
+#else
+#define CR_TR(slot) \
+  do {              \
+  } while (0)
+#endif
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -95,7 +122,22 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t r[16]) {
                :
                : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CR_EPI_WARPS * 32) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+// non-blocking phase test
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 
 __host__ __device__ constexpr uint32_t row_idesc(uint32_t fmt, uint32_t n) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
@@ -112,10 +154,12 @@ template <int KS, int PARTS>
 __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_constant__ ConvRowParams p) {
   using G = RowGeom<KS, PARTS>;
   constexpr int P = G::P, N = G::N, NSTAGE = G::NSTAGE, ND = G::ND, PLANE = G::PLANE;
+  static_assert(8 * (2 * NSTAGE + 2 * ND) <= 448, "barrier area");
+  static_assert((NSTAGE & (NSTAGE - 1)) == 0, "NSTAGE must be a power of two");
   constexpr uint32_t FMT = PARTS == 2 ? 0u : 1u;  // fp16 hi|lo split, or one bf16 pass
   constexpr uint32_t IDESC = row_idesc(FMT, N);
   extern __shared__ __align__(128) unsigned char smem[];
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 448);  // barriers occupy [0, 8 * (2 NSTAGE + 2 ND))
   RowGroup* gtab = reinterpret_cast<RowGroup*>(smem + 512);
   double* red = reinterpret_cast<double*>(smem + 1152);
   unsigned char* Bs = smem + CR_SMEM_HDR;
@@ -131,23 +175,24 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
   const int nrows = min(p.rpc, H - y0);
   const int nin = nrows + KS - 1;
   const int NG = p.ngroups;
-  const int total = nin * NG;
+  const int total = nin * NG;  // stage st = (input row ri, 16-channel group g), row-major: st = ri * NG + g
   const size_t plane_px = (size_t)H * W;
   const uint32_t bar0 = smem_u32(smem);
-  auto a_full = [&](int s) { return bar0 + (uint32_t)s * 8u; };
-  auto a_empty = [&](int s) { return bar0 + (uint32_t)(NSTAGE + s) * 8u; };
-  auto d_full = [&](int d) { return bar0 + (uint32_t)(2 * NSTAGE + d) * 8u; };
-  auto d_empty = [&](int d) { return bar0 + (uint32_t)(2 * NSTAGE + ND + d) * 8u; };
+  auto a_full = [&](uint32_t s) { return bar0 + s * 8u; };
+  auto a_empty = [&](uint32_t s) { return bar0 + (uint32_t)(NSTAGE + s) * 8u; };
+  auto d_full = [&](uint32_t d) { return bar0 + (uint32_t)(2 * NSTAGE + d) * 8u; };
+  auto d_empty = [&](uint32_t d) { return bar0 + (uint32_t)(2 * NSTAGE + ND + d) * 8u; };
 
   // ---- one-time setup
   if (tid == 0) {
+    CR_TR(0);
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(a_full(s), 5);   // 4 producer warps + the halo warp
+      mbar_init(a_full(s), 4);   // the 4 warps of the producer group that owns the stage
       mbar_init(a_empty(s), 1);  // tcgen05.commit
     }
     for (int d = 0; d < ND; ++d) {
-      mbar_init(d_full(d), 1);   // tcgen05.commit
-      mbar_init(d_empty(d), 4);  // 4 epilogue warps
+      mbar_init(d_full(d), 1);        // tcgen05.commit
+      mbar_init(d_empty(d), 4 * KS);  // 4 epilogue warps x the KS output rows that read D_d
     }
     fence_mbar_init();
     int g = 0, c0 = 0;
@@ -188,34 +233,53 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) CR_TR(1);
 
-  if (warp < 4) {
-    // ================================================================ epilogue
-    const int col = warp * 32 + lane, gx = x0 + col;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  if (warp < CR_EPI_WARPS) {
+    // ================================================================ epilogue: two sets of 4 warps,
+    // set e takes output rows yo = e, e+2, ...; thread = output column (TMEM lane quarter = warp & 3)
+    const int eset = warp >> 2, q = warp & 3;
+    const int col = q * 32 + lane, gx = x0 + col;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     float bias[16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int qb = 0; qb < 4; ++qb) {
       float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q < p.cout_blks) bq = ldg4(p.bias + q * 4);
-      bias[q * 4 + 0] = bq.x; bias[q * 4 + 1] = bq.y; bias[q * 4 + 2] = bq.z; bias[q * 4 + 3] = bq.w;
+      if (qb < p.cout_blks) bq = ldg4(p.bias + qb * 4);
+      bias[qb * 4 + 0] = bq.x; bias[qb * 4 + 1] = bq.y; bias[qb * 4 + 2] = bq.z; bias[qb * 4 + 3] = bq.w;
     }
-    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, cs[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) cs[c] = 0.f;
-    for (int yo = 0; yo < nrows; ++yo) {
-      const int rl = yo + KS - 1;  // the last input row this output row needs (commits are in order)
-      mbar_wait(d_full(rl % ND), (uint32_t)(rl / ND) & 1u);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};  // zero-mean sums: only the c_out <= 4 head conv asks for them
+    const bool want_cs = p.out_chan_sum != nullptr;
+    float* orow = p.out + (((size_t)b * p.cout_blks) * plane_px + (size_t)(y0 + eset) * W + gx) * 4;
+    const size_t blk_stride = plane_px * 4, row_stride = (size_t)2 * W * 4;
+    // ring positions advance by 2 rows per iteration (ND is even: a set always sees the same slot parity class)
+    uint32_t s_lo = (uint32_t)eset % ND, s_hi = (uint32_t)(eset + KS - 1) % ND, par_hi = ((uint32_t)(eset + KS - 1) / ND) & 1u;
+    for (int yo = eset; yo < nrows; yo += 2) {
+      mbar_wait(d_full(s_hi), par_hi);  // the last input row this output row needs (commits are in order)
       tc_fence_after();
+      if ((tid & 127) == 0) CR_TR(1200 + 3 * yo);
       uint32_t r[KS][16];
+      uint32_t sl = s_lo;
 #pragma unroll
-      for (int dy = 0; dy < KS; ++dy) tmem_ld16_issue(lane_addr + (uint32_t)(((yo + dy) % ND) * N + dy * 16), r[dy]);
+      for (int dy = 0; dy < KS; ++dy) {
+        tmem_ld16_issue(lane_addr + sl * (uint32_t)N + (uint32_t)(dy * 16), r[dy]);
+        if (++sl == (uint32_t)ND) sl = 0;
+      }
 #pragma unroll
       for (int dy = 0; dy < KS; ++dy) tmem_ld_wait16(r[dy]);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(d_empty(yo % ND));  // D_yo has now been read by all of its k consumers
-      const int gy = y0 + yo;
+      if (lane == 0) {
+        // D_{yo+dy} is read by output rows yo+dy-KS+1 .. yo+dy; rows < 0 do not exist, so row 0 arrives for them
+        sl = s_lo;
+#pragma unroll
+        for (int dy = 0; dy < KS; ++dy) {
+          mbar_arrive_n(d_empty(sl), yo == 0 ? (uint32_t)(KS - dy) : 1u);
+          if (++sl == (uint32_t)ND) sl = 0;
+        }
+      }
+      if ((tid & 127) == 0) CR_TR(1201 + 3 * yo);
       if (gx < W) {
 #pragma unroll
         for (int qb = 0; qb < 4; ++qb) {
@@ -229,16 +293,20 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
               a += bias[qb * 4 + e];
               if (p.epi_act == PBMC_ACT_GELU) a = gelu_erf(a);
               o[e] = a;
-              cs[qb * 4 + e] += a;
             }
-            *reinterpret_cast<float4*>(p.out + (((size_t)b * p.cout_blks + qb) * plane_px + (size_t)gy * W + gx) * 4) =
-                make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(orow + qb * blk_stride) = make_float4(o[0], o[1], o[2], o[3]);
             s1[qb] += (o[0] + o[1]) + (o[2] + o[3]);
-            s2[qb] += (o[0] * o[0] + o[1] * o[1]) + (o[2] * o[2] + o[3] * o[3]);
+            s2[qb] = fmaf(o[0], o[0], fmaf(o[1], o[1], fmaf(o[2], o[2], fmaf(o[3], o[3], s2[qb]))));
+            if (qb == 0 && want_cs) { cs[0] += o[0]; cs[1] += o[1]; cs[2] += o[2]; cs[3] += o[3]; }
           }
         }
       }
+      orow += row_stride;
+      s_lo += 2; if (s_lo >= (uint32_t)ND) s_lo -= ND;
+      s_hi += 2; if (s_hi >= (uint32_t)ND) { s_hi -= ND; par_hi ^= 1u; }
+      if ((tid & 127) == 0) CR_TR(1202 + 3 * yo);
     }
+    if (tid == 0) CR_TR(3);
     if (p.out_stats != nullptr) {
 #pragma unroll
       for (int qb = 0; qb < 4; ++qb) {
@@ -249,61 +317,117 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
       epi_bar_sync();
       if (tid < 8 && (tid >> 1) < p.cout_blks) {
         double t = 0.0;
-        for (int w = 0; w < 4; ++w) t += red[(w * 4 + (tid >> 1)) * 2 + (tid & 1)];
+        for (int w = 0; w < CR_EPI_WARPS; ++w) t += red[(w * 4 + (tid >> 1)) * 2 + (tid & 1)];
         atomicAdd(p.out_stats + ((size_t)b * p.cout_blks + (tid >> 1)) * 2 + (tid & 1), t);
       }
       epi_bar_sync();
     }
-    if (p.out_chan_sum != nullptr) {
+    if (want_cs) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
+      for (int c = 0; c < 4; ++c) {
         const double a = warp_sum((double)cs[c]);
-        if (lane == 0) red[warp * 16 + c] = a;
+        if (lane == 0) red[warp * 4 + c] = a;
       }
       epi_bar_sync();
-      if (tid < p.cout_blks * 4) {
+      if (tid < 4) {
         double t = 0.0;
-        for (int w = 0; w < 4; ++w) t += red[w * 16 + tid];
-        atomicAdd(p.out_chan_sum + (size_t)b * p.cout_blks * 4 + tid, t);
+        for (int w = 0; w < CR_EPI_WARPS; ++w) t += red[w * 4 + tid];
+        atomicAdd(p.out_chan_sum + (size_t)b * 4 + tid, t);
       }
     }
   } else if (warp < CR_MMA_WARP) {
-    // ================================================================ producers (one thread per position)
-    const int pg = (warp - 4) >> 2;
-    const int i = ((warp - 4) & 3) * 32 + lane;
+    // ================================================================ producers: NPG groups of 128 threads,
+    // one thread per position; group pg owns stages pg, pg + NPG, ...  Warp 0 of a group also produces the
+    // KS-1 halo positions (one channel per lane).  Loads run TWO stages ahead and are issued right after
+    // the stage's fence: fence.proxy.async is MEMBAR + FENCE.VIEW.ASYNC, and the MEMBAR would otherwise wait
+    // for freshly issued prefetch loads.
+    const int pw = warp - CR_EPI_WARPS;
+    const int pg = pw >> 2, wq = pw & 3;
+    const int i = wq * 32 + lane;
     const int gxp = x0 - P + i;
     const int sx = pad_index(gxp, W, p.pad_mode);
     const bool col_ok = gxp < W + P && sx >= 0;  // columns past the image feed masked outputs only
-    float4 cur[4], nxt[4];
-    bool ok_cur = false, ok_nxt = false;
-    auto load_stage = [&](int st, float4 (&r)[4]) -> bool {
-      const int ri = st / NG, g = st - ri * NG;
+    constexpr int HITEMS = ((KS - 1) * 16 + 31) / 32;
+    const bool tr_lane = lane == 0 && wq == 0;
+    (void)tr_lane;
+    int hsx[HITEMS];
+    bool hok[HITEMS];
+#pragma unroll
+    for (int k = 0; k < HITEMS; ++k) {
+      const int item = lane + 32 * k, e = item >> 4;
+      const int gxh = x0 - P + 128 + e;
+      hsx[k] = pad_index(gxh, W, p.pad_mode);
+      hok[k] = wq == 0 && e < KS - 1 && gxh < W + P && hsx[k] >= 0;
+    }
+    struct Buf {
+      float4 v[4];
+      float h[HITEMS];
+      bool ok;
+    };
+    auto load_stage = [&](int ri, int g, Buf& B) {
       const int sy = pad_index(y0 - P + ri, H, p.pad_mode);
-      const bool ok = col_ok && sy >= 0;
       const RowGroup gi = gtab[g];
+      B.ok = sy >= 0;
+      const bool ok = col_ok && sy >= 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && j < gi.nb) r[j] = ldg4(gi.base + ((size_t)j * plane_px + (size_t)sy * W + sx) * 4);
+        B.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && j < gi.nb) B.v[j] = ldg4(gi.base + ((size_t)j * plane_px + (size_t)sy * W + sx) * 4);
       }
-      return ok;
+#pragma unroll
+      for (int k = 0; k < HITEMS; ++k) {
+        const int ch = (lane + 32 * k) & 15;
+        B.h[k] = 0.f;
+        if (hok[k] && sy >= 0 && (ch >> 2) < gi.nb)
+          B.h[k] = __ldg(gi.base + ((size_t)(ch >> 2) * plane_px + (size_t)sy * W + hsx[k]) * 4 + (ch & 3));
+      }
     };
-    int st = pg;
-    if (st < total) ok_cur = load_stage(st, cur);
-    for (; st < total; st += 2) {
-      if (st + 2 < total) ok_nxt = load_stage(st + 2, nxt);
-      const int ri = st / NG, g = st - ri * NG;
+    auto process = [&](int st, int g, Buf& B) {
+      if (tr_lane) CR_TR(100 + pg * 300 + 4 * (st / CR_NPG));
       const RowGroup gi = gtab[g];
       float v[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float4 t = cur[j];
-        if (ok_cur && j < gi.nb) t = xform4(t, xf_a + gi.chan0 + 4 * j, xf_b + gi.chan0 + 4 * j, gi.xform);
-        v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        v[4 * j + 0] = B.v[j].x; v[4 * j + 1] = B.v[j].y; v[4 * j + 2] = B.v[j].z; v[4 * j + 3] = B.v[j].w;
       }
-      const int slot = st % NSTAGE;
-      uint4* stage = reinterpret_cast<uint4*>(As + (size_t)slot * G::STAGE_BYTES);
-      mbar_wait(a_empty(slot), ((uint32_t)(st / NSTAGE) & 1u) ^ 1u);
+      float hv[HITEMS];
+#pragma unroll
+      for (int k = 0; k < HITEMS; ++k) hv[k] = B.h[k];
+      if (B.ok && gi.xform != PBMC_XFORM_NONE) {
+        const float4* a4 = reinterpret_cast<const float4*>(xf_a + gi.chan0);
+        const float4* b4 = reinterpret_cast<const float4*>(xf_b + gi.chan0);
+        const bool do_gn = gi.xform != PBMC_XFORM_GELU, do_gelu = gi.xform != PBMC_XFORM_GN;
+        if (col_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < gi.nb) {  // absent blocks of a partial group stay exactly zero
+              if (do_gn) {
+                const float4 a = a4[j], bb = b4[j];
+                v[4 * j + 0] = fmaf(v[4 * j + 0], a.x, bb.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, bb.y);
+                v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, bb.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, bb.w);
+              }
+              if (do_gelu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[4 * j + e] = gelu_erf(v[4 * j + e]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < HITEMS; ++k) {
+          const int ch = (lane + 32 * k) & 15;
+          if (hok[k] && (ch >> 2) < gi.nb) {
+            if (do_gn) hv[k] = fmaf(hv[k], xf_a[gi.chan0 + ch], xf_b[gi.chan0 + ch]);
+            if (do_gelu) hv[k] = gelu_erf(hv[k]);
+          }
+        }
+      }
+      const uint32_t slot = (uint32_t)st & (NSTAGE - 1);
+      unsigned char* stage_b = As + (size_t)slot * G::STAGE_BYTES;
+      uint4* stage = reinterpret_cast<uint4*>(stage_b);
+      if (tr_lane) CR_TR(101 + pg * 300 + 4 * (st / CR_NPG));
+      mbar_wait(a_empty(slot), (((uint32_t)st / NSTAGE) & 1u) ^ 1u);
+      if (tr_lane) CR_TR(102 + pg * 300 + 4 * (st / CR_NPG));
       if (PARTS == 2) {
         uint4 h0, l0, h1, l1;
         split_f16(v, h0, l0);
@@ -316,107 +440,112 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         stage[i] = pack_bf16(v);
         stage[PLANE + i] = pack_bf16(v + 8);
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full(slot));
+      if (wq == 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
-      ok_cur = ok_nxt;
-    }
-  } else if (warp == CR_MMA_WARP) {
-    // ================================================================ MMA issuer
-    if (lane == 0) {
-      const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
-      constexpr uint32_t A_LBO = PLANE * 16, B_LBO = N * 16, SBO = 128;
-      int st = 0;
-      for (int ri = 0; ri < nin; ++ri) {
-        const int ds = ri % ND;
-        mbar_wait(d_empty(ds), ((uint32_t)(ri / ND) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t dcol = tmem_base + (uint32_t)(ds * N);
-        for (int g = 0; g < NG; ++g, ++st) {
-          const int slot = st % NSTAGE;
-          mbar_wait(a_full(slot), (uint32_t)(st / NSTAGE) & 1u);
-          tc_fence_after();
-          const uint32_t a_st = a_base + (uint32_t)slot * G::STAGE_BYTES;
-          const uint32_t b_g = b_base + (uint32_t)g * G::B_GROUP;
-#pragma unroll
-          for (int dx = 0; dx < KS; ++dx) {
-            const uint64_t a_hi = umma_desc(a_st + (uint32_t)dx * 16, A_LBO, SBO);
-            const uint64_t b_hi = umma_desc(b_g + (uint32_t)(dx * PARTS) * G::B_TILE, B_LBO, SBO);
-            umma_ss<1>(dcol, a_hi, b_hi, IDESC, (g == 0 && dx == 0) ? 0u : 1u);
+        for (int k = 0; k < HITEMS; ++k) {
+          const int item = lane + 32 * k, e = item >> 4, ch = item & 15;
+          if (e < KS - 1) {
+            const size_t off = ((size_t)(ch >> 3) * PLANE + 128 + e) * 16 + (size_t)(ch & 7) * 2;
             if (PARTS == 2) {
-              const uint64_t a_lo = umma_desc(a_st + G::PART_BYTES + (uint32_t)dx * 16, A_LBO, SBO);
-              const uint64_t b_lo = umma_desc(b_g + (uint32_t)(dx * PARTS + 1) * G::B_TILE, B_LBO, SBO);
-              umma_ss<1>(dcol, a_lo, b_hi, IDESC, 1u);
-              umma_ss<1>(dcol, a_hi, b_lo, IDESC, 1u);
+              const __half h = __float2half_rn(hv[k]);
+              const __half l = __float2half_rn(hv[k] - __half2float(h));
+              *reinterpret_cast<__half*>(stage_b + off) = h;
+              *reinterpret_cast<__half*>(stage_b + G::PART_BYTES + off) = l;
+            } else {
+              *reinterpret_cast<__nv_bfloat16*>(stage_b + off) = __float2bfloat16_rn(hv[k]);
             }
           }
-          umma_commit(a_empty(slot));  // frees the smem stage once these MMAs have read it
-        }
-        umma_commit(d_full(ds));  // D_ri complete
-      }
-    }
-    __syncwarp();
-  } else {
-    // ================================================================ halo producer: positions 128 .. 128+k-2
-    constexpr int ITEMS = ((KS - 1) * 16 + 31) / 32;
-    float cur[ITEMS], nxt[ITEMS];
-    auto load_stage = [&](int st, float (&r)[ITEMS]) {
-      const int ri = st / NG, g = st - ri * NG;
-      const int sy = pad_index(y0 - P + ri, H, p.pad_mode);
-      const RowGroup gi = gtab[g];
-#pragma unroll
-      for (int k = 0; k < ITEMS; ++k) {
-        const int item = lane + 32 * k, e = item >> 4, ch = item & 15;
-        const int gxp = x0 - P + 128 + e;
-        const int sx = pad_index(gxp, W, p.pad_mode);
-        const bool ok = e < KS - 1 && gxp < W + P && sx >= 0 && sy >= 0 && (ch >> 2) < gi.nb;
-        float val = 0.f;
-        if (ok) {
-          val = __ldg(gi.base + ((size_t)(ch >> 2) * plane_px + (size_t)sy * W + sx) * 4 + (ch & 3));
-          val = xform1(val, xf_a[gi.chan0 + ch], xf_b[gi.chan0 + ch], gi.xform);
-        }
-        r[k] = val;
-      }
-    };
-    if (total > 0) load_stage(0, cur);
-    for (int st = 0; st < total; ++st) {
-      if (st + 1 < total) load_stage(st + 1, nxt);
-      const int slot = st % NSTAGE;
-      unsigned char* stage = As + (size_t)slot * G::STAGE_BYTES;
-      mbar_wait(a_empty(slot), ((uint32_t)(st / NSTAGE) & 1u) ^ 1u);
-#pragma unroll
-      for (int k = 0; k < ITEMS; ++k) {
-        const int item = lane + 32 * k, e = item >> 4, ch = item & 15;
-        if (e < KS - 1) {
-          const size_t off = ((size_t)(ch >> 3) * PLANE + 128 + e) * 16 + (size_t)(ch & 7) * 2;
-          if (PARTS == 2) {
-            const __half h = __float2half_rn(cur[k]);
-            const __half l = __float2half_rn(cur[k] - __half2float(h));
-            *reinterpret_cast<__half*>(stage + off) = h;
-            *reinterpret_cast<__half*>(stage + G::PART_BYTES + off) = l;
-          } else {
-            *reinterpret_cast<__nv_bfloat16*>(stage + off) = __float2bfloat16_rn(cur[k]);
-          }
         }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(slot));
-#pragma unroll
-      for (int k = 0; k < ITEMS; ++k) cur[k] = nxt[k];
+      if (tr_lane) CR_TR(103 + pg * 300 + 4 * (st / CR_NPG));
+    };
+    auto advance = [&](int& ri, int& g) {
+      g += CR_NPG;
+      while (g >= NG) { g -= NG; ++ri; }
+    };
+    Buf b0, b1;
+    int cg = pg, cri = 0;  // (row, group) of the stage processed next
+    while (cg >= NG) { cg -= NG; ++cri; }
+    int lri = cri, lg = cg;  // (row, group) of the stage loaded next
+    if (pg < total) load_stage(lri, lg, b0);
+    advance(lri, lg);
+    if (pg + CR_NPG < total) load_stage(lri, lg, b1);
+    advance(lri, lg);
+    for (int st = pg; st < total; st += 2 * CR_NPG) {
+      process(st, cg, b0);
+      if (st + 2 * CR_NPG < total) load_stage(lri, lg, b0);
+      advance(lri, lg);
+      advance(cri, cg);
+      if (st + CR_NPG < total) {
+        process(st + CR_NPG, cg, b1);
+        if (st + 3 * CR_NPG < total) load_stage(lri, lg, b1);
+        advance(lri, lg);
+        advance(cri, cg);
+      }
     }
+  } else {
+    // ================================================================ MMA issuer
+    // The whole warp walks the (uniform) pipeline state; one elected lane issues tcgen05.mma / commit.
+    // This warp's serial instruction stream bounds the stage rate, so everything is incremental: descriptors
+    // are base + small constant (the 14-bit address field cannot carry: smem < 256 KB), and the barrier of
+    // the NEXT stage is tested (non-blocking) before the current stage's MMAs are issued, so its latency hides
+    // behind the (back-pressured, ~400 clk) issue of 9 MMAs.
+    const bool leader = elect_one();
+    constexpr uint32_t A_LBO = PLANE * 16, B_LBO = N * 16, SBO = 128;
+    const uint64_t a_desc0 = umma_desc(smem_u32(As), A_LBO, SBO), b_desc0 = umma_desc(smem_u32(Bs), B_LBO, SBO);
+    const uint32_t dx_step = (uint32_t)p.dbg_dx >> 4;
+    uint32_t ds = 0, d_par = 0;
+    int st = 0;
+    bool ready = total > 0 && mbar_test(a_full(0), 0u);
+    for (int ri = 0; ri < nin; ++ri) {
+      if (ri >= ND) mbar_wait(d_empty(ds), d_par ^ 1u);  // first ND rows: the ring is free
+      const uint32_t dcol = tmem_base + ds * (uint32_t)N;
+      for (int g = 0; g < NG; ++g, ++st) {
+        const uint32_t slot = (uint32_t)st & (NSTAGE - 1);
+        if (!ready) mbar_wait(a_full(slot), ((uint32_t)st / NSTAGE) & 1u);
+        tc_fence_after();
+        ready = (st + 1 < total) && mbar_test(a_full((uint32_t)(st + 1) & (NSTAGE - 1)), ((uint32_t)(st + 1) / NSTAGE) & 1u);
+        if (leader) {
+          CR_TR(1400 + 2 * st);
+          const uint64_t a_s = a_desc0 + (uint64_t)(slot * (uint32_t)(G::STAGE_BYTES >> 4));
+          const uint64_t b_s = b_desc0 + (uint64_t)((uint32_t)g * (uint32_t)(G::B_GROUP >> 4));
+#pragma unroll
+          for (int dx = 0; dx < KS; ++dx) {
+            const uint64_t a_hi = a_s + (uint64_t)(dx * dx_step);
+            const uint64_t b_hi = b_s + (uint64_t)(dx * PARTS * (G::B_TILE >> 4));
+            umma_ss<1>(dcol, a_hi, b_hi, IDESC, (uint32_t)(g | dx));
+            if (PARTS == 2) {
+              umma_ss<1>(dcol, a_hi + (uint64_t)(G::PART_BYTES >> 4), b_hi, IDESC, 1u);
+              umma_ss<1>(dcol, a_hi, b_hi + (uint64_t)(G::B_TILE >> 4), IDESC, 1u);
+            }
+          }
+          umma_commit(a_empty(slot));                // frees the smem stage once these MMAs have read it
+          if (g == NG - 1) umma_commit(d_full(ds));  // D_ri complete
+          CR_TR(1401 + 2 * st);
+        }
+      }
+      if (++ds == (uint32_t)ND) { ds = 0; d_par ^= 1u; }
+    }
+    __syncwarp();
   }
 
   // ---- teardown
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) CR_TR(2);
   if (warp == CR_MMA_WARP) {
     __syncwarp();
     tmem_dealloc(tmem_base, G::TMEM_COLS);
   }
 }
+
+#ifdef PBMC_ROW_TRACE
+static unsigned long long* g_row_trace = nullptr;
+extern "C" void pbmc_debug_set_row_trace(void* dev_buf) { g_row_trace = reinterpret_cast<unsigned long long*>(dev_buf); }
+#endif
 
 // rows per CTA: minimise waves * (rows + halo + fixed per-CTA cost in row units)
 static int choose_rpc(int units, int H, int ks) {
@@ -461,13 +590,14 @@ static int row_groups(const pbmc_conv_desc& d) {
 bool conv_row_supported(const pbmc_conv_desc& d) {
   if (d.ksize != 3 && d.ksize != 5) return false;
   if (d.cout > 16) return false;
+  if (d.out_chan_sum != nullptr && d.cout > 4) return false;  // per-channel sums: head conv only
   const int ng = row_groups(d);
   if (ng > CR_MAXG) return false;
   int cin = 0;
   for (int s = 0; s < d.nsrc; ++s) cin += d.src[s].nblk * 4;
   const size_t n = (size_t)d.ksize * 16, b_group = (size_t)d.ksize * 2 * (2 * n * 16);
   const size_t plane = ((128 + d.ksize - 1) + 7) / 8 * 8;
-  const size_t smem = CR_SMEM_HDR + ng * b_group + 4 * (2 * 2 * plane * 16) + (size_t)cin * 8;
+  const size_t smem = CR_SMEM_HDR + ng * b_group + 8 * (2 * 2 * plane * 16) + (size_t)cin * 8;
   return smem <= 227 * 1024;
 }
 
@@ -486,6 +616,11 @@ int conv_row_dispatch(const pbmc_conv_desc& d, cudaStream_t st) {
   p.ngroups = row_groups(d);
   p.cin_ch = cin;
   p.rpc = 1;
+  p.trace = nullptr;
+  p.dbg_dx = getenv("PBMC_ROW_DBG_DX") ? atoi(getenv("PBMC_ROW_DBG_DX")) : 16;
+#ifdef PBMC_ROW_TRACE
+  p.trace = g_row_trace;
+#endif
   p.bias = d.bias; p.out = d.out; p.out_stats = d.out_stats; p.out_chan_sum = d.out_chan_sum;
   const char* base = reinterpret_cast<const char*>(d.wpk_row);
   if (!base) return PBMC_ERR_NULL_POINTER;

@@ -108,7 +108,7 @@ def row_supported(cout: int, ksize: int, src_channels) -> bool:
     groups = sum((nblk(c) + 3) // 4 for c in src_channels)
     n = ksize * 16
     plane = (128 + ksize - 1 + 7) // 8 * 8
-    smem = 2176 + groups * ksize * 2 * (2 * n * 16) + 4 * (2 * 2 * plane * 16) + sum(nblk(c) * 4 for c in src_channels) * 8
+    smem = 2176 + groups * ksize * 2 * (2 * n * 16) + 8 * (2 * 2 * plane * 16) + sum(nblk(c) * 4 for c in src_channels) * 8
     return groups <= 24 and smem <= 227 * 1024
 
 

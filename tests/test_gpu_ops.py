@@ -160,8 +160,9 @@ def test_conv_row(case, impl, tol):
     ref = RN.conv2d_same(x, w, b, pad)
     assert ops.row_supported(Co, k, [Ci])
     wpk, wrow = ops.pack_conv_weight(cu(w), [Ci]), ops.pack_conv_weight_row(cu(w), [Ci])
+    want_cs = Co <= 4  # the row kernel produces the zero-mean channel sums only for the (c_out <= 4) head conv
     out, stats, csum = ops.conv_fwd([ops.Source(ops.pack_nchw(cu(x)))], wpk, ops.pad_vec(cu(b), Co, DEV), Co, k, pad,
-                                    want_stats=True, want_chan_sum=True, impl=impl, wpk_row=wrow)
+                                    want_stats=True, want_chan_sum=want_cs, impl=impl, wpk_row=wrow)
     y = ops.unpack_nchw(out, Co).cpu().numpy()
     assert relerr(y, ref) < tol, relerr(y, ref)
     if impl == "row_bf16":
@@ -173,7 +174,8 @@ def test_conv_row(case, impl, tol):
     st = stats.cpu().numpy()
     assert np.allclose(st[..., 0], rs.sum(-1), rtol=1e-5, atol=1e-4 * np.sqrt(rs.shape[-1]))
     assert np.allclose(st[..., 1], (rs**2).sum(-1), rtol=1e-5)
-    assert np.allclose(csum.cpu().numpy(), refp.sum((2, 3)), rtol=1e-5, atol=1e-4 * np.sqrt(H * W))
+    if want_cs:
+        assert np.allclose(csum.cpu().numpy(), refp.sum((2, 3)), rtol=1e-5, atol=1e-4 * np.sqrt(H * W))
     if Co % 4:
         assert np.all(out[:, -1, :, :, Co % 4:].cpu().numpy() == 0)
 
