@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
   extern __shared__ __align__(128) unsigned char smem[];
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 448);  // barriers occupy [0, 8 * (2 NSTAGE + 2 ND))
   RowGroup* gtab = reinterpret_cast<RowGroup*>(smem + 512);
-  double* red = reinterpret_cast<double*>(smem + 1152);
+  double* red = reinterpret_cast<double*>(smem + 1152);             // 8 warps x 8 doubles
+  float* bias_s = reinterpret_cast<float*>(smem + 1152 + 512);      // 16 floats (zero padded)
   unsigned char* Bs = smem + CR_SMEM_HDR;
   unsigned char* As = Bs + (size_t)p.ngroups * G::B_GROUP;
   float* xf_a = reinterpret_cast<float*>(As + NSTAGE * G::STAGE_BYTES);
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
       }
       c0 += S.nblk * 4;
     }
+    if (tid < 16) bias_s[tid] = tid < p.cout_blks * 4 ? __ldg(p.bias + tid) : 0.f;
     const uint4* wsrc = reinterpret_cast<const uint4*>(p.wpk);
     uint4* wdst = reinterpret_cast<uint4*>(Bs);
     for (int e = tid; e < NG * (G::B_GROUP / 16); e += CR_THREADS) wdst[e] = __ldg(wsrc + e);
@@ -241,13 +243,6 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     const int eset = warp >> 2, q = warp & 3;
     const int col = q * 32 + lane, gx = x0 + col;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float bias[16];
-#pragma unroll
-    for (int qb = 0; qb < 4; ++qb) {
-      float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (qb < p.cout_blks) bq = ldg4(p.bias + qb * 4);
-      bias[qb * 4 + 0] = bq.x; bias[qb * 4 + 1] = bq.y; bias[qb * 4 + 2] = bq.z; bias[qb * 4 + 3] = bq.w;
-    }
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     float cs[4] = {0.f, 0.f, 0.f, 0.f};  // zero-mean sums: only the c_out <= 4 head conv asks for them
     const bool want_cs = p.out_chan_sum != nullptr;
@@ -256,7 +251,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     // ring positions advance by 2 rows per iteration (ND is even: a set always sees the same slot parity class)
     uint32_t s_lo = (uint32_t)eset % ND, s_hi = (uint32_t)(eset + KS - 1) % ND, par_hi = ((uint32_t)(eset + KS - 1) / ND) & 1u;
     for (int yo = eset; yo < nrows; yo += 2) {
-      mbar_wait(d_full(s_hi), par_hi);  // the last input row this output row needs (commits are in order)
+      mbar_wait_parked(d_full(s_hi), par_hi);  // the last input row this output row needs (commits are in order)
       tc_fence_after();
       if ((tid & 127) == 0) CR_TR(1200 + 3 * yo);
       uint32_t r[KS][16];
@@ -284,13 +279,15 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
 #pragma unroll
         for (int qb = 0; qb < 4; ++qb) {
           if (qb < p.cout_blks) {
+            const float4 bq = reinterpret_cast<const float4*>(bias_s)[qb];
+            const float bias4[4] = {bq.x, bq.y, bq.z, bq.w};
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float a = __uint_as_float(r[0][qb * 4 + e]);
 #pragma unroll
               for (int dy = 1; dy < KS; ++dy) a += __uint_as_float(r[dy][qb * 4 + e]);
-              a += bias[qb * 4 + e];
+              a += bias4[e];
               if (p.epi_act == PBMC_ACT_GELU) a = gelu_erf(a);
               o[e] = a;
             }
@@ -426,7 +423,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
       unsigned char* stage_b = As + (size_t)slot * G::STAGE_BYTES;
       uint4* stage = reinterpret_cast<uint4*>(stage_b);
       if (tr_lane) CR_TR(101 + pg * 300 + 4 * (st / CR_NPG));
-      mbar_wait(a_empty(slot), (((uint32_t)st / NSTAGE) & 1u) ^ 1u);
+      mbar_wait_parked(a_empty(slot), (((uint32_t)st / NSTAGE) & 1u) ^ 1u);
       if (tr_lane) CR_TR(102 + pg * 300 + 4 * (st / CR_NPG));
       if (PARTS == 2) {
         uint4 h0, l0, h1, l1;

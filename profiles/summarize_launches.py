@@ -13,6 +13,9 @@ def main(path, step_index=3):
     ki, vi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
     seq = [(r[ki], float(r[vi].replace(",", "")), r[gi]) for r in data if len(r) > vi]
     idx = [i for i, (n, _, _) in enumerate(seq) if "build_input" in n]
+    if len(idx) < 2:
+        raise SystemExit(f"need two build_input launches to delimit a step; the capture has {len(idx)} (skip more warm-up launches: ncu -s)")
+    step_index = min(step_index, len(idx) - 2)
     step = seq[idx[step_index]:idx[step_index + 1]]
     own = [s for s in step if "pbmc::" in s[0]]
     tot = sum(v for _, v, _ in own)

@@ -112,6 +112,35 @@ def test_TS_dropin_unmodified_reference_128x506():
     assert np.abs(V[0, 0].cpu().numpy() - g["V5"]).max() < 2e-5  # float32 exp of z ~ -20..0
 
 
+def test_TS_cached_graph_path_equals_eager_and_tracks_arguments():
+    """TS.forward replays one CUDA graph from the second call on (cached buffers).  Every call must still
+    see ITS arguments (new T, new Ra), return tensors the caller owns, and equal the eager path bit for bit."""
+    g = load("roll64x96")
+    spec = RN.NetSpec(levels=4)
+    net = make_net(spec, load_weights("roll64x96"), impl="auto")
+    mk = lambda: P.TS(net, P.ADNet(DEV, CN_max=0.99), DEV, ts=2, scale=True, p_pred=True, net="newfluidnet")
+    ts_g, ts_e = mk(), mk()
+    ts_e.use_cuda_graph = False
+    T0 = g["T0"]
+    T1 = np.clip(T0 + 0.05 * np.sin(np.arange(T0.shape[1]) / 7.0)[None, :], 0.0, 1.0)
+    P2 = (3.2, 2.0e7, 5.0)
+    calls = [(T0, PARAMS), (T1, PARAMS), (T0, P2), (T1, P2), (T0, PARAMS)]
+    kept = []
+    for T, prm in calls:
+        a = _ts_call(ts_g, T, g["xc"], g["yc"], params=prm)
+        b = _ts_call(ts_e, T, g["xc"], g["yc"], params=prm)
+        for ta, tb in [(a[0][1], b[0][1]), (a[0][2], b[0][2]), (a[2], b[2]), (a[3], b[3]), (a[4], b[4]), (a[5], b[5]),
+                       (a[1][1], b[1][1]), (a[1][2], b[1][2])]:
+            assert ta.dtype == torch.float64 and torch.equal(ta, tb)
+        kept.append((a[0][2].clone(), a[0][2]))
+    assert ts_g._plan.graph is not None and ts_e._plan.graph is None
+    for snap, live in kept:  # results of earlier calls were not overwritten by later replays
+        assert torch.equal(snap, live)
+    # different arguments gave different results (the graph did not freeze its first inputs)
+    assert not torch.equal(kept[0][1], kept[1][1]) and not torch.equal(kept[0][1], kept[2][1])
+    assert torch.equal(kept[0][1], kept[4][1])
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 def test_rollout_100_steps_diagnostics(impl):
     """BASELINE config 1 (128x128, 100 steps): T fields and mean-T / profile diagnostics vs the reference."""
