@@ -27,6 +27,8 @@
 // rows that read it).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -52,6 +54,7 @@ struct ConvRowParams {
   double* out_stats;
   double* out_chan_sum;
   int dbg_dx;  // developer experiment: byte offset per dx tap (16 = correct)
+  int dbg_flags;  // developer experiment bits, see CR_DBG
   unsigned long long* trace;  // developer timeline (PBMC_ROW_TRACE builds only), else NULL
 };
 
@@ -81,6 +84,16 @@ struct RowGeom {
   static_assert(ND * N <= 512, "TMEM has 512 columns");
   static_assert(ND >= KS + 1, "the MMA must be able to run ahead of the epilogue");
 };
+
+// Developer experiments (PBMC_ROW_TRACE builds only; results become WRONG): skip parts of the pipeline to see what
+// bounds it.  1 no MMA issue, 2 no global loads, 4 no STS, 8 no LDTM, 16 no STG, 32 no proxy fence.
+// Finding (B200, 32 x 256^2, plain 16->16): all of them skipped still costs 60 % of the full kernel's time --
+// the per-stage barrier protocol + addressing on single warps (~330 instructions, ~7 clk each) is the bound.
+#ifdef PBMC_ROW_TRACE
+#define CR_DBG(flag) ((p.dbg_flags & (flag)) != 0)
+#else
+#define CR_DBG(flag) false
+#endif
 
 #ifdef PBMC_ROW_TRACE
 #define CR_TR(slot)                                                                              \
@@ -246,63 +259,77 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     float cs[4] = {0.f, 0.f, 0.f, 0.f};  // zero-mean sums: only the c_out <= 4 head conv asks for them
     const bool want_cs = p.out_chan_sum != nullptr;
-    float* orow = p.out + (((size_t)b * p.cout_blks) * plane_px + (size_t)(y0 + eset) * W + gx) * 4;
+    const int cout_blks = p.cout_blks;
+    const bool epi_gelu = p.epi_act == PBMC_ACT_GELU;
+    const uint32_t bias_addr = smem_u32(bias_s);
+    float* orow = p.out + (((size_t)b * cout_blks) * plane_px + (size_t)(y0 + eset) * W + gx) * 4;
     const size_t blk_stride = plane_px * 4, row_stride = (size_t)2 * W * 4;
-    // ring positions advance by 2 rows per iteration (ND is even: a set always sees the same slot parity class)
-    uint32_t s_lo = (uint32_t)eset % ND, s_hi = (uint32_t)(eset + KS - 1) % ND, par_hi = ((uint32_t)(eset + KS - 1) / ND) & 1u;
-    for (int yo = eset; yo < nrows; yo += 2) {
-      mbar_wait_parked(d_full(s_hi), par_hi);  // the last input row this output row needs (commits are in order)
-      tc_fence_after();
-      if ((tid & 127) == 0) CR_TR(1200 + 3 * yo);
-      uint32_t r[KS][16];
-      uint32_t sl = s_lo;
-#pragma unroll
-      for (int dy = 0; dy < KS; ++dy) {
-        tmem_ld16_issue(lane_addr + sl * (uint32_t)N + (uint32_t)(dy * 16), r[dy]);
-        if (++sl == (uint32_t)ND) sl = 0;
-      }
-#pragma unroll
-      for (int dy = 0; dy < KS; ++dy) tmem_ld_wait16(r[dy]);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        // D_{yo+dy} is read by output rows yo+dy-KS+1 .. yo+dy; rows < 0 do not exist, so row 0 arrives for them
-        sl = s_lo;
+    const bool col_in = gx < W;
+    // The epilogue's instruction stream is the busiest in the CTA (ncu: half of all issued instructions), so
+    // the common shape -- 16 outputs, no activation, no channel sums -- gets a loop with nothing else in it.
+    auto row_loop = [&](auto lean_tag) {
+      constexpr bool LEAN = decltype(lean_tag)::value;
+      // ring positions advance by 2 rows per iteration (ND is even: a set always sees the same slot parity class)
+      uint32_t s_lo = (uint32_t)eset % ND, s_hi = (uint32_t)(eset + KS - 1) % ND, par_hi = ((uint32_t)(eset + KS - 1) / ND) & 1u;
+      for (int yo = eset; yo < nrows; yo += 2) {
+        mbar_wait_parked(d_full(s_hi), par_hi);  // the last input row this output row needs (commits are in order)
+        tc_fence_after();
+        if ((tid & 127) == 0) CR_TR(1200 + 3 * yo);
+        uint32_t r[KS][16];
+        uint32_t sl = s_lo;
 #pragma unroll
         for (int dy = 0; dy < KS; ++dy) {
-          mbar_arrive_n(d_empty(sl), yo == 0 ? (uint32_t)(KS - dy) : 1u);
+          if (!CR_DBG(8)) tmem_ld16_issue(lane_addr + sl * (uint32_t)N + (uint32_t)(dy * 16), r[dy]);
           if (++sl == (uint32_t)ND) sl = 0;
         }
-      }
-      if ((tid & 127) == 0) CR_TR(1201 + 3 * yo);
-      if (gx < W) {
 #pragma unroll
-        for (int qb = 0; qb < 4; ++qb) {
-          if (qb < p.cout_blks) {
-            const float4 bq = reinterpret_cast<const float4*>(bias_s)[qb];
-            const float bias4[4] = {bq.x, bq.y, bq.z, bq.w};
-            float o[4];
+        for (int dy = 0; dy < KS; ++dy) tmem_ld_wait16(r[dy]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          // D_{yo+dy} is read by output rows yo+dy-KS+1 .. yo+dy; rows < 0 do not exist, so row 0 arrives for them
+          sl = s_lo;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a = __uint_as_float(r[0][qb * 4 + e]);
-#pragma unroll
-              for (int dy = 1; dy < KS; ++dy) a += __uint_as_float(r[dy][qb * 4 + e]);
-              a += bias4[e];
-              if (p.epi_act == PBMC_ACT_GELU) a = gelu_erf(a);
-              o[e] = a;
-            }
-            *reinterpret_cast<float4*>(orow + qb * blk_stride) = make_float4(o[0], o[1], o[2], o[3]);
-            s1[qb] += (o[0] + o[1]) + (o[2] + o[3]);
-            s2[qb] = fmaf(o[0], o[0], fmaf(o[1], o[1], fmaf(o[2], o[2], fmaf(o[3], o[3], s2[qb]))));
-            if (qb == 0 && want_cs) { cs[0] += o[0]; cs[1] += o[1]; cs[2] += o[2]; cs[3] += o[3]; }
+          for (int dy = 0; dy < KS; ++dy) {
+            mbar_arrive_n(d_empty(sl), yo == 0 ? (uint32_t)(KS - dy) : 1u);
+            if (++sl == (uint32_t)ND) sl = 0;
           }
         }
+        if ((tid & 127) == 0) CR_TR(1201 + 3 * yo);
+        if (col_in && !CR_DBG(16)) {
+#pragma unroll
+          for (int qb = 0; qb < 4; ++qb) {
+            if (LEAN || qb < cout_blks) {
+              float4 bq;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bq.x), "=f"(bq.y), "=f"(bq.z), "=f"(bq.w) : "r"(bias_addr + qb * 16));
+              const float bias4[4] = {bq.x, bq.y, bq.z, bq.w};
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = __uint_as_float(r[0][qb * 4 + e]);
+#pragma unroll
+                for (int dy = 1; dy < KS; ++dy) a += __uint_as_float(r[dy][qb * 4 + e]);
+                a += bias4[e];
+                if (!LEAN && epi_gelu) a = gelu_erf(a);
+                o[e] = a;
+              }
+              *reinterpret_cast<float4*>(orow + qb * blk_stride) = make_float4(o[0], o[1], o[2], o[3]);
+              s1[qb] += (o[0] + o[1]) + (o[2] + o[3]);
+              s2[qb] = fmaf(o[0], o[0], fmaf(o[1], o[1], fmaf(o[2], o[2], fmaf(o[3], o[3], s2[qb]))));
+              if (!LEAN && qb == 0 && want_cs) { cs[0] += o[0]; cs[1] += o[1]; cs[2] += o[2]; cs[3] += o[3]; }
+            }
+          }
+        }
+        orow += row_stride;
+        s_lo += 2; if (s_lo >= (uint32_t)ND) s_lo -= ND;
+        s_hi += 2; if (s_hi >= (uint32_t)ND) { s_hi -= ND; par_hi ^= 1u; }
+        if ((tid & 127) == 0) CR_TR(1202 + 3 * yo);
       }
-      orow += row_stride;
-      s_lo += 2; if (s_lo >= (uint32_t)ND) s_lo -= ND;
-      s_hi += 2; if (s_hi >= (uint32_t)ND) { s_hi -= ND; par_hi ^= 1u; }
-      if ((tid & 127) == 0) CR_TR(1202 + 3 * yo);
-    }
+    };
+    if (cout_blks == 4 && !epi_gelu && !want_cs)
+      row_loop(std::true_type{});
+    else
+      row_loop(std::false_type{});
     if (tid == 0) CR_TR(3);
     if (p.out_stats != nullptr) {
 #pragma unroll
@@ -365,7 +392,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
       const int sy = pad_index(y0 - P + ri, H, p.pad_mode);
       const RowGroup gi = gtab[g];
       B.ok = sy >= 0;
-      const bool ok = col_ok && sy >= 0;
+      const bool ok = col_ok && sy >= 0 && !CR_DBG(2);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         B.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -395,17 +422,30 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         const float4* b4 = reinterpret_cast<const float4*>(xf_b + gi.chan0);
         const bool do_gn = gi.xform != PBMC_XFORM_GELU, do_gelu = gi.xform != PBMC_XFORM_GN;
         if (col_ok) {
+          if (gi.nb == 4 && gi.xform == PBMC_XFORM_GN_GELU) {
+            // the trunk's shape, branch-free: 16 independent GN+GELU chains that the scheduler can interleave
+            // (a lone warp is latency-bound on the 10-FMA polynomial: 706 clk per 16 values vs 325 clk of issue)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < gi.nb) {  // absent blocks of a partial group stay exactly zero
-              if (do_gn) {
-                const float4 a = a4[j], bb = b4[j];
-                v[4 * j + 0] = fmaf(v[4 * j + 0], a.x, bb.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, bb.y);
-                v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, bb.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, bb.w);
-              }
-              if (do_gelu) {
+            for (int j = 0; j < 4; ++j) {
+              const float4 a = a4[j], bb = b4[j];
+              v[4 * j + 0] = fmaf(v[4 * j + 0], a.x, bb.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, bb.y);
+              v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, bb.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, bb.w);
+            }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[4 * j + e] = gelu_erf(v[4 * j + e]);
+            for (int c = 0; c < 16; ++c) v[c] = gelu_erf(v[c]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < gi.nb) {  // absent blocks of a partial group stay exactly zero
+                if (do_gn) {
+                  const float4 a = a4[j], bb = b4[j];
+                  v[4 * j + 0] = fmaf(v[4 * j + 0], a.x, bb.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, bb.y);
+                  v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, bb.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, bb.w);
+                }
+                if (do_gelu) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) v[4 * j + e] = gelu_erf(v[4 * j + e]);
+                }
               }
             }
           }
@@ -425,7 +465,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
       if (tr_lane) CR_TR(101 + pg * 300 + 4 * (st / CR_NPG));
       mbar_wait_parked(a_empty(slot), (((uint32_t)st / NSTAGE) & 1u) ^ 1u);
       if (tr_lane) CR_TR(102 + pg * 300 + 4 * (st / CR_NPG));
-      if (PARTS == 2) {
+      if (CR_DBG(4)) {
+      } else if (PARTS == 2) {
         uint4 h0, l0, h1, l1;
         split_f16(v, h0, l0);
         split_f16(v + 8, h1, l1);
@@ -454,7 +495,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
           }
         }
       }
-      fence_proxy_async_smem();
+      if (!CR_DBG(32)) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(slot));
       if (tr_lane) CR_TR(103 + pg * 300 + 4 * (st / CR_NPG));
@@ -493,7 +534,11 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     const bool leader = elect_one();
     constexpr uint32_t A_LBO = PLANE * 16, B_LBO = N * 16, SBO = 128;
     const uint64_t a_desc0 = umma_desc(smem_u32(As), A_LBO, SBO), b_desc0 = umma_desc(smem_u32(Bs), B_LBO, SBO);
+#ifdef PBMC_ROW_TRACE
     const uint32_t dx_step = (uint32_t)p.dbg_dx >> 4;
+#else
+    constexpr uint32_t dx_step = 1;  // one position = 16 B
+#endif
     uint32_t ds = 0, d_par = 0;
     int st = 0;
     bool ready = total > 0 && mbar_test(a_full(0), 0u);
@@ -513,6 +558,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
           for (int dx = 0; dx < KS; ++dx) {
             const uint64_t a_hi = a_s + (uint64_t)(dx * dx_step);
             const uint64_t b_hi = b_s + (uint64_t)(dx * PARTS * (G::B_TILE >> 4));
+            if (CR_DBG(1)) continue;
             umma_ss<1>(dcol, a_hi, b_hi, IDESC, (uint32_t)(g | dx));
             if (PARTS == 2) {
               umma_ss<1>(dcol, a_hi + (uint64_t)(G::PART_BYTES >> 4), b_hi, IDESC, 1u);
@@ -615,6 +661,7 @@ int conv_row_dispatch(const pbmc_conv_desc& d, cudaStream_t st) {
   p.rpc = 1;
   p.trace = nullptr;
   p.dbg_dx = getenv("PBMC_ROW_DBG_DX") ? atoi(getenv("PBMC_ROW_DBG_DX")) : 16;
+  p.dbg_flags = getenv("PBMC_ROW_DBG_FLAGS") ? atoi(getenv("PBMC_ROW_DBG_FLAGS")) : 0;
 #ifdef PBMC_ROW_TRACE
   p.trace = g_row_trace;
 #endif

@@ -1,1 +1,1 @@
-for dx in 16 0 128; do echo "== dbg_dx=$dx"; PBMC_ROW_DBG_DX=$dx python tools/kbench.py row_f16x2 2>&1 | grep -E "B32|B1 512x512"; done
+for fl in 0 1 2 4 6 8 16 24 32 7 31 63; do echo "== flags=$fl"; PBMC_ROW_DBG_FLAGS=$fl python tools/kbench.py row_f16x2 2>&1 | grep -E "plain +B32|plain +B1 512x512|gelu +B32"; done
