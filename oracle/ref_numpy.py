@@ -271,13 +271,19 @@ def build_input(T, xc, yc, ycc, raq, fkt, fkp):
     return inp, V
 
 
-def adnet_forward(u, v, T, raq, xc, yc, CN_max, dt=None):
+def adnet_forward(u, v, T, raq, xc, yc, CN_max, dt=None, y_walls=(True, True)):
     """ADNet.forward, pytorch_networks_convae.py:522-568.  u,v,T [B,H,W]; xc,yc [H,W].
-    Returns (T_new [B,H,W] incl. ADNet's own wall rows, dt scalar)."""
+    Returns (T_new [B,H,W] incl. ADNet's own wall rows, dt scalar).
+    y_walls: which of the first / last rows are real walls.  The reference always has both; a row slab of a
+    decomposed grid has a ghost row instead, whose coordinate is NOT forced and whose
+    output value is left to the halo exchange."""
     xc = xc.copy()
     yc = yc.copy()
     xc[:, 0], xc[:, -1] = 0.0, 4.0  # :532-535
-    yc[0, :], yc[-1, :] = 0.0, 1.0
+    if y_walls[0]:
+        yc[0, :] = 0.0
+    if y_walls[1]:
+        yc[-1, :] = 1.0
     ui, vi = u[:, 1:-1, 1:-1], v[:, 1:-1, 1:-1]
     dx_l = (xc[1:-1, 1:-1] - xc[1:-1, :-2])[None]
     dx_r = (xc[1:-1, 2:] - xc[1:-1, 1:-1])[None]
@@ -301,8 +307,10 @@ def adnet_forward(u, v, T, raq, xc, yc, CN_max, dt=None):
         dt = min(dt_adv, dt_dif)
     Tn = Tc + dt * (-ui * dT_dx - vi * dT_dy + lap + raq)
     out = np.pad(Tn, ((0, 0), (1, 1), (1, 1)), mode="edge")
-    out[:, 0, :] = 1.0
-    out[:, -1, :] = 0.0
+    if y_walls[0]:
+        out[:, 0, :] = 1.0
+    if y_walls[1]:
+        out[:, -1, :] = 0.0
     return out.astype(T.dtype), dt
 
 

@@ -1,0 +1,76 @@
+"""Slab decomposition on the GPU.  One GPU is available to the test box, so the
+two ranks are emulated in ONE process: two `SlabStencil` objects with the real CUDA local update (ghost rows,
+sliced y-coefficients, kernel wall writes landing in ghosts), the all-reduce replaced by a max over the two
+local reductions and the send/recv by direct row copies.  The real NCCL path is exercised by
+`bench.py --workload slab --gpus N` / tools/slab_check.py on a multi-GPU box and by the gloo tests on CPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_numpy as RN
+from pbml_mantle_convection_b200 import multigpu as MG
+from pbml_mantle_convection_b200 import ops
+from pbml_mantle_convection_b200.engine import Grid
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _fields(H, W, seed=5):
+    xc, yc = RN.synthetic_grid(H, W)
+    T = RN.synthetic_T0(H, W, seed=seed).astype(np.float32)
+    psi = np.sin(np.pi * xc / 4 * 3) * np.sin(np.pi * yc)
+    u = (np.gradient(psi, axis=0) * 3e3).astype(np.float32)
+    v = (-np.gradient(psi, axis=1) * 3e3).astype(np.float32)
+    return xc, yc, T, u, v
+
+
+def _single_gpu(xc, yc, T, u, v, steps, raq):
+    g = Grid(torch.tensor(xc), torch.tensor(yc), torch.tensor(yc), DEV)
+    members = ops.make_members([(raq, 1.0, 1.0)], DEV)
+    Tc = torch.tensor(T[None], device=DEV)
+    ud, vd = torch.tensor(u[None], device=DEV), torch.tensor(v[None], device=DEV)
+    uv = ops.uvmax_reduce(ud, vd, batch_global=True)
+    dts = []
+    for _ in range(steps):
+        Tc, dt, _ = ops.advect_diffuse(Tc, ud, vd, g.xcoef, g.ycoef, members, uv, g.dx_min, 0.99, per_member_dt=False)
+        dts.append(float(dt[0]))
+    return Tc[0].cpu().numpy(), dts
+
+
+@pytest.mark.parametrize("H,W,world", [(64, 128, 2), (67, 100, 3), (130, 64, 4)])
+def test_emulated_slabs_equal_single_gpu(H, W, world):
+    xc, yc, T, u, v = _fields(H, W)
+    raq, steps = 2.5, 5
+    ref, ref_dts = _single_gpu(xc, yc, T, u, v, steps, raq)
+    sts = [MG.SlabStencil(H, W, xc[0], yc[:, 0], r, world, DEV, raq=raq, cn_max=0.99) for r in range(world)]
+    for st in sts:
+        st.scatter(T, u, v)
+    dts = []
+    for _ in range(steps):
+        bits = torch.stack([st.local_uvmax(st.u, st.v) for st in sts]).max(0).values  # the all-reduce(MAX)
+        new = []
+        for st in sts:
+            Tn, dt = st.local_step(st.T, st.u, st.v, bits)
+            new.append(Tn)
+        for r, st in enumerate(sts):  # the halo exchange
+            if st.slab.up:
+                new[r][0, 0].copy_(new[r - 1][0, sts[r - 1].slab.rows - 2])
+            if st.slab.down:
+                new[r][0, st.slab.rows - 1].copy_(new[r + 1][0, 1])
+        for st, Tn in zip(sts, new):
+            st.T = Tn
+        dts.append(float(dt[0]))
+    got = np.concatenate([st.slab.owned(st.T)[0].cpu().numpy() for st in sts], 0)
+    assert np.array_equal(got, ref), np.abs(got - ref).max()
+    assert dts == ref_dts
+
+
+def test_world_one_slab_is_the_plain_kernel():
+    H, W = 48, 96
+    xc, yc, T, u, v = _fields(H, W, seed=9)
+    ref, ref_dts = _single_gpu(xc, yc, T, u, v, 3, 1.0)
+    st = MG.SlabStencil(H, W, xc[0], yc[:, 0], 0, 1, DEV, raq=1.0)
+    st.scatter(T, u, v)
+    st.step(3)
+    assert np.array_equal(st.gather().cpu().numpy(), ref) and float(st.last_dt[0]) == ref_dts[-1]

@@ -1,0 +1,58 @@
+"""Multi-GPU check of the slab-decomposed stencil (config 5): run under torchrun on N GPUs of one box,
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/slab_check.py [H W steps]
+every rank advances its slab with NCCL halo exchange + dt all-reduce; rank 0 also runs the whole grid alone and
+the gathered result must be bit-identical.  Prints device-timed cell-updates/s (max over ranks)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pbml_mantle_convection_b200 import multigpu as MG  # noqa: E402
+from pbml_mantle_convection_b200 import rollout as RO  # noqa: E402
+
+
+def main():
+    H = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+    W = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    xc, yc = RO.synthetic_grid(H, W)
+    T = RO.synthetic_T0(H, W, seed=1).astype(np.float32)
+    psi = np.sin(np.pi * xc / 4 * 3) * np.sin(np.pi * yc)
+    u = (np.gradient(psi, axis=0) * 1e3 * H).astype(np.float32)
+    v = (-np.gradient(psi, axis=1) * 1e3 * W).astype(np.float32)
+    st = MG.SlabStencil(H, W, xc[0], yc[:, 0], rank, world, dev, raq=2.0)
+    st.scatter(T, u, v)
+    st.step(3)  # warm-up (NCCL communicators, module load)
+    st.scatter(T, u, v)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    st.step(steps)
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    full = st.gather()
+    ok = True
+    if rank == 0:
+        ref = MG.SlabStencil(H, W, xc[0], yc[:, 0], 0, 1, dev, raq=2.0)
+        ref.scatter(T, u, v)
+        ref.step(steps)
+        ok = bool(torch.equal(ref.gather(), full))
+        print(f"slab_check H={H} W={W} world={world} steps={steps}: identical_to_single_gpu={ok} "
+              f"{H * W * steps / (ms.item() * 1e-3):.4g} cell-updates/s ({ms.item() / steps:.3f} ms/step)", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
