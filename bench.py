@@ -221,6 +221,51 @@ def kernel_rooflines(net, H, W, B, dev, flush):
     return out
 
 
+def stencil_sweep(dev, sizes=(256, 512, 1024, 2048, 4096, 8192), sweeps=50):
+    """BASELINE config 3: the advection-diffusion stencil + in-pass CFL reduction alone, ping-pong over `sweeps`
+    steps per grid (16 B per cell-update: T, u, v in, T' out; max|u|,|v| comes out of the same pass).  Grids whose
+    four fields fit the 126 MB L2 (<= 2048^2) are L2-resident by construction -- the GB/s there is not an HBM number."""
+    from pbml_mantle_convection_b200 import ops
+
+    hbm, _, _, which = measured_peaks()
+    rows = []
+    g = torch.Generator(device=dev).manual_seed(7)
+    for n in sizes:
+        grid = eng_grid(n, n, dev)
+        T = torch.rand(1, n, n, device=dev, generator=g)
+        xs = torch.linspace(0, 1, n, device=dev)
+        psi = torch.sin(3.14159265 * 3 * xs)[None, :] * torch.sin(3.14159265 * xs)[:, None]
+        u = ((psi[2:, :] - psi[:-2, :]) * n * 50).new_zeros(n, n)
+        u[1:-1] = (psi[2:, :] - psi[:-2, :]) * n * 50
+        v = torch.zeros(n, n, device=dev)
+        v[:, 1:-1] = -(psi[:, 2:] - psi[:, :-2]) * n * 50
+        u, v = u[None].contiguous(), v[None].contiguous()
+        members = ops.make_members([PARAMS0], dev)
+        uv = [ops.uvmax_reduce(u, v), torch.zeros(1, dtype=torch.int32, device=dev)]
+        Tb = [T, torch.empty_like(T)]
+        dto = torch.empty(1, dtype=torch.float64, device=dev)
+
+        def run(k):
+            for i in range(k):
+                uv[(i + 1) % 2].zero_()
+                ops.advect_diffuse(Tb[i % 2], u, v, grid.xcoef, grid.ycoef, members, uv[i % 2], grid.dx_min, 0.99,
+                                   T_out=Tb[(i + 1) % 2], dt_out=dto, uv_out=uv[(i + 1) % 2])
+
+        run(4)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run(sweeps)
+        b.record()
+        b.synchronize()
+        ms = a.elapsed_time(b) / sweeps
+        gbs = n * n * 16 / (ms * 1e-3) / 1e9
+        rows.append({"grid": [n, n], "ms_per_sweep": ms, "cell_updates_per_s": n * n / (ms * 1e-3), "achieved_gbs": gbs,
+                     "frac_of_hbm_peak": gbs / hbm, "resident": "L2" if 4 * n * n * 4 <= 100e6 else "HBM"})
+    return {"bytes_per_cell_update": 16, "peak_gbs": hbm, "peak_source": which, "sweeps": sweeps,
+            "note": "includes the 4-byte memset + launch per sweep (CUDA events around the whole ping-pong loop)", "rows": rows}
+
+
 def eng_grid(H, W, dev):
     import pbml_mantle_convection_b200 as P
     from pbml_mantle_convection_b200.engine import Grid
@@ -339,6 +384,7 @@ def run_ours(args, wl):
     line = None
     if rank == 0:
         roofs = kernel_rooflines(net, H, W, B, dev, flush)
+        sweep = stencil_sweep(dev)
         step_ms = dev_ms / K
         # dominant kernel = largest share of the step (conv[1] runs once, the level-0 trunk layer R times)
         share = {"conv1_103x16": roofs["conv1_103x16"]["ms"], "conv16x16_l0": roofs["conv16x16_l0"]["ms"] * 4,
@@ -369,6 +415,7 @@ def run_ours(args, wl):
             "wall_ms_per_step": 1e3 * wall / K,
             "roofline": roofline,
             "kernels": roofs,
+            "stencil_sweep": sweep,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_rate, "unit": "cell-updates/s", "h2d_bytes_per_step": int(Tp.numel() * 8), "d2h_bytes_per_step": int(d2h),
                     "steps": K2, "api": "TS.forward(ts=1) with pinned host float64 T in, (T,u,v,V,dt) read back"},

@@ -7,6 +7,8 @@
 // Algorithmic traffic: read T,u,v + write T' = 16 B per cell (fp32).  The CFL reduction
 // max|u|,|v| of the interior is produced in the same pass (warp shuffle -> block -> one
 // atomicMax per CTA), so a following step (or sweep) never needs a separate reduction pass.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pbmc {
@@ -179,6 +181,103 @@ __global__ void __launch_bounds__(ST_BX* ST_BY) stencil_kernel(const StencilPara
   }
 }
 
+// ---- register-marching form of the same update for 16-byte aligned rows (W % 4 == 0): a warp owns a strip of
+// 128 columns (one float4 per lane) and walks down `rpw` rows keeping rows r-1, r, r+1 of T in registers; the
+// left / right neighbours of a lane's four cells come from the adjacent lanes by shuffle (the strip's two halo
+// columns by one predicated scalar load each).  No shared memory, no block barrier: every row is one 128-bit
+// load of T, u and v and one 128-bit store, with the next row's loads in flight during the arithmetic --
+// 16 B per cell-update of HBM traffic plus 2/rpw of a row of T for the strip's top and bottom halo.
+__global__ void __launch_bounds__(128) stencil_march_kernel(const StencilParams p, int rpw) {
+  const int H = p.H, W = p.W, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x0 = (blockIdx.x * 32 + lane) * 4;
+  const int y0 = (blockIdx.y * 4 + warp) * rpw;
+  if (y0 >= H) return;  // whole warp
+  const int y1 = min(y0 + rpw, H);
+  const bool act = x0 < W;              // W % 4 == 0: a lane's four columns are all inside or all outside
+  const int xs = act ? x0 : W - 4;      // inactive lanes shadow the last float4 (they take part in the shuffles)
+  const size_t plane = (size_t)H * W;
+  const float* Tb = p.T + (size_t)b * plane;
+  const float* ub = p.u + (size_t)b * plane;
+  const float* vb = p.v + (size_t)b * plane;
+  float* To = p.T_out + (size_t)b * plane;
+
+  double dtd = p.dt_fixed;
+  if (!(dtd > 0.0)) dtd = cfl_dt((double)__uint_as_float(__ldg(p.uvmax_in + (size_t)b * p.member_stride)), p.dx_min, p.cn_max);
+  const float dt = (float)dtd;
+  if (p.dt_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dt_out[b] = dtd;
+  const float raq = p.mem ? p.mem[b].raq : 0.f;
+  const float4 ixl = ldg4(p.xcoef + xs), ixr = ldg4(p.xcoef + W + xs), ixc = ldg4(p.xcoef + 2 * W + xs);
+  const float xl[4] = {ixl.x, ixl.y, ixl.z, ixl.w}, xr[4] = {ixr.x, ixr.y, ixr.z, ixr.w}, xcn[4] = {ixc.x, ixc.y, ixc.z, ixc.w};
+  const bool need_l = lane == 0 && x0 > 0, need_r = (lane == 31 || x0 + 4 >= W) && x0 + 4 < W;
+
+  auto row4 = [&](const float* base, int r) { return __ldcs(reinterpret_cast<const float4*>(base + (size_t)r * W + xs)); };
+  auto rowT = [&](int r) { return __ldg(reinterpret_cast<const float4*>(Tb + (size_t)r * W + xs)); };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // rows r-1, r, r+1 of T; u, v, the two halo scalars and the y coefficients of row r
+  float4 Tm = y0 > 0 ? rowT(y0 - 1) : zero4, Tc = rowT(y0), Tp = y0 + 1 < H ? rowT(y0 + 1) : zero4;
+  float4 uc = row4(ub, y0), vc = row4(vb, y0);
+  float hl = need_l ? __ldg(Tb + (size_t)y0 * W + x0 - 1) : 0.f, hr = need_r ? __ldg(Tb + (size_t)y0 * W + x0 + 4) : 0.f;
+  float cyt = __ldg(p.ycoef + y0), cyb = __ldg(p.ycoef + H + y0), cyc = __ldg(p.ycoef + 2 * H + y0);
+  float m = 0.f;
+  for (int r = y0; r < y1; ++r) {
+    // next row's operands first: they are in flight during this row's arithmetic
+    const int rn = r + 1;
+    const bool more = rn < y1;
+    float4 Tn = zero4, un = zero4, vn = zero4;
+    float hln = 0.f, hrn = 0.f, cytn = 0.f, cybn = 0.f, cycn = 0.f;
+    if (rn + 1 < H && more) Tn = rowT(rn + 1);
+    if (more) {
+      un = row4(ub, rn);
+      vn = row4(vb, rn);
+      if (need_l) hln = __ldg(Tb + (size_t)rn * W + x0 - 1);
+      if (need_r) hrn = __ldg(Tb + (size_t)rn * W + x0 + 4);
+      cytn = __ldg(p.ycoef + rn); cybn = __ldg(p.ycoef + H + rn); cycn = __ldg(p.ycoef + 2 * H + rn);
+    }
+    float left = __shfl_up_sync(0xffffffffu, Tc.w, 1), right = __shfl_down_sync(0xffffffffu, Tc.x, 1);
+    if (need_l) left = hl;
+    if (need_r) right = hr;
+    float o[4];
+    if (r == 0) {
+      o[0] = o[1] = o[2] = o[3] = 1.0f;  // hot bottom wall (:566, :468)
+    } else if (r == H - 1) {
+      o[0] = o[1] = o[2] = o[3] = 0.0f;  // cold top wall (:567, :469)
+    } else {
+      const float tc[6] = {left, Tc.x, Tc.y, Tc.z, Tc.w, right};
+      const float tm[4] = {Tm.x, Tm.y, Tm.z, Tm.w}, tp[4] = {Tp.x, Tp.y, Tp.z, Tp.w};
+      const float u4[4] = {uc.x, uc.y, uc.z, uc.w}, v4[4] = {vc.x, vc.y, vc.z, vc.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = x0 + k;
+        o[k] = 0.f;
+        if (j > 0 && j < W - 1) {
+          const float c = tc[k + 1];
+          const float Tl = (c - tc[k]) * xl[k];
+          const float Tr = (tc[k + 2] - c) * xr[k];
+          const float Tt = (c - tm[k]) * cyt;
+          const float Tbm = (tp[k] - c) * cyb;
+          const float u_ = u4[k], v_ = v4[k];
+          const float Tx = u_ > 0.f ? Tl : (u_ < 0.f ? Tr : 0.f);
+          const float Ty = v_ > 0.f ? Tt : (v_ < 0.f ? Tbm : 0.f);
+          const float lap = (Tr - Tl) * xcn[k] + (Tbm - Tt) * cyc;
+          o[k] = c + dt * (-u_ * Tx - v_ * Ty + lap + raq);
+          m = fmaxf(m, fmaxf(fabsf(u_), fabsf(v_)));
+        }
+      }
+      // side columns copy their interior neighbour (replicate pad :565, :470-471)
+      if (x0 == 0) o[0] = o[1];
+      if (x0 + 4 == W) o[3] = o[2];
+    }
+    if (act) __stcs(reinterpret_cast<float4*>(To + (size_t)r * W + x0), make_float4(o[0], o[1], o[2], o[3]));
+    Tm = Tc; Tc = Tp; Tp = Tn;
+    uc = un; vc = vn; hl = hln; hr = hrn; cyt = cytn; cyb = cybn; cyc = cycn;
+  }
+  if (p.uvmax_out != nullptr) {
+    m = warp_max(act ? m : 0.f);
+    if (lane == 0 && m > 0.f) atomic_max_nonneg(p.uvmax_out + (size_t)b * p.member_stride, m);
+  }
+}
+
 // ---- stand-alone interior max|u|,|v| (only when no producer supplied it)
 __global__ void __launch_bounds__(256) uvmax_kernel(const float* __restrict__ u, const float* __restrict__ v,
                                                     uint32_t* __restrict__ out, int member_stride, int H, int W) {
@@ -330,6 +429,18 @@ extern "C" int pbmc_advect_diffuse(const float* T, const float* u, const float* 
   if (T == T_out) return PBMC_ERR_UNSUPPORTED;  // out-of-place only (neighbours are read)
   StencilParams p{T, u, v, x, y, members, uvmax_in, uvmax_out, T_out, dt_out, dx_min, cn_max, dt_fixed, member_stride, H, W};
   const bool vec = (W % 4 == 0) && aligned16(T) && aligned16(u) && aligned16(v) && aligned16(T_out);
+  static const int tiled = getenv("PBMC_STENCIL_TILED") ? atoi(getenv("PBMC_STENCIL_TILED")) : 0;  // developer knob: old kernel
+  if (vec && aligned16(x) && !tiled) {
+    // rows per warp: enough warps to fill the machine (148 SMs x 16 warps), at most 64 rows (2/rpw halo re-read)
+    const int strips = cdiv(W, 128);
+    long want = ((long)H * strips * B + 2367) / 2368;
+    const int rpw = (int)(want < 4 ? 4 : (want > 64 ? 64 : want));
+    dim3 grid(strips, cdiv(H, 4 * rpw), B);
+    if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
+    stencil_march_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, rpw);
+    PBMC_CHECK_LAUNCH("stencil_march_kernel");
+    return PBMC_OK;
+  }
   const int TW = vec ? ST_BX * 4 : ST_BX;
   dim3 grid(cdiv(W, TW), cdiv(H, ST_TH), B);
   if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
