@@ -37,6 +37,8 @@ WORKLOADS = {
     "rollout512": dict(H=512, W=512, B=1, desc="512x512 batch-1 surrogate rollout (BASELINE config 2)"),
     "rollout128": dict(H=128, W=128, B=1, desc="128x128 batch-1 surrogate rollout (BASELINE config 1 grid)"),
     "ensemble256": dict(H=256, W=256, B=32, desc="32 members/GPU of 256x256 (BASELINE config 4, weak scaling)"),
+    "slab8192": dict(H=8192, W=8192, B=1, desc="one 8192x8192 grid, row slabs over the ranks: stencil + one-row T halo "
+                                                "send/recv + dt all-reduce, given u,v (BASELINE config 5, strong scaling)"),
 }
 
 
@@ -253,9 +255,14 @@ def stencil_sweep(dev, sizes=(256, 512, 1024, 2048, 4096, 8192), sweeps=50):
 
         run(4)
         torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()  # the ping-pong loop as one graph: no per-launch host cost in the timing
+        with torch.cuda.graph(graph):
+            run(sweeps)
+        graph.replay()
+        torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        run(sweeps)
+        graph.replay()
         b.record()
         b.synchronize()
         ms = a.elapsed_time(b) / sweeps
@@ -263,7 +270,7 @@ def stencil_sweep(dev, sizes=(256, 512, 1024, 2048, 4096, 8192), sweeps=50):
         rows.append({"grid": [n, n], "ms_per_sweep": ms, "cell_updates_per_s": n * n / (ms * 1e-3), "achieved_gbs": gbs,
                      "frac_of_hbm_peak": gbs / hbm, "resident": "L2" if 4 * n * n * 4 <= 100e6 else "HBM"})
     return {"bytes_per_cell_update": 16, "peak_gbs": hbm, "peak_source": which, "sweeps": sweeps,
-            "note": "includes the 4-byte memset + launch per sweep (CUDA events around the whole ping-pong loop)", "rows": rows}
+            "note": "CUDA events around one graph replay of the whole ping-pong loop (kernel + 4-byte memset per sweep)", "rows": rows}
 
 
 def eng_grid(H, W, dev):
@@ -430,6 +437,71 @@ def run_ours(args, wl):
         print(json.dumps(line), flush=True)
 
 
+def run_slab(args, wl):
+    """BASELINE config 5: a single large grid, slab-decomposed over the ranks (strong scaling: total work fixed)."""
+    import torch.distributed as dist
+
+    import pbml_mantle_convection_b200 as P
+    from pbml_mantle_convection_b200 import multigpu as MG
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, W = wl["H"], wl["W"]
+    K, Wm = args.steps, max(args.warmup, 3)
+    xc, yc = P.synthetic_grid(H, W)
+    st = MG.SlabStencil(H, W, xc[0], yc[:, 0], rank, world, dev, raq=PARAMS0[0], cn_max=0.99, halo=args.halo)
+    s = st.slab
+    g = torch.Generator(device=dev).manual_seed(3 + rank)
+    ys = torch.tensor(yc[s.l0:s.l1, 0], dtype=torch.float32, device=dev)
+    xs = torch.tensor(xc[0], dtype=torch.float32, device=dev)
+    T = (1.0 - ys)[:, None] + 0.01 * torch.rand(s.rows, W, device=dev, generator=g)
+    psi_x, psi_y = torch.sin(3.14159265 * xs / 4 * 3), torch.sin(3.14159265 * ys)
+    u = 1e3 * torch.cos(3.14159265 * ys)[:, None] * psi_x[None, :]  # smooth, max|u| = 1e3 (SURVEY.md section 8d config 3)
+    v = -1e3 * psi_y[:, None] * torch.cos(3.14159265 * xs / 4 * 3)[None, :] * 0.75
+    st.set_local(T, u, v)
+    st.step(Wm)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    with ClockSampler(local) as clk:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        st.step(K)
+        b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    t_ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = t_ms.item()
+    finite = bool(torch.isfinite(st.T).all().item())
+    if rank == 0:
+        hbm, _, _, which = measured_peaks()
+        rate = H * W * K / (ms * 1e-3)
+        gbs = rate * 16 / world / 1e9  # per rank: T, u, v in, T' out; max|u|,|v| for the next dt comes out of the same pass
+        line = {"metric": "stencil cell-updates/s", "value": rate, "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "desc": wl["desc"], "grid": [H, W], "rows_per_rank": s.hi - s.lo,
+                           "l2": "fields (>= 256 MiB per rank at 8 ranks x 3 fields) exceed L2; no flush",
+                           "parallelism": f"{world} row slabs, halo={args.halo} ("
+                                          + ("rows stored into the neighbours' ghost rows by the update kernel, peer memory"
+                                             if args.halo == "p2p" else "NCCL send/recv of one row each way")
+                                          + ") + all_reduce(MAX) of max|u|,|v| per step"},
+                "roofline": {"kernel": "stencil_march_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                             "frac": gbs / hbm, "traffic": None, "peak_source": which,
+                             "note": "per GPU, 16 algorithmic B/cell; the step also holds the dt all-reduce(MAX) and the halo exchange"},
+                "cpu_baseline": None, "e2e": None, "gpu_launches": K, "clocks": clk.summary(), "finite": finite}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -439,10 +511,13 @@ def main():
     ap.add_argument("--workload", default="rollout512", choices=sorted(WORKLOADS))
     ap.add_argument("--conv", default="auto", choices=["auto", "ffma", "umma_3xtf32", "umma_bf16", "umma_f16x2", "row_f16x2", "row_bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p"], help="slab workloads: how the one-row T halo moves")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
+    elif args.workload.startswith("slab"):
+        run_slab(args, wl)
     else:
         run_ours(args, wl)
 

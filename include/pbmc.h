@@ -168,6 +168,17 @@ int pbmc_advect_diffuse(const float* T, const float* u, const float* v, const fl
                         const pbmc_member* members, const uint32_t* uvmax_in, int member_stride, double dx_min,
                         double cn_max, double dt_fixed, float* T_out, uint32_t* uvmax_out, double* dt_out, int B, int H,
                         int W, void* stream);
+/* Row-slab form for a grid decomposed over several GPUs (new: the reference is single-device).
+ * T, u, v, T_out are the LOCAL [H][W] arrays of one rank, ghost rows included: has_up / has_down say that local
+ * row 0 / H-1 is a ghost row (a neighbour's row) instead of a wall; ghost rows are read, never written.
+ * ycoef [3][H] must be the slice of the GLOBAL coefficients.  If peer_*_ghost_row is non-NULL the first / last
+ * OWNED row of T_out is additionally stored there -- a pointer into the neighbour rank's T_out ghost row
+ * (peer memory over NVLink): the halo exchange is fused into the update, no send/recv follows.  The caller
+ * orders steps across ranks (the per-step dt all-reduce does).  Needs W % 4 == 0 and 16-byte aligned rows. */
+int pbmc_advect_diffuse_slab(const float* T, const float* u, const float* v, const float* xcoef, const float* ycoef,
+                             const pbmc_member* members, const uint32_t* uvmax_in, double dx_min, double cn_max,
+                             double dt_fixed, float* T_out, uint32_t* uvmax_out, double* dt_out, int H, int W, int has_up,
+                             int has_down, float* peer_up_ghost_row, float* peer_down_ghost_row, void* stream);
 /* max|u|,|v| over the interior as a stand-alone reduction (only needed when nothing upstream produced it) */
 int pbmc_uvmax(const float* u, const float* v, uint32_t* uvmax, int member_stride, int B, int H, int W, void* stream);
 /* general form, exactly ADNet's inputs tensor: xc, yc as [H][W] fields (coord_batch_stride = 0) or

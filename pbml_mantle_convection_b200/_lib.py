@@ -70,6 +70,7 @@ SIGNATURES = {
     "pbmc_bicubic_up": (_i, [C.POINTER(Src), _vp, _i, _i, _i, _i, _i, _vp]),
     "pbmc_head": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pbmc_advect_diffuse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "pbmc_advect_diffuse_slab": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pbmc_stencil_coefs": (_i, [_vp, _i, _d, _d, _vp, _vp]),
     "pbmc_uvmax": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "pbmc_advect_diffuse_fields": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _i, _vp, _d, _vp, _vp, _vp, _i, _i,

@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
               v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, bb.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, bb.w);
             }
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = gelu_erf(v[c]);
+            for (int c = 0; c < 16; c += 2) gelu_erf2(v[c], v[c + 1]);  // packed fp32x2 FMAs, bit-identical to gelu_erf
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

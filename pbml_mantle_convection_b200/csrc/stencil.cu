@@ -21,6 +21,11 @@ struct StencilParams {
   const pbmc_member* mem; const uint32_t* uvmax_in; uint32_t* uvmax_out; float* T_out; double* dt_out;
   double dx_min, cn_max, dt_fixed;
   int member_stride, H, W;
+  // row-slab extras (pbmc_advect_diffuse_slab): rows outside [store_lo, store_hi) are ghost rows and are not
+  // written; the first / last owned row is ALSO stored into the neighbour rank's ghost row (peer memory)
+  int store_lo, store_hi, push_up_row, push_down_row;
+  float* push_up;
+  float* push_down;
 };
 
 __device__ __forceinline__ double cfl_dt(double uvm, double dx_min, double cn_max) {
@@ -268,7 +273,13 @@ __global__ void __launch_bounds__(128) stencil_march_kernel(const StencilParams 
       if (x0 == 0) o[0] = o[1];
       if (x0 + 4 == W) o[3] = o[2];
     }
-    if (act) __stcs(reinterpret_cast<float4*>(To + (size_t)r * W + x0), make_float4(o[0], o[1], o[2], o[3]));
+    if (act && r >= p.store_lo && r < p.store_hi) {
+      const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+      __stcs(reinterpret_cast<float4*>(To + (size_t)r * W + x0), o4);
+      // fused halo exchange: the slab's boundary rows go straight into the neighbours' ghost rows over NVLink
+      if (r == p.push_up_row && p.push_up != nullptr) *reinterpret_cast<float4*>(p.push_up + x0) = o4;
+      if (r == p.push_down_row && p.push_down != nullptr) *reinterpret_cast<float4*>(p.push_down + x0) = o4;
+    }
     Tm = Tc; Tc = Tp; Tp = Tn;
     uc = un; vc = vn; hl = hln; hr = hrn; cyt = cytn; cyb = cybn; cyc = cycn;
   }
@@ -419,18 +430,21 @@ extern "C" int pbmc_stencil_coefs(const double* coord, int n, double wall_lo, do
   return PBMC_OK;
 }
 
-extern "C" int pbmc_advect_diffuse(const float* T, const float* u, const float* v, const float* x, const float* y,
-                                   const pbmc_member* members, const uint32_t* uvmax_in, int member_stride,
-                                   double dx_min, double cn_max, double dt_fixed, float* T_out, uint32_t* uvmax_out,
-                                   double* dt_out, int B, int H, int W, void* stream) {
+static int advect_diffuse_launch(const float* T, const float* u, const float* v, const float* x, const float* y,
+                                 const pbmc_member* members, const uint32_t* uvmax_in, int member_stride, double dx_min,
+                                 double cn_max, double dt_fixed, float* T_out, uint32_t* uvmax_out, double* dt_out, int B, int H,
+                                 int W, int has_up, int has_down, float* peer_up, float* peer_down, void* stream) {
   if (!T || !u || !v || !x || !y || !T_out) return PBMC_ERR_NULL_POINTER;
   if (!(dt_fixed > 0.0) && !uvmax_in) return PBMC_ERR_NULL_POINTER;
   if (B <= 0 || H < 3 || W < 3 || (member_stride != 0 && member_stride != 1)) return PBMC_ERR_BAD_SHAPE;
   if (T == T_out) return PBMC_ERR_UNSUPPORTED;  // out-of-place only (neighbours are read)
-  StencilParams p{T, u, v, x, y, members, uvmax_in, uvmax_out, T_out, dt_out, dx_min, cn_max, dt_fixed, member_stride, H, W};
+  const bool slab = has_up || has_down || peer_up || peer_down;
+  StencilParams p{T, u, v, x, y, members, uvmax_in, uvmax_out, T_out, dt_out, dx_min, cn_max, dt_fixed, member_stride, H, W,
+                  has_up ? 1 : 0, has_down ? H - 1 : H, has_up ? 1 : -1, has_down ? H - 2 : -1, peer_up, peer_down};
   const bool vec = (W % 4 == 0) && aligned16(T) && aligned16(u) && aligned16(v) && aligned16(T_out);
   static const int tiled = getenv("PBMC_STENCIL_TILED") ? atoi(getenv("PBMC_STENCIL_TILED")) : 0;  // developer knob: old kernel
-  if (vec && aligned16(x) && !tiled) {
+  if (vec && aligned16(x) && (!tiled || slab)) {
+    if ((peer_up && !aligned16(peer_up)) || (peer_down && !aligned16(peer_down))) return PBMC_ERR_MISALIGNED;
     // rows per warp: enough warps to fill the machine (148 SMs x 16 warps), at most 64 rows (2/rpw halo re-read)
     const int strips = cdiv(W, 128);
     long want = ((long)H * strips * B + 2367) / 2368;
@@ -441,6 +455,7 @@ extern "C" int pbmc_advect_diffuse(const float* T, const float* u, const float* 
     PBMC_CHECK_LAUNCH("stencil_march_kernel");
     return PBMC_OK;
   }
+  if (slab) return PBMC_ERR_UNSUPPORTED;  // the slab form needs 16-byte aligned rows (W % 4 == 0)
   const int TW = vec ? ST_BX * 4 : ST_BX;
   dim3 grid(cdiv(W, TW), cdiv(H, ST_TH), B);
   if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
@@ -450,6 +465,24 @@ extern "C" int pbmc_advect_diffuse(const float* T, const float* u, const float* 
     stencil_kernel<1><<<grid, dim3(ST_BX, ST_BY), 0, (cudaStream_t)stream>>>(p);
   PBMC_CHECK_LAUNCH("stencil_kernel");
   return PBMC_OK;
+}
+
+extern "C" int pbmc_advect_diffuse(const float* T, const float* u, const float* v, const float* x, const float* y,
+                                   const pbmc_member* members, const uint32_t* uvmax_in, int member_stride,
+                                   double dx_min, double cn_max, double dt_fixed, float* T_out, uint32_t* uvmax_out,
+                                   double* dt_out, int B, int H, int W, void* stream) {
+  return advect_diffuse_launch(T, u, v, x, y, members, uvmax_in, member_stride, dx_min, cn_max, dt_fixed, T_out, uvmax_out,
+                               dt_out, B, H, W, 0, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int pbmc_advect_diffuse_slab(const float* T, const float* u, const float* v, const float* x, const float* y,
+                                        const pbmc_member* members, const uint32_t* uvmax_in, double dx_min, double cn_max,
+                                        double dt_fixed, float* T_out, uint32_t* uvmax_out, double* dt_out, int H, int W,
+                                        int has_up, int has_down, float* peer_up_ghost_row, float* peer_down_ghost_row,
+                                        void* stream) {
+  if ((peer_up_ghost_row && !has_up) || (peer_down_ghost_row && !has_down)) return PBMC_ERR_BAD_SHAPE;
+  return advect_diffuse_launch(T, u, v, x, y, members, uvmax_in, 0, dx_min, cn_max, dt_fixed, T_out, uvmax_out, dt_out, 1, H, W,
+                               has_up, has_down, peer_up_ghost_row, peer_down_ghost_row, stream);
 }
 
 extern "C" int pbmc_uvmax(const float* u, const float* v, uint32_t* uvmax, int member_stride, int B, int H, int W,

@@ -320,6 +320,21 @@ def advect_diffuse(T, u, v, xcoef, ycoef, members, uvmax, dx_min, cn_max, per_me
     return T_out, dt_out, uv_out
 
 
+def advect_diffuse_slab(T, u, v, xcoef, ycoef, members, uvmax, dx_min, cn_max, T_out, dt_out, has_up, has_down,
+                        peer_up_row_ptr=0, peer_down_row_ptr=0, dt_fixed=0.0, uv_out=None):
+    """One rank's row slab of a decomposed grid (T, u, v [1,rows,W] with ghost rows).  peer_*_row_ptr: raw device
+    addresses (ints) of the neighbours' ghost rows in THEIR T_out (peer memory), 0 = no fused push."""
+    _chk_cuda(T, u, v, xcoef, ycoef, T_out)
+    _, H, W = T.shape
+    assert xcoef.shape == (3, W) and ycoef.shape == (3, H) and T.shape[0] == 1
+    L.check(L.load().pbmc_advect_diffuse_slab(L.ptr(T), L.ptr(u), L.ptr(v), L.ptr(xcoef), L.ptr(ycoef), L.ptr(members),
+                                              L.ptr(uvmax), float(dx_min), float(cn_max), float(dt_fixed), L.ptr(T_out),
+                                              L.ptr(uv_out), L.ptr(dt_out), H, W, int(bool(has_up)), int(bool(has_down)),
+                                              int(peer_up_row_ptr) or None, int(peer_down_row_ptr) or None,
+                                              L.stream_ptr(T.device)), "pbmc_advect_diffuse_slab")
+    return T_out, dt_out
+
+
 def advect_diffuse_fields(T, u, v, xc, yc, raq_field, members, uvmax, dx_min_dev, cn_max, per_member_dt=False,
                           dt_fixed_dev=None):
     """General form (coordinates as float64 fields, RaQ optionally a field; ADNet.forward semantics)."""

@@ -74,3 +74,30 @@ def test_world_one_slab_is_the_plain_kernel():
     st.scatter(T, u, v)
     st.step(3)
     assert np.array_equal(st.gather().cpu().numpy(), ref) and float(st.last_dt[0]) == ref_dts[-1]
+
+
+@pytest.mark.parametrize("H,W,world", [(64, 128, 2), (71, 256, 3)])
+def test_fused_halo_push_emulated(H, W, world):
+    """`pbmc_advect_diffuse_slab` with peer ghost-row pointers: the first / last owned row of the output is also
+    stored into the neighbour's ghost row by the update kernel itself (no exchange step).  The 'peers' are slabs on
+    the same GPU here; on a multi-GPU box the same pointers come from symmetric memory (SlabStencil halo='p2p')."""
+    xc, yc, T, u, v = _fields(H, W, seed=13)
+    raq, steps = 1.5, 4
+    ref, ref_dts = _single_gpu(xc, yc, T, u, v, steps, raq)
+    sts = [MG.SlabStencil(H, W, xc[0], yc[:, 0], r, world, DEV, raq=raq, cn_max=0.99) for r in range(world)]
+    for st in sts:
+        st.scatter(T, u, v)
+    bufs = [[st.T.clone(), torch.full_like(st.T, float("nan"))] for st in sts]  # ping-pong per slab; NaN = never written
+    dt = torch.zeros(1, dtype=torch.float64, device=DEV)
+    for k in range(steps):
+        i, o = k % 2, (k + 1) % 2
+        bits = torch.stack([st.local_uvmax(st.u, st.v) for st in sts]).max(0).values
+        for r, st in enumerate(sts):
+            s = st.slab
+            up = bufs[r - 1][o][0, sts[r - 1].slab.rows - 1].data_ptr() if s.up else 0
+            down = bufs[r + 1][o][0, 0].data_ptr() if s.down else 0
+            ops.advect_diffuse_slab(bufs[r][i], st.u, st.v, st.xcoef, st.ycoef, st.members, bits, st.dx_min, 0.99, bufs[r][o], dt,
+                                    s.up, s.down, up, down)
+    got = np.concatenate([st.slab.owned(bufs[r][steps % 2])[0].cpu().numpy() for r, st in enumerate(sts)], 0)
+    assert np.array_equal(got, ref), np.abs(got - ref).max()
+    assert float(dt[0]) == ref_dts[-1]
