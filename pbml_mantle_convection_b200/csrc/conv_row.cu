@@ -504,6 +504,118 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
       g += CR_NPG;
       while (g >= NG) { g -= NG; ++ri; }
     };
+    // ---- fast path: ONE full 16-channel group (every trunk layer and the two last head convs: 25 of the 28 convs
+    // of a forward).  A stage is then simply an input row; everything that does not change from row to row is
+    // hoisted, the body is straight-line: the generic loop below spends ~330 instructions per stage on
+    // bookkeeping and the stage rate of a CTA is bounded by exactly this serial, single-warp chain.
+    if (NG == 1 && gtab[0].nb == 4 && (gtab[0].xform == PBMC_XFORM_NONE || gtab[0].xform == PBMC_XFORM_GN_GELU)) {
+      const RowGroup gi = gtab[0];
+      const bool do_x = gi.xform == PBMC_XFORM_GN_GELU;
+      const size_t pstride = plane_px * 4;
+      const float* cb0 = gi.base + (size_t)(sx < 0 ? 0 : sx) * 4;  // this thread's column, channel block 0
+      const float* cb1 = cb0 + pstride;
+      const float* cb2 = cb1 + pstride;
+      const float* cb3 = cb2 + pstride;
+      // halo (warp 0 of the group, KS == 3: lane = (extra position e, channel ch))
+      const int hch = lane & 15, he = lane >> 4;
+      const bool h_on = wq == 0 && hok[0];
+      const float* hbase = gi.base + (size_t)(hch >> 2) * pstride + (size_t)(h_on ? hsx[0] : 0) * 4 + (hch & 3);
+      const float h_a = do_x ? xf_a[gi.chan0 + hch] : 1.f, h_b = do_x ? xf_b[gi.chan0 + hch] : 0.f;
+      const uint32_t h_off = (uint32_t)(((hch >> 3) * PLANE + 128 + he) * 16 + (hch & 7) * 2);
+      const uint32_t as_addr = smem_u32(As) + (uint32_t)i * 16u;
+      const uint32_t xfa_addr = smem_u32(xf_a + gi.chan0), xfb_addr = smem_u32(xf_b + gi.chan0);
+      const size_t rstride = (size_t)W * 4;
+      struct FBuf {
+        float4 v0, v1, v2, v3;
+        float h;
+        bool ok;
+      };
+      auto fload = [&](int ri, FBuf& B) {
+        const int sy = pad_index(y0 - P + ri, H, p.pad_mode);
+        B.ok = sy >= 0;
+        const size_t ro = (size_t)(sy < 0 ? 0 : sy) * rstride;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        B.v0 = B.v1 = B.v2 = B.v3 = z;
+        B.h = 0.f;
+        if (col_ok && sy >= 0) {
+          B.v0 = ldg4(cb0 + ro); B.v1 = ldg4(cb1 + ro); B.v2 = ldg4(cb2 + ro); B.v3 = ldg4(cb3 + ro);
+        }
+        if (h_on && sy >= 0) B.h = __ldg(hbase + ro);
+      };
+      auto fproc = [&](int st, FBuf& B) {
+        if (tr_lane) CR_TR(100 + pg * 300 + 4 * (st / CR_NPG));
+        float v[16] = {B.v0.x, B.v0.y, B.v0.z, B.v0.w, B.v1.x, B.v1.y, B.v1.z, B.v1.w,
+                       B.v2.x, B.v2.y, B.v2.z, B.v2.w, B.v3.x, B.v3.y, B.v3.z, B.v3.w};
+        float hv = B.h;
+        if (do_x && B.ok) {
+          if (col_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 a, bb;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(xfa_addr + j * 16));
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w) : "r"(xfb_addr + j * 16));
+              v[4 * j + 0] = fmaf(v[4 * j + 0], a.x, bb.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, bb.y);
+              v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, bb.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, bb.w);
+            }
+#pragma unroll
+            for (int c2 = 0; c2 < 16; c2 += 2) gelu_erf2(v[c2], v[c2 + 1]);
+          }
+          if (h_on) hv = gelu_erf(fmaf(hv, h_a, h_b));
+        }
+        const uint32_t slot = (uint32_t)st & (NSTAGE - 1);
+        const uint32_t sa = as_addr + slot * (uint32_t)G::STAGE_BYTES;
+        if (tr_lane) CR_TR(101 + pg * 300 + 4 * (st / CR_NPG));
+        if (st >= NSTAGE) mbar_wait_parked(a_empty(slot), (((uint32_t)st / NSTAGE) & 1u) ^ 1u);  // first pass: ring is free
+        if (tr_lane) CR_TR(102 + pg * 300 + 4 * (st / CR_NPG));
+        auto sts = [](uint32_t addr, uint4 q) {
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+        };
+        if (CR_DBG(4)) {
+        } else if (PARTS == 2) {
+          uint4 h0, l0, h1, l1;
+          split_f16(v, h0, l0);
+          split_f16(v + 8, h1, l1);
+          sts(sa, h0);
+          sts(sa + PLANE * 16, h1);
+          sts(sa + 2 * PLANE * 16, l0);
+          sts(sa + 3 * PLANE * 16, l1);
+        } else {
+          sts(sa, pack_bf16(v));
+          sts(sa + PLANE * 16, pack_bf16(v + 8));
+        }
+        if (wq == 0 && he < KS - 1) {
+          const uint32_t ha = smem_u32(As) + slot * (uint32_t)G::STAGE_BYTES + h_off;
+          if (PARTS == 2) {
+            const __half hh = __float2half_rn(hv);
+            const __half hl = __float2half_rn(hv - __half2float(hh));
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha), "h"(__half_as_ushort(hh)) : "memory");
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha + (uint32_t)G::PART_BYTES), "h"(__half_as_ushort(hl)) : "memory");
+          } else {
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha), "h"(__bfloat16_as_ushort(__float2bfloat16_rn(hv))) : "memory");
+          }
+        }
+        if (!CR_DBG(32)) fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full(slot));
+        if (tr_lane) CR_TR(103 + pg * 300 + 4 * (st / CR_NPG));
+      };
+      static_assert(KS == 3 || HITEMS == 2, "halo lanes");
+      if (KS == 3) {
+        FBuf f0, f1;
+        if (pg < nin) fload(pg, f0);
+        if (pg + CR_NPG < nin) fload(pg + CR_NPG, f1);
+        for (int st = pg; st < nin; st += 2 * CR_NPG) {
+          fproc(st, f0);
+          if (st + 2 * CR_NPG < nin) fload(st + 2 * CR_NPG, f0);
+          if (st + CR_NPG < nin) {
+            fproc(st + CR_NPG, f1);
+            if (st + 3 * CR_NPG < nin) fload(st + 3 * CR_NPG, f1);
+          }
+        }
+        goto producer_done;
+      }
+    }
+    {
     Buf b0, b1;
     int cg = pg, cri = 0;  // (row, group) of the stage processed next
     while (cg >= NG) { cg -= NG; ++cri; }
@@ -524,6 +636,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         advance(cri, cg);
       }
     }
+    }
+  producer_done:;
   } else {
     // ================================================================ MMA issuer
     // The whole warp walks the (uniform) pipeline state; one elected lane issues tcgen05.mma / commit.

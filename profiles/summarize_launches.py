@@ -17,7 +17,7 @@ def main(path, step_index=3):
         raise SystemExit(f"need two build_input launches to delimit a step; the capture has {len(idx)} (skip more warm-up launches: ncu -s)")
     step_index = min(step_index, len(idx) - 2)
     step = seq[idx[step_index]:idx[step_index + 1]]
-    own = [s for s in step if "pbmc::" in s[0]]
+    own = [s for s in step if "pbmc::" in s[0]] or [s for s in step if "at::" not in s[0] and "nccl" not in s[0].lower()]
     tot = sum(v for _, v, _ in own)
     print(f"# one rollout step: {len(own)} pbmc kernels, sum of serialised cold-cache durations {tot/1e3:.1f} us")
     agg = collections.OrderedDict()
