@@ -398,12 +398,19 @@ def run_ours(args, wl):
                  "stencil": roofs["stencil"]["ms"]}
         dom = max(share, key=share.get)
         r = roofs[dom]
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if args.workload == "rollout512" and os.path.exists(tpath):  # recorded ncu capture of this kernel at this shape
+            rec = json.load(open(tpath)).get(dom)
+            if rec:
+                traffic, traffic_src = rec["dram_bytes_per_launch"], rec["source"]
         roofline = {"kernel": dom, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
-                    "frac": r["frac"], "traffic": None, "peak_source": r["peak_source"], "ms_per_launch": r["ms"],
-                    "share_of_step": share[dom] / step_ms}
+                    "frac": r["frac"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)",
+                    "traffic_source": traffic_src, "algorithmic_bytes_per_launch": B * H * W * (128 if dom == "conv16x16_l0" else 480 if dom == "conv1_103x16" else 16),
+                    "peak_source": r["peak_source"], "ms_per_launch": r["ms"], "share_of_step": share[dom] / step_ms}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            n_cpu = max(2, min(10, int(20.0 / (2.5e-6 * H * W))))  # ~10-30 s of CPU work
+            n_cpu = max(2, min(60, int(15.0 / (1.45e-6 * H * W))))  # ~10-30 s of CPU work (0.38 s per 512^2 step on 16 cores)
             rate, secs, threads = cpu_port_rate(H, W, n_cpu)
             cpu = {"value": rate, "unit": "cell-updates/s", "cores": threads, "kind": "port",
                    "sample": f"{n_cpu} time steps of the same {H}x{W} batch-1 rollout, float64 ATen-CPU port of the "
