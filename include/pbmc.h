@@ -121,7 +121,7 @@ typedef struct {
   int pad_mode; /* PBMC_PAD_* */
   int epi_act;  /* PBMC_ACT_* */
   int impl;     /* PBMC_CONV_* */
-  int reserved;
+  int max_ctas; /* 0 = fill the GPU; > 0: use at most this many CTAs (several convs sharing the GPU on different streams) */
   const float* wpk;
   const void* wpk_umma;  /* tensor-core operand image of the same weights (NULL => FFMA only) */
   const void* wpk_row;   /* operand image for the row-streaming tensor-core kernel (NULL => not available) */

@@ -36,7 +36,7 @@ class Src(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [("src", Src * MAX_SRC), ("nsrc", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
                 ("cout", C.c_int), ("ksize", C.c_int), ("pad_mode", C.c_int), ("epi_act", C.c_int), ("impl", C.c_int),
-                ("reserved", C.c_int), ("wpk", C.c_void_p), ("wpk_umma", C.c_void_p), ("wpk_row", C.c_void_p),
+                ("max_ctas", C.c_int), ("wpk", C.c_void_p), ("wpk_umma", C.c_void_p), ("wpk_row", C.c_void_p),
                 ("bias", C.c_void_p), ("out", C.c_void_p), ("out_stats", C.c_void_p), ("out_chan_sum", C.c_void_p)]
 
 

@@ -30,6 +30,7 @@ struct pbmc_ctx {
   cudaStream_t s[NSTREAM];
   cudaEvent_t ev_fork[NSTREAM + 2];
   cudaEvent_t ev_join[NSTREAM];
+  cudaEvent_t ev_in, ev_out;
 };
 
 extern "C" const char* pbmc_error_string(int st) {
@@ -121,11 +122,17 @@ extern "C" int pbmc_conv_fwd(const pbmc_conv_desc* d, void* stream) {
 extern "C" int pbmc_ctx_create(pbmc_ctx** out) {
   if (!out) return PBMC_ERR_NULL_POINTER;
   pbmc_ctx* c = new pbmc_ctx();
+  // s[0] carries the critical chain (conv0 -> level-0 trunk -> conv1..3 -> head) at the highest priority, the
+  // coarse pyramid levels run on s[1..] at the lowest: a level-0 CTA never queues behind coarse-level work
+  int prio_lo = 0, prio_hi = 0;
+  PBMC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (int i = 0; i < pbmc_ctx::NSTREAM; ++i) {
-    PBMC_CUDA(cudaStreamCreateWithFlags(&c->s[i], cudaStreamNonBlocking));
+    PBMC_CUDA(cudaStreamCreateWithPriority(&c->s[i], cudaStreamNonBlocking, i == 0 ? prio_hi : prio_lo));
     PBMC_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
   }
   for (int i = 0; i < pbmc_ctx::NSTREAM + 2; ++i) PBMC_CUDA(cudaEventCreateWithFlags(&c->ev_fork[i], cudaEventDisableTiming));
+  PBMC_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+  PBMC_CUDA(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
   *out = c;
   return PBMC_OK;
 }
@@ -136,6 +143,8 @@ extern "C" int pbmc_ctx_destroy(pbmc_ctx* c) {
     cudaEventDestroy(c->ev_join[i]);
   }
   for (int i = 0; i < pbmc_ctx::NSTREAM + 2; ++i) cudaEventDestroy(c->ev_fork[i]);
+  cudaEventDestroy(c->ev_in);
+  cudaEventDestroy(c->ev_out);
   delete c;
   return PBMC_OK;
 }
@@ -221,9 +230,26 @@ extern "C" size_t pbmc_workspace_bytes(const pbmc_net* n, int B, int H, int W) {
   } while (0)
 
 // Enqueue one surrogate forward.  `uv` points at the 2*B uint32 slots (uvmax of this step).
+static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, char* ws, const float* inp,
+                                const pbmc_member* members, float* u, float* v, float* p, uint32_t* uvmax, int B, int H,
+                                int W, cudaStream_t st);
+
+// The forward runs on the context's high-priority stream, forked from / joined to the caller's stream.
 static int surrogate_enqueue(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, char* ws, const float* inp,
                              const pbmc_member* members, float* u, float* v, float* p, uint32_t* uvmax, int B, int H,
-                             int W, cudaStream_t st) {
+                             int W, cudaStream_t caller) {
+  PBMC_CUDA(cudaEventRecord(ctx->ev_in, caller));
+  PBMC_CUDA(cudaStreamWaitEvent(ctx->s[0], ctx->ev_in, 0));
+  const int rc = surrogate_enqueue_on(ctx, n, P, ws, inp, members, u, v, p, uvmax, B, H, W, ctx->s[0]);
+  // join even on error so that a capture in progress is not left with a dangling fork
+  cudaEventRecord(ctx->ev_out, ctx->s[0]);
+  cudaStreamWaitEvent(caller, ctx->ev_out, 0);
+  return rc;
+}
+
+static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, char* ws, const float* inp,
+                                const pbmc_member* members, float* u, float* v, float* p, uint32_t* uvmax, int B, int H,
+                                int W, cudaStream_t st) {
   const int L = P.L, R = P.R, CB = P.CB;
   auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto S = [&](int slot) { return reinterpret_cast<double*>(ws + P.stat_off(slot, B)); };
@@ -241,6 +267,24 @@ static int surrogate_enqueue(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, ch
   PBMC_CUDA(cudaEventRecord(ctx->ev_fork[0], st));
 
   // pyramid levels (:1319-1327): level l runs on stream l (level 0 on the caller's stream)
+  // The L level chains run side by side and a tensor-core conv CTA owns an SM, so each level gets a share of the
+  // 148 SMs in proportion to its row-strip count (with a floor so that the small levels do not become the
+  // longest chain): every level then needs about the same time per layer instead of each launch trying to
+  // fill the GPU on its own and queueing behind the others.
+  int cta_budget[PBMC_MAX_LEVELS];
+  {
+    double tot = 0.0, w[PBMC_MAX_LEVELS];
+    for (int l = 0; l < L; ++l) { w[l] = (double)B * ((P.Wl[l] + 127) / 128) * P.Hl[l]; tot += w[l]; }
+    for (int l = 0; l < L; ++l) {
+      const int strips = B * ((P.Wl[l] + 127) / 128);
+      int share = (int)(148.0 * w[l] / tot);
+      const int floor_ctas = strips * ((P.Hl[l] + 7) / 8);  // no need for more than one CTA per 8 rows
+      int want = share < 2 ? 2 : share;
+      if (want > floor_ctas) want = floor_ctas;
+      if (want < strips) want = strips;
+      cta_budget[l] = L > 1 ? want : 0;
+    }
+  }
   const float* level_in[PBMC_MAX_LEVELS];
   level_in[0] = F(P.x0);
   for (int l = 0; l < L; ++l) {
@@ -259,6 +303,7 @@ static int surrogate_enqueue(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, ch
     for (int r = 0; r < R; ++r) {
       const pbmc_layer& Lr = n.trunk[l * PBMC_MAX_REPEATS + r];
       fill_conv(d, n, Lr, B, Hl, Wl, F(P.ping[l][r & 1]), S(1 + l * R + r), nullptr, PBMC_ACT_NONE);
+      d.max_ctas = cta_budget[l];
       d.nsrc = 1;
       if (r == 0) {
         d.src[0] = (l == 0) ? make_src(F(P.x0), CB, PBMC_XFORM_GN_GELU, S(0), &n.conv0, invc)

@@ -48,6 +48,7 @@ struct ConvRowParams {
   int ngroups;  // 16-channel K groups over the concatenated sources
   int cin_ch;   // padded channel count of the concatenation (sum nblk * 4)
   int rpc;      // output rows per CTA
+  int max_ctas; // CTA budget (0 = whole GPU)
   const void* wpk;  // [group][dx][part][2 K-chunks][N = k*16 rows (dy, c_out)][8 c_in] 16-bit
   const float* bias;
   float* out;
@@ -705,9 +706,14 @@ extern "C" void pbmc_debug_set_row_trace(void* dev_buf) { g_row_trace = reinterp
 #endif
 
 // rows per CTA: minimise waves * (rows + halo + fixed per-CTA cost in row units)
-static int choose_rpc(int units, int H, int ks) {
+static int choose_rpc(int units, int H, int ks, int max_ctas) {
   static const int forced = getenv("PBMC_ROW_RPC") ? atoi(getenv("PBMC_ROW_RPC")) : 0;  // developer knob
   if (forced > 0) return forced < H ? forced : H;
+  if (max_ctas > 0) {
+    // a share of the GPU: the fewest rows per CTA that stay within the CTA budget (the conv runs next to others)
+    for (int r = 1; r <= H; ++r)
+      if ((long)units * cdiv(H, r) <= max_ctas || r == H) return r;
+  }
   int best = 1;
   double best_cost = 1e30;
   for (int r = 1; r <= 64 && r <= H; ++r) {
@@ -730,7 +736,7 @@ static int launch_row(ConvRowParams& p, cudaStream_t st) {
     attr_set = true;
   }
   const int nstrips = cdiv(p.W, 128);
-  p.rpc = choose_rpc(nstrips * p.B, p.H, KS);
+  p.rpc = choose_rpc(nstrips * p.B, p.H, KS, p.max_ctas);
   dim3 grid(cdiv(p.H, p.rpc), nstrips, p.B);
   if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
   conv_row_kernel<KS, PARTS><<<grid, CR_THREADS, smem, st>>>(p);
@@ -773,6 +779,7 @@ int conv_row_dispatch(const pbmc_conv_desc& d, cudaStream_t st) {
   p.ngroups = row_groups(d);
   p.cin_ch = cin;
   p.rpc = 1;
+  p.max_ctas = d.max_ctas;
   p.trace = nullptr;
   p.dbg_dx = getenv("PBMC_ROW_DBG_DX") ? atoi(getenv("PBMC_ROW_DBG_DX")) : 16;
   p.dbg_flags = getenv("PBMC_ROW_DBG_FLAGS") ? atoi(getenv("PBMC_ROW_DBG_FLAGS")) : 0;

@@ -109,7 +109,7 @@ __global__ void avgpool2_kernel(const pbmc_src S, float* __restrict__ dst, int H
 // ---------------------------------------------------------------- A5: bicubic up-sampling
 // nn.Upsample(size, mode="bicubic"): align_corners=False, A = -0.75, source index
 // scale*(dst+0.5)-0.5 NOT clamped, the four taps clamped to [0, n-1].
-constexpr int BU_TW = 32, BU_TH = 8;  // output tile; 256 threads, one output pixel (float4) each
+constexpr int BU_TW = 128, BU_TH = 8;  // output tile; 256 threads, four output pixels (float4 each) per thread
 constexpr int BU_MAX_SW = BU_TW + 4, BU_MAX_SH = BU_TH + 4;
 
 __device__ __forceinline__ void cubic_w(float t, float w[4]) {
@@ -128,19 +128,19 @@ __device__ __forceinline__ int src_floor(int d, float scale, float& t) {
   return (int)f;
 }
 
-__global__ void __launch_bounds__(BU_TW* BU_TH) bicubic_kernel(const pbmc_src S, float* __restrict__ dst, int Hs, int Ws,
-                                                                int H, int W, float sy_scale, float sx_scale) {
+// Separable in shared memory, same association as oracle/ref_numpy.bicubic_upsample (rows first, then columns):
+//   pass 1  colv[r][c] = sum_ky wy_r[ky] * src[cy_r[ky]][c]      for the 8 output rows x the tile's source columns
+//   pass 2  out[r][x]  = sum_kx wx_x[kx] * colv[r][cx_x[kx]]
+// i.e. 4 + <=4 shared-memory reads per output instead of 16 (the first version was shared-memory bound: 16.6 us per level).
+__global__ void __launch_bounds__(256) bicubic_kernel(const pbmc_src S, float* __restrict__ dst, int Hs, int Ws, int H, int W,
+                                                      float sy_scale, float sx_scale) {
   __shared__ float4 tile[BU_MAX_SH][BU_MAX_SW];
+  __shared__ float4 colv[BU_TH][BU_MAX_SW];
   __shared__ float a4[4], b4[4];
+  __shared__ float wy_s[BU_TH][4];
+  __shared__ int cy_s[BU_TH][4];
   const int cb = blockIdx.z % S.nblk, b = blockIdx.z / S.nblk;
-  const int tid = threadIdx.y * BU_TW + threadIdx.x;
-  if (tid < 4) {
-    float a = 1.f, bb = 0.f;
-    if (S.xform == PBMC_XFORM_GN_GELU || S.xform == PBMC_XFORM_GN)
-      gn_coeffs(S.stats + ((size_t)b * S.nblk + cb) * 2, S.inv_count, S.gamma[cb * 4 + tid], S.beta[cb * 4 + tid], a, bb);
-    a4[tid] = a;
-    b4[tid] = bb;
-  }
+  const int tid = threadIdx.x;
   const int ox0 = blockIdx.x * BU_TW, oy0 = blockIdx.y * BU_TH;
   const int ox1 = min(ox0 + BU_TW, W) - 1, oy1 = min(oy0 + BU_TH, H) - 1;
   float tdum;
@@ -148,41 +148,63 @@ __global__ void __launch_bounds__(BU_TW* BU_TH) bicubic_kernel(const pbmc_src S,
   const int fx0 = max(src_floor(ox0, sx_scale, tdum) - 1, 0), fx1 = min(src_floor(ox1, sx_scale, tdum) + 2, Ws - 1);
   const int fy0 = max(src_floor(oy0, sy_scale, tdum) - 1, 0), fy1 = min(src_floor(oy1, sy_scale, tdum) + 2, Hs - 1);
   const int fw = fx1 - fx0 + 1, fh = fy1 - fy0 + 1;  // <= BU_T? + 4 because scale <= 1
+  if (tid < 4) {
+    float a = 1.f, bb = 0.f;
+    if (S.xform == PBMC_XFORM_GN_GELU || S.xform == PBMC_XFORM_GN)
+      gn_coeffs(S.stats + ((size_t)b * S.nblk + cb) * 2, S.inv_count, S.gamma[cb * 4 + tid], S.beta[cb * 4 + tid], a, bb);
+    a4[tid] = a;
+    b4[tid] = bb;
+  }
+  if (tid >= 32 && tid < 32 + BU_TH) {
+    const int r = tid - 32, oy = min(oy0 + r, H - 1);
+    float ty, wy[4];
+    const int iy = src_floor(oy, sy_scale, ty);
+    cubic_w(ty, wy);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      wy_s[r][k] = wy[k];
+      cy_s[r][k] = min(max(iy - 1 + k, 0), Hs - 1) - fy0;
+    }
+  }
   __syncthreads();
   const float* base = S.ptr + ((size_t)b * S.nblk + cb) * (size_t)Hs * Ws * 4;
-  for (int e = tid; e < fw * fh; e += BU_TW * BU_TH) {
-    const int r = e / fw, c = e % fw;
+  for (int e = tid; e < fw * fh; e += 256) {
+    const int r = e / fw, c = e - r * fw;
     float4 v = ldg4(base + ((size_t)(fy0 + r) * Ws + fx0 + c) * 4);
     tile[r][c] = xform4(v, a4, b4, S.xform);
   }
   __syncthreads();
-  const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
-  if (ox >= W || oy >= H) return;
-  float tx, ty, wx[4], wy[4];
-  const int ix = src_floor(ox, sx_scale, tx), iy = src_floor(oy, sy_scale, ty);
-  cubic_w(tx, wx);
-  cubic_w(ty, wy);
-  int cx[4], cy[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    cx[k] = min(max(ix - 1 + k, 0), Ws - 1) - fx0;
-    cy[k] = min(max(iy - 1 + k, 0), Hs - 1) - fy0;
-  }
-  // rows first, then columns: same association as oracle/ref_numpy.bicubic_upsample
-  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int kx = 0; kx < 4; ++kx) {
-    float4 colv = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int nrow = oy1 - oy0 + 1;
+  for (int e = tid; e < nrow * fw; e += 256) {
+    const int r = e / fw, c = e - r * fw;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
-      const float4 v = tile[cy[ky]][cx[kx]];
-      colv.x = fmaf(wy[ky], v.x, colv.x); colv.y = fmaf(wy[ky], v.y, colv.y);
-      colv.z = fmaf(wy[ky], v.z, colv.z); colv.w = fmaf(wy[ky], v.w, colv.w);
+      const float w = wy_s[r][ky];
+      const float4 v = tile[cy_s[r][ky]][c];
+      acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
     }
-    o.x = fmaf(wx[kx], colv.x, o.x); o.y = fmaf(wx[kx], colv.y, o.y);
-    o.z = fmaf(wx[kx], colv.z, o.z); o.w = fmaf(wx[kx], colv.w, o.w);
+    colv[r][c] = acc;
   }
-  *reinterpret_cast<float4*>(dst + (((size_t)b * S.nblk + cb) * (size_t)H * W + (size_t)oy * W + ox) * 4) = o;
+  __syncthreads();
+  const int ty_ = tid >> 5, lane = tid & 31;
+  const int oy = oy0 + ty_;
+  if (oy >= H) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ox = ox0 + lane + 32 * j;
+    if (ox >= W) break;
+    float tx, wx[4];
+    const int ix = src_floor(ox, sx_scale, tx);
+    cubic_w(tx, wx);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      const float4 v = colv[ty_][min(max(ix - 1 + kx, 0), Ws - 1) - fx0];
+      o.x = fmaf(wx[kx], v.x, o.x); o.y = fmaf(wx[kx], v.y, o.y); o.z = fmaf(wx[kx], v.z, o.z); o.w = fmaf(wx[kx], v.w, o.w);
+    }
+    *reinterpret_cast<float4*>(dst + (((size_t)b * S.nblk + cb) * (size_t)H * W + (size_t)oy * W + ox) * 4) = o;
+  }
 }
 
 }  // namespace pbmc
@@ -254,7 +276,7 @@ extern "C" int pbmc_bicubic_up(const pbmc_src* S, float* dst, int B, int Hs, int
   if (!aligned16(S->ptr) || !aligned16(dst)) return PBMC_ERR_MISALIGNED;
   dim3 grid(cdiv(W, BU_TW), cdiv(H, BU_TH), B * S->nblk);
   if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
-  bicubic_kernel<<<grid, dim3(BU_TW, BU_TH), 0, (cudaStream_t)stream>>>(*S, dst, Hs, Ws, H, W, (float)Hs / (float)H,
+  bicubic_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*S, dst, Hs, Ws, H, W, (float)Hs / (float)H,
                                                                        (float)Ws / (float)W);
   PBMC_CHECK_LAUNCH("bicubic_kernel");
   return PBMC_OK;
