@@ -616,6 +616,119 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         goto producer_done;
       }
     }
+    // ---- lean path for several groups / partial groups (conv[1]: 7 sources, conv[0]: 8 of 16 channels) with
+    // xform NONE or GN+GELU per group: same straight-line body, the group's few parameters travel with the buffer
+    if (KS == 3) {
+      bool simple = true;
+      for (int g = 0; g < NG; ++g) simple = simple && (gtab[g].xform == PBMC_XFORM_NONE || gtab[g].xform == PBMC_XFORM_GN_GELU);
+      if (simple) {
+        const size_t pstride = plane_px * 4;
+        const size_t coff = (size_t)(sx < 0 ? 0 : sx) * 4;
+        const int hch = lane & 15, he = lane >> 4;
+        const bool h_on = wq == 0 && hok[0];
+        const size_t hoff = (size_t)(hch >> 2) * pstride + (size_t)(h_on ? hsx[0] : 0) * 4 + (hch & 3);
+        const uint32_t h_off = (uint32_t)(((hch >> 3) * PLANE + 128 + he) * 16 + (hch & 7) * 2);
+        const uint32_t as_addr = smem_u32(As) + (uint32_t)i * 16u;
+        const uint32_t xfa0 = smem_u32(xf_a), xfb0 = smem_u32(xf_b);
+        const size_t rstride = (size_t)W * 4;
+        struct GBuf {
+          float4 v0, v1, v2, v3;
+          float h;
+          int chan0;  // >= 0: GN+GELU with the tables at chan0; -1: plain
+          int nb;
+        };
+        auto gload = [&](int ri, int g, GBuf& B) {
+          const int sy = pad_index(y0 - P + ri, H, p.pad_mode);
+          const RowGroup gi = gtab[g];
+          B.chan0 = (gi.xform == PBMC_XFORM_GN_GELU && sy >= 0) ? gi.chan0 : -1;
+          B.nb = gi.nb;
+          const size_t ro = (size_t)(sy < 0 ? 0 : sy) * rstride;
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          B.v0 = B.v1 = B.v2 = B.v3 = z;
+          B.h = 0.f;
+          const float* cb = gi.base + coff + ro;
+          if (col_ok && sy >= 0) {
+            B.v0 = ldg4(cb);
+            if (gi.nb > 1) B.v1 = ldg4(cb + pstride);
+            if (gi.nb > 2) B.v2 = ldg4(cb + 2 * pstride);
+            if (gi.nb > 3) B.v3 = ldg4(cb + 3 * pstride);
+          }
+          if (h_on && sy >= 0 && (hch >> 2) < gi.nb) B.h = __ldg(gi.base + hoff + ro);
+        };
+        auto gproc = [&](int st, GBuf& B) {
+          float v[16] = {B.v0.x, B.v0.y, B.v0.z, B.v0.w, B.v1.x, B.v1.y, B.v1.z, B.v1.w,
+                         B.v2.x, B.v2.y, B.v2.z, B.v2.w, B.v3.x, B.v3.y, B.v3.z, B.v3.w};
+          float hv = B.h;
+          if (B.chan0 >= 0) {
+            if (col_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (j < B.nb) {
+                  float4 a, bb;
+                  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(xfa0 + (B.chan0 + 4 * j) * 4));
+                  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w) : "r"(xfb0 + (B.chan0 + 4 * j) * 4));
+                  v[4 * j + 0] = fmaf(v[4 * j + 0], a.x, bb.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, bb.y);
+                  v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, bb.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, bb.w);
+                  gelu_erf2(v[4 * j + 0], v[4 * j + 1]);
+                  gelu_erf2(v[4 * j + 2], v[4 * j + 3]);
+                }
+              }
+            }
+            if (h_on && (hch >> 2) < B.nb) hv = gelu_erf(fmaf(hv, xf_a[B.chan0 + hch], xf_b[B.chan0 + hch]));
+          }
+          const uint32_t slot = (uint32_t)st & (NSTAGE - 1);
+          const uint32_t sa = as_addr + slot * (uint32_t)G::STAGE_BYTES;
+          if (st >= NSTAGE) mbar_wait_parked(a_empty(slot), (((uint32_t)st / NSTAGE) & 1u) ^ 1u);  // first pass: ring is free
+          auto sts = [](uint32_t addr, uint4 q) {
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+          };
+          if (PARTS == 2) {
+            uint4 h0, l0, h1, l1;
+            split_f16(v, h0, l0);
+            split_f16(v + 8, h1, l1);
+            sts(sa, h0);
+            sts(sa + PLANE * 16, h1);
+            sts(sa + 2 * PLANE * 16, l0);
+            sts(sa + 3 * PLANE * 16, l1);
+          } else {
+            sts(sa, pack_bf16(v));
+            sts(sa + PLANE * 16, pack_bf16(v + 8));
+          }
+          if (wq == 0 && he < KS - 1) {
+            const uint32_t ha = smem_u32(As) + slot * (uint32_t)G::STAGE_BYTES + h_off;
+            if (PARTS == 2) {
+              const __half hh = __float2half_rn(hv);
+              const __half hl = __float2half_rn(hv - __half2float(hh));
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha), "h"(__half_as_ushort(hh)) : "memory");
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha + (uint32_t)G::PART_BYTES), "h"(__half_as_ushort(hl)) : "memory");
+            } else {
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha), "h"(__bfloat16_as_ushort(__float2bfloat16_rn(hv))) : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full(slot));
+        };
+        GBuf g0, g1;
+        int lg = pg, lri = 0;  // (row, group) of the stage loaded next
+        while (lg >= NG) { lg -= NG; ++lri; }
+        if (pg < total) gload(lri, lg, g0);
+        advance(lri, lg);
+        if (pg + CR_NPG < total) gload(lri, lg, g1);
+        advance(lri, lg);
+        for (int st = pg; st < total; st += 2 * CR_NPG) {
+          gproc(st, g0);
+          if (st + 2 * CR_NPG < total) gload(lri, lg, g0);
+          advance(lri, lg);
+          if (st + CR_NPG < total) {
+            gproc(st + CR_NPG, g1);
+            if (st + 3 * CR_NPG < total) gload(lri, lg, g1);
+            advance(lri, lg);
+          }
+        }
+        goto producer_done;
+      }
+    }
     {
     Buf b0, b1;
     int cg = pg, cri = 0;  // (row, group) of the stage processed next
