@@ -227,6 +227,16 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
   }
   if (warp == CR_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), G::TMEM_COLS);
   {
+    // filters and bias are constants of the network: copied before the programmatic-dependent-launch wait
+    if (tid < 16) bias_s[tid] = tid < p.cout_blks * 4 ? __ldg(p.bias + tid) : 0.f;
+    const uint4* wsrc = reinterpret_cast<const uint4*>(p.wpk);
+    uint4* wdst = reinterpret_cast<uint4*>(Bs);
+    for (int e = tid; e < NG * (G::B_GROUP / 16); e += CR_THREADS) wdst[e] = __ldg(wsrc + e);
+  }
+  // Everything above overlaps the tail of the previous kernel in the stream when this kernel was launched with
+  // programmatic stream serialization; the producer's outputs (activations, GroupNorm sums) are read only below.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  {
     int c0 = 0;
     for (int s = 0; s < p.nsrc; ++s) {
       const pbmc_src& S = p.src[s];
@@ -239,11 +249,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
       }
       c0 += S.nblk * 4;
     }
-    if (tid < 16) bias_s[tid] = tid < p.cout_blks * 4 ? __ldg(p.bias + tid) : 0.f;
-    const uint4* wsrc = reinterpret_cast<const uint4*>(p.wpk);
-    uint4* wdst = reinterpret_cast<uint4*>(Bs);
-    for (int e = tid; e < NG * (G::B_GROUP / 16); e += CR_THREADS) wdst[e] = __ldg(wsrc + e);
   }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel may start its own prologue
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -852,7 +859,21 @@ static int launch_row(ConvRowParams& p, cudaStream_t st) {
   p.rpc = choose_rpc(nstrips * p.B, p.H, KS, p.max_ctas);
   dim3 grid(cdiv(p.H, p.rpc), nstrips, p.B);
   if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
-  conv_row_kernel<KS, PARTS><<<grid, CR_THREADS, smem, st>>>(p);
+  // Programmatic dependent launch is wired but OFF: measured 0.269 vs 0.243 ms/step at 512^2 -- a dependent CTA that
+  // becomes resident early sits in griddepcontrol.wait holding an SM (a conv CTA owns one), which starves the
+  // other pyramid levels' streams.  (With PDL off griddepcontrol.wait / launch_dependents are no-ops.)
+  static const int pdl = getenv("PBMC_ROW_PDL") ? atoi(getenv("PBMC_ROW_PDL")) : 0;  // developer knob
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(CR_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  PBMC_CUDA(cudaLaunchKernelEx(&cfg, conv_row_kernel<KS, PARTS>, p));
   PBMC_CHECK_LAUNCH("conv_row_kernel");
   return PBMC_OK;
 }
