@@ -282,6 +282,8 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
       int want = share < 2 ? 2 : share;
       if (want > floor_ctas) want = floor_ctas;
       if (want < strips) want = strips;
+      // big batches: a level that needs more CTAs than its share even at 64 rows per CTA simply runs in waves
+      if ((long)strips * ((P.Hl[l] + 63) / 64) > want) want = 0;
       cta_budget[l] = L > 1 ? want : 0;
     }
   }
