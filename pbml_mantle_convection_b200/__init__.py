@@ -11,5 +11,6 @@ from .symmetric_layers_torch import SymmetricConv2d  # noqa: F401
 from .scaler import scale_var, unscale_var  # noqa: F401
 from .calculate_profiles import calc_mlp_profile  # noqa: F401
 from .rollout import EnsembleRollout, synthetic_grid, synthetic_T0  # noqa: F401
+from . import driver, multigpu  # noqa: F401
 
 __version__ = "0.1.0"

@@ -285,3 +285,34 @@ def test_no_silent_fallback_on_gpu_box():
     with pytest.raises(L.PbmcError):
         P.NewFluidNet(2, 7, 16, 2, DEV, act_fn="gelu", r_p="replicate", loss_type="curl", use_symm=True,
                       repeats=1)(torch.zeros(1, 7, 16, 16))  # CPU tensor on a CUDA model: refuse, do not fall back
+
+
+def test_driver_per_step_and_resident_agree(tmp_path):
+    """driver.attempt (one TS call per step, host round trip, advect_wi_gaia.py:583-668) and driver.attempt_resident
+    (EnsembleRollout, k steps per CUDA graph) log the same simulated times and mean temperatures."""
+    from pbml_mantle_convection_b200 import driver as D
+
+    g = load("roll64x96")
+    spec = RN.NetSpec(levels=4)
+    net = make_net(spec, load_weights("roll64x96"), impl="auto")
+    H, W = g["T0"].shape
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    xcc, ycc = t64(g["xc"]).view(1, 1, H, W), t64(g["yc"]).view(1, 1, H, W)
+    nd = RN.nondim_params(*PARAMS)
+    ts = P.TS(net, P.ADNet(DEV, CN_max=0.99), DEV, ts=1, scale=True, p_pred=True, net="newfluidnet")
+    t_a, n_a, (snap_a, TS_a, tv_a, Tv_a) = D.attempt(ts, t64(g["T0"]).view(1, 1, H, W), xcc, ycc, t64(PARAMS[0]), t64(PARAMS[1]),
+                                                    t64(PARAMS[2]), t64(nd[0]), t64(nd[1]), t64(nd[2]), t_end=1.0,
+                                                    out_dir=str(tmp_path / "a"), max_steps=12, save_every=0.0)
+    ens = P.EnsembleRollout(net, H, W, [PARAMS], DEV, xc=g["xc"], yc=g["yc"], cn_max=0.99, per_member_dt=False)
+    ens.set_T(g["T0"][None])
+    t_b, n_b, (snap_b, TS_b, tv_b, Tv_b) = D.attempt_resident(ens, xcc, ycc, t_end=1.0, out_dir=str(tmp_path / "b"), max_steps=12,
+                                                             check_every=4, save_every=0.0)
+    assert n_a == 12 and n_b == 12
+    assert np.allclose(tv_a["ML"], tv_b["ML"], rtol=1e-6)
+    # the reference's 10-step golden T is matched by both (same bound as the rollout test)
+    assert np.abs(snap_a["ML"]["T"][10].reshape(H, W) - g["T10"]).max() < 5e-5
+    assert abs(Tv_a["ML"][12] - Tv_b["ML"][12]) < 1e-6  # block-end sample of the resident path == per-step value
+    assert np.abs(snap_a["ML"]["T"][-1] - snap_b["ML"]["T"][-1]).max() < 1e-6
+    assert snap_b["ML"]["v"][-1].shape == (H * W, 3) and len(snap_b["ML"]["T"]) == 1 + 3  # initial + one per block
+    for sub in ("a", "b"):
+        assert (tmp_path / sub / "snapshots_ML.pkl").exists() and (tmp_path / sub / "T_vec_ML.pkl").exists()
