@@ -516,7 +516,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rollout512", choices=sorted(WORKLOADS))
-    ap.add_argument("--conv", default="auto", choices=["auto", "ffma", "umma_3xtf32", "umma_bf16", "umma_f16x2", "row_f16x2", "row_bf16"])
+    ap.add_argument("--conv", default="auto", choices=["auto", "ffma", "umma_3xtf32", "umma_bf16", "umma_f16x2", "row_f16x2", "row_bf16", "mux_f16x2", "mux_bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p"], help="slab workloads: how the one-row T halo moves")
     args = ap.parse_args()

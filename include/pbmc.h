@@ -52,9 +52,12 @@ enum { PBMC_HEAD_CURL = 0, PBMC_HEAD_MAE = 1 };
  * fp32-grade accuracy; BF16 = single pass with bf16 operands (looser, stated bound).
  * ROW_* = the row-streaming warp-specialised tcgen05 kernel (csrc/conv_row.cu; vertical taps folded
  * into the MMA's N dimension), F16X2 = fp16 hi+lo 3-pass (fp32-grade), BF16 = single bf16 pass.
- * AUTO = ROW_F16X2 where the shape is supported, else UMMA_F16X2, else FFMA. */
+ * MUX_* = the time-multiplexed row kernel (csrc/conv_mux.cu: the same GEMM, all warps stage rows, then all
+ * warps run the epilogue) for single-source 3x3 convs with c_in, c_out <= 16; other shapes asked for with
+ * MUX_* run the ROW_* kernel of the same precision.
+ * AUTO = MUX_F16X2 where the shape is supported and the grid fits one wave, else ROW_F16X2, else UMMA_F16X2, else FFMA. */
 enum { PBMC_CONV_AUTO = 0, PBMC_CONV_FFMA = 1, PBMC_CONV_UMMA_3XTF32 = 2, PBMC_CONV_UMMA_BF16 = 3, PBMC_CONV_UMMA_F16X2 = 4,
-       PBMC_CONV_ROW_F16X2 = 5, PBMC_CONV_ROW_BF16 = 6 };
+       PBMC_CONV_ROW_F16X2 = 5, PBMC_CONV_ROW_BF16 = 6, PBMC_CONV_MUX_F16X2 = 7, PBMC_CONV_MUX_BF16 = 8 };
 
 const char* pbmc_error_string(int status);
 int pbmc_version(void);

@@ -20,6 +20,9 @@ int conv_umma_dispatch(const pbmc_conv_desc& d, cudaStream_t st);  // conv_umma.
 bool conv_umma_supported(const pbmc_conv_desc& d);
 int conv_row_dispatch(const pbmc_conv_desc& d, cudaStream_t st);  // conv_row.cu
 bool conv_row_supported(const pbmc_conv_desc& d);
+int conv_mux_dispatch(const pbmc_conv_desc& d, cudaStream_t st);  // conv_mux.cu
+bool conv_mux_supported(const pbmc_conv_desc& d);
+bool conv_mux_one_wave(const pbmc_conv_desc& d);
 
 }  // namespace pbmc
 
@@ -93,9 +96,19 @@ static int conv_enqueue(const pbmc_conv_desc& d, cudaStream_t st) {
   if (rc != PBMC_OK) return rc;
   int impl = d.impl;
   if (impl == PBMC_CONV_AUTO)
-    impl = (d.wpk_row && conv_row_supported(d))     ? PBMC_CONV_ROW_F16X2
+    impl = (d.wpk_row && conv_mux_supported(d) && conv_mux_one_wave(d)) ? PBMC_CONV_MUX_F16X2
+           : (d.wpk_row && conv_row_supported(d))   ? PBMC_CONV_ROW_F16X2
            : (d.wpk_umma && conv_umma_supported(d)) ? PBMC_CONV_UMMA_F16X2
                                                     : PBMC_CONV_FFMA;
+  if (impl == PBMC_CONV_MUX_F16X2 || impl == PBMC_CONV_MUX_BF16) {
+    if (!d.wpk_row) return PBMC_ERR_UNSUPPORTED;
+    if (conv_mux_supported(d)) {
+      pbmc_conv_desc e = d;
+      e.impl = impl;
+      return conv_mux_dispatch(e, st);
+    }
+    impl = impl == PBMC_CONV_MUX_F16X2 ? PBMC_CONV_ROW_F16X2 : PBMC_CONV_ROW_BF16;  // multi-source / 5x5: row kernel
+  }
   if (impl == PBMC_CONV_ROW_F16X2 || impl == PBMC_CONV_ROW_BF16) {
     if (!d.wpk_row || !conv_row_supported(d)) return PBMC_ERR_UNSUPPORTED;
     pbmc_conv_desc e = d;

@@ -108,54 +108,7 @@ struct RowGeom {
   } while (0)
 #endif
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t r[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-// the wait names the destination registers as in/out operands so that no use of them can be scheduled above it
-__device__ __forceinline__ void tmem_ld_wait16(uint32_t r[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CR_EPI_WARPS * 32) : "memory"); }
-__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-// non-blocking phase test
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-
-__host__ __device__ constexpr uint32_t row_idesc(uint32_t fmt, uint32_t n) {
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
-}
 
 __device__ __forceinline__ float xform1(float v, float a, float b, int xform) {
   if (xform == PBMC_XFORM_NONE) return v;
@@ -375,6 +328,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     // for freshly issued prefetch loads.
     const int pw = warp - CR_EPI_WARPS;
     const int pg = pw >> 2, wq = pw & 3;
+    if (lane == 0 && wq == 0) CR_TR(4 + pg);
     const int i = wq * 32 + lane;
     const int gxp = x0 - P + i;
     const int sx = pad_index(gxp, W, p.pad_mode);
@@ -551,7 +505,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         if (h_on && sy >= 0) B.h = __ldg(hbase + ro);
       };
       auto fproc = [&](int st, FBuf& B) {
-        if (tr_lane) CR_TR(100 + pg * 300 + 4 * (st / CR_NPG));
+        if (tr_lane) CR_TR(100 + pg * 300 + 8 * (st / CR_NPG));
         float v[16] = {B.v0.x, B.v0.y, B.v0.z, B.v0.w, B.v1.x, B.v1.y, B.v1.z, B.v1.w,
                        B.v2.x, B.v2.y, B.v2.z, B.v2.w, B.v3.x, B.v3.y, B.v3.z, B.v3.w};
         float hv = B.h;
@@ -572,9 +526,9 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         }
         const uint32_t slot = (uint32_t)st & (NSTAGE - 1);
         const uint32_t sa = as_addr + slot * (uint32_t)G::STAGE_BYTES;
-        if (tr_lane) CR_TR(101 + pg * 300 + 4 * (st / CR_NPG));
+        if (tr_lane) CR_TR(101 + pg * 300 + 8 * (st / CR_NPG));
         if (st >= NSTAGE) mbar_wait_parked(a_empty(slot), (((uint32_t)st / NSTAGE) & 1u) ^ 1u);  // first pass: ring is free
-        if (tr_lane) CR_TR(102 + pg * 300 + 4 * (st / CR_NPG));
+        if (tr_lane) CR_TR(102 + pg * 300 + 8 * (st / CR_NPG));
         auto sts = [](uint32_t addr, uint4 q) {
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
         };
@@ -602,19 +556,23 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
             asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha), "h"(__bfloat16_as_ushort(__float2bfloat16_rn(hv))) : "memory");
           }
         }
+        if (tr_lane) CR_TR(104 + pg * 300 + 8 * (st / CR_NPG));
         if (!CR_DBG(32)) fence_proxy_async_smem();
+        if (tr_lane) CR_TR(105 + pg * 300 + 8 * (st / CR_NPG));
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full(slot));
-        if (tr_lane) CR_TR(103 + pg * 300 + 4 * (st / CR_NPG));
+        if (tr_lane) CR_TR(103 + pg * 300 + 8 * (st / CR_NPG));
       };
       static_assert(KS == 3 || HITEMS == 2, "halo lanes");
       if (KS == 3) {
         FBuf f0, f1;
+        if (tr_lane) CR_TR(8 + pg);
         if (pg < nin) fload(pg, f0);
         if (pg + CR_NPG < nin) fload(pg + CR_NPG, f1);
         for (int st = pg; st < nin; st += 2 * CR_NPG) {
           fproc(st, f0);
           if (st + 2 * CR_NPG < nin) fload(st + 2 * CR_NPG, f0);
+          if (tr_lane) CR_TR(106 + pg * 300 + 8 * (st / CR_NPG));
           if (st + CR_NPG < nin) {
             fproc(st + CR_NPG, f1);
             if (st + 3 * CR_NPG < nin) fload(st + 3 * CR_NPG, f1);

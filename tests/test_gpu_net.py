@@ -33,7 +33,7 @@ def fwd_bound(noise):
     return np.maximum(1e-5, 1.5 * np.asarray(noise))
 
 
-IMPLS = ["ffma", "umma_3xtf32", "umma_f16x2", "row_f16x2"]
+IMPLS = ["ffma", "umma_3xtf32", "umma_f16x2", "row_f16x2", "mux_f16x2"]
 
 
 @pytest.mark.parametrize("impl", IMPLS)

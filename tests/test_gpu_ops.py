@@ -180,6 +180,95 @@ def test_conv_row(case, impl, tol):
         assert np.all(out[:, -1, :, :, Co % 4:].cpu().numpy() == 0)
 
 
+MUX_CASES = [
+    (1, 16, 16, 17, 31, 3, "replicate"),
+    (2, 16, 16, 40, 300, 3, "reflect"),      # three strips, partial last strip
+    (1, 16, 16, 33, 128, 3, "zeros"),        # zero padding: out-of-image taps stay zero
+    (1, 7, 16, 50, 140, 3, "replicate"),     # conv[0]: 7 input channels (two blocks, one lane empty)
+    (1, 4, 16, 9, 140, 3, "zeros"),          # one block
+    (1, 16, 2, 64, 64, 3, "replicate"),      # conv[3]: c_out = 2 with the zero-mean channel sums
+    (1, 16, 16, 1, 5, 3, "zeros"),
+    (1, 16, 16, 3, 3, 3, "replicate"),
+    (3, 16, 16, 200, 256, 3, "replicate"),   # several waves; accumulator ring wraps
+    (1, 16, 12, 23, 129, 3, "replicate"),    # one column in the second strip
+]
+
+
+@pytest.mark.parametrize("impl,tol", [("mux_f16x2", 3e-6), ("mux_bf16", 1e-2)])
+@pytest.mark.parametrize("case", MUX_CASES)
+def test_conv_mux(case, impl, tol):
+    """Time-multiplexed row kernel (csrc/conv_mux.cu): same arithmetic as the row kernel, fp32-grade with
+    the fp16 hi+lo split; single-pass bf16 with its stated bound."""
+    B, Ci, Co, H, W, k, pad = case
+    r = rng(29)
+    x = r.standard_normal((B, Ci, H, W))
+    w = r.standard_normal((Co, Ci, k, k)) / np.sqrt(Ci * k * k)
+    b = r.standard_normal(Co)
+    ref = RN.conv2d_same(x, w, b, pad)
+    wpk, wrow = ops.pack_conv_weight(cu(w), [Ci]), ops.pack_conv_weight_row(cu(w), [Ci])
+    want_cs = Co <= 4
+    out, stats, csum = ops.conv_fwd([ops.Source(ops.pack_nchw(cu(x)))], wpk, ops.pad_vec(cu(b), Co, DEV), Co, k, pad,
+                                    want_stats=True, want_chan_sum=want_cs, impl=impl, wpk_row=wrow)
+    y = ops.unpack_nchw(out, Co).cpu().numpy()
+    assert relerr(y, ref) < tol, relerr(y, ref)
+    if impl == "mux_bf16":
+        ref = y.astype(np.float64)
+    cb = (Co + 3) // 4
+    refp = np.zeros((B, cb * 4, H, W))
+    refp[:, :Co] = ref
+    rs = refp.reshape(B, cb, -1)
+    st = stats.cpu().numpy()
+    assert np.allclose(st[..., 0], rs.sum(-1), rtol=1e-5, atol=1e-4 * np.sqrt(rs.shape[-1]))
+    assert np.allclose(st[..., 1], (rs**2).sum(-1), rtol=1e-5)
+    if want_cs:
+        assert np.allclose(csum.cpu().numpy(), refp.sum((2, 3)), rtol=1e-5, atol=1e-4 * np.sqrt(H * W))
+    if Co % 4:
+        assert np.all(out[:, -1, :, :, Co % 4:].cpu().numpy() == 0)
+
+
+@pytest.mark.parametrize("pad", ["replicate", "zeros", "reflect"])
+@pytest.mark.parametrize("H,W", [(26, 45), (61, 200)])
+def test_conv_mux_fused_groupnorm_gelu_and_epilogue_gelu(H, W, pad):
+    """conv -> [GN+GELU folded into the mux kernel's row staging] -> conv + GELU epilogue (the conv[1] -> conv[2] shape)."""
+    r = rng(31)
+    B = 2
+    x0 = r.standard_normal((B, 16, H, W))
+    w1, b1 = r.standard_normal((16, 16, 3, 3)) / 12, r.standard_normal(16)
+    g1, be1 = 1 + 0.2 * r.standard_normal(16), 0.2 * r.standard_normal(16)
+    w2, b2 = r.standard_normal((16, 16, 3, 3)) / 12, r.standard_normal(16)
+    y1 = RN.conv2d_same(x0, w1, b1, pad)
+    a1 = RN.gelu(RN.group_norm(y1, g1, be1, 4))
+    ref = RN.gelu(RN.conv2d_same(a1, w2, b2, pad))
+    y1b, st1, _ = ops.conv_fwd([ops.Source(ops.pack_nchw(cu(x0)))], ops.pack_conv_weight(cu(w1), [16]), ops.pad_vec(cu(b1), 16, DEV),
+                               16, 3, pad, want_stats=True, impl="mux_f16x2", wpk_row=ops.pack_conv_weight_row(cu(w1), [16]))
+    assert relerr(ops.unpack_nchw(y1b, 16).cpu().numpy(), y1) < 3e-6
+    out, _, _ = ops.conv_fwd([ops.Source(y1b, L.XFORM_GN_GELU, st1, cu(g1), cu(be1))], ops.pack_conv_weight(cu(w2), [16]),
+                             ops.pad_vec(cu(b2), 16, DEV), 16, 3, pad, epi_act=L.ACT_GELU, impl="mux_f16x2",
+                             wpk_row=ops.pack_conv_weight_row(cu(w2), [16]))
+    assert relerr(ops.unpack_nchw(out, 16).cpu().numpy(), ref) < 5e-6
+
+
+@pytest.mark.parametrize("ts", [0, 1])
+@pytest.mark.parametrize("rpc", [1, 2, 3, 7, 22])
+def test_conv_mux_any_rows_per_cta(rpc, ts):
+    """Rows per CTA is a scheduling choice: same result for any of them, with the A operand staged in shared memory
+    (ts=0, default) and in tensor memory (ts=1, csrc/conv_mux_ts.cuh: accumulator / operand rings wrap from 6 rows on)."""
+    import os, subprocess, sys
+    code = (
+        "import numpy as np, torch\n"
+        "from oracle import ref_numpy as RN\n"
+        "from pbml_mantle_convection_b200 import ops\n"
+        "r=np.random.default_rng(5); x=r.standard_normal((1,16,37,150)); w=r.standard_normal((16,16,3,3))/12; b=r.standard_normal(16)\n"
+        "cu=lambda a: torch.tensor(np.ascontiguousarray(a),dtype=torch.float32,device='cuda:0')\n"
+        "o,_,_=ops.conv_fwd([ops.Source(ops.pack_nchw(cu(x)))],ops.pack_conv_weight(cu(w),[16]),ops.pad_vec(cu(b),16,'cuda:0'),16,3,'replicate',impl='mux_f16x2',wpk_row=ops.pack_conv_weight_row(cu(w),[16]))\n"
+        "y=ops.unpack_nchw(o,16).cpu().numpy(); ref=RN.conv2d_same(x,w,b,'replicate')\n"
+        "e=np.linalg.norm(y-ref)/np.linalg.norm(ref); print(e); assert e<3e-6\n")
+    env = dict(os.environ, PBMC_MUX_RPC=str(rpc), PBMC_MUX_TS=str(ts))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+
+
 @pytest.mark.parametrize("rpc", [1, 2, 5, 64])
 def test_conv_row_any_rows_per_cta(rpc, monkeypatch):
     """The strip decomposition (rows per CTA) is a scheduling choice: results must not depend on it."""
@@ -208,7 +297,7 @@ def test_conv_gelu_epilogue():
     assert relerr(ops.unpack_nchw(out, 16).cpu().numpy(), ref) < 2e-6
 
 
-@pytest.mark.parametrize("impl", ["ffma", "umma_3xtf32", "umma_f16x2", "row_f16x2"])
+@pytest.mark.parametrize("impl", ["ffma", "umma_3xtf32", "umma_f16x2", "row_f16x2", "mux_f16x2"])
 def test_fluid_layer_chain_with_fused_groupnorm_and_concat(impl):
     """conv -> [GN+GELU fused into the next load] -> conv over a 3-source concat (one plain source)."""
     r = rng(3)

@@ -32,7 +32,7 @@ def timeit(fn, iters=30, warm=5, flush=None):
 
 
 def main():
-    impls = sys.argv[1:] or ["row_f16x2", "umma_f16x2"]
+    impls = sys.argv[1:] or ["mux_f16x2", "row_f16x2"]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     w = torch.randn(16, 16, 3, 3, device=dev, generator=g) / 12
     w1 = torch.randn(16, 103, 3, 3, device=dev, generator=g) / 30
