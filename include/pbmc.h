@@ -46,6 +46,13 @@ typedef enum {
 enum { PBMC_PAD_ZEROS = 0, PBMC_PAD_REPLICATE = 1, PBMC_PAD_REFLECT = 2 };
 enum { PBMC_XFORM_NONE = 0, PBMC_XFORM_GN_GELU = 1, PBMC_XFORM_GN = 2, PBMC_XFORM_GELU = 3 };
 enum { PBMC_ACT_NONE = 0, PBMC_ACT_GELU = 1 };
+/* Source layouts.  BLOCKED: float [B][nblk][H][W][4].  STAGED16: the tensor-core operand image of a 16-channel
+ * tensor, ready to be copied into shared memory by the TMA engine with no thread touching it:
+ *   __half [B][H][part = hi, lo][chunk = channels 0-7, 8-15][Wp][8],  Wp = pbmc_staged_width(W) = roundup(W,128) + 2,
+ * position 0 / W+1 = the replicate-padded columns -1 / W, hi + lo = the fp32 value split into two fp16
+ * (the split the row conv kernel's producer warps would compute).  Accepted by pbmc_conv_fwd for 3x3, replicate
+ * padding, xform NONE, nblk = 4, on the ROW_F16X2 kernel (AUTO picks it). */
+enum { PBMC_LAYOUT_BLOCKED = 0, PBMC_LAYOUT_STAGED16 = 1 };
 enum { PBMC_HEAD_CURL = 0, PBMC_HEAD_MAE = 1 };
 /* conv implementation selector: FFMA = fp32 CUDA cores; UMMA_* = tcgen05 tensor cores:
  * 3XTF32 / F16X2 split every operand into hi + lo (tf32 resp. fp16) and issue 3 passes --
@@ -105,6 +112,8 @@ typedef struct {
   int nblk;
   int xform;           /* PBMC_XFORM_* */
   double inv_count;    /* 1 / (channels_per_group * H * W) */
+  int layout;          /* PBMC_LAYOUT_*: BLOCKED (default) or STAGED16 (see pbmc_bicubic_up_staged) */
+  int reserved;
 } pbmc_src;
 
 /* k x k, stride 1, 'same' conv (k in {3,5}) over the concatenation of `nsrc` sources.
@@ -146,6 +155,11 @@ int pbmc_avgpool2(const pbmc_src* src_h, float* dst, int B, int H, int W, void* 
 /* nn.Upsample(size=(H,W), mode="bicubic"), align_corners=False, A=-0.75 (:1227-1229, :1326),
  * source transform (GroupNorm+GELU of the level's last FluidLayer) fused. */
 int pbmc_bicubic_up(const pbmc_src* src_h, float* dst, int B, int Hs, int Ws, int H, int W, void* stream);
+/* Same, written in PBMC_LAYOUT_STAGED16 (src nblk must be 4): the up-sampled levels are read only by conv[1]
+ * (:1332-1335), whose operand loader is then a bulk copy.  dst: pbmc_staged_bytes(B, H, W) bytes. */
+int pbmc_bicubic_up_staged(const pbmc_src* src_h, void* dst, int B, int Hs, int Ws, int H, int W, void* stream);
+int pbmc_staged_width(int W);
+size_t pbmc_staged_bytes(int B, int H, int W);
 
 /* ------------------------------------------------------------------ A7: head
  * zero-mean (:1343), curl (:1357-1370), replicate pad + wall BCs (:1372-1386),

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_PKG, "libpbmc.so")
 MAX_SRC, MAX_LEVELS, MAX_REPEATS = 8, 8, 8
 PAD = {"zeros": 0, "constant": 0, "replicate": 1, "reflect": 2}
 XFORM_NONE, XFORM_GN_GELU, XFORM_GN, XFORM_GELU = 0, 1, 2, 3
+LAYOUT_BLOCKED, LAYOUT_STAGED16 = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
 HEAD_CURL, HEAD_MAE = 0, 1
 CONV_IMPL = {"auto": 0, "ffma": 1, "umma_3xtf32": 2, "umma_bf16": 3, "umma_f16x2": 4,
@@ -30,7 +31,7 @@ class Member(C.Structure):
 
 class Src(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
-                ("nblk", C.c_int), ("xform", C.c_int), ("inv_count", C.c_double)]
+                ("nblk", C.c_int), ("xform", C.c_int), ("inv_count", C.c_double), ("layout", C.c_int), ("reserved", C.c_int)]
 
 
 class ConvDesc(C.Structure):
@@ -68,6 +69,9 @@ SIGNATURES = {
     "pbmc_conv_fwd": (_i, [C.POINTER(ConvDesc), _vp]),
     "pbmc_avgpool2": (_i, [C.POINTER(Src), _vp, _i, _i, _i, _vp]),
     "pbmc_bicubic_up": (_i, [C.POINTER(Src), _vp, _i, _i, _i, _i, _i, _vp]),
+    "pbmc_bicubic_up_staged": (_i, [C.POINTER(Src), _vp, _i, _i, _i, _i, _i, _vp]),
+    "pbmc_staged_width": (_i, [_i]),
+    "pbmc_staged_bytes": (C.c_size_t, [_i, _i, _i]),
     "pbmc_head": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pbmc_advect_diffuse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pbmc_advect_diffuse_slab": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -136,8 +140,8 @@ def stream_ptr(device=None):
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def make_src(t, nblk, xform=XFORM_NONE, stats=None, gamma=None, beta=None, inv_count=0.0):
+def make_src(t, nblk, xform=XFORM_NONE, stats=None, gamma=None, beta=None, inv_count=0.0, layout=LAYOUT_BLOCKED):
     s = Src()
     s.ptr, s.stats, s.gamma, s.beta = ptr(t), ptr(stats), ptr(gamma), ptr(beta)
-    s.nblk, s.xform, s.inv_count = int(nblk), int(xform), float(inv_count)
+    s.nblk, s.xform, s.inv_count, s.layout = int(nblk), int(xform), float(inv_count), int(layout)
     return s

@@ -1,8 +1,10 @@
 // C ABI glue: validation, conv dispatch, workspace planning, and the DAG that enqueues a
 // whole surrogate forward (NewFluidNet.forward, pytorch_networks_convae.py:1315-1388) and
 // the TS time-stepping loop (:377-475) without any host synchronisation.
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 
 #include "common.cuh"
@@ -95,6 +97,16 @@ static int conv_enqueue(const pbmc_conv_desc& d, cudaStream_t st) {
   int rc = validate_conv(d);
   if (rc != PBMC_OK) return rc;
   int impl = d.impl;
+  bool staged = false;
+  for (int s = 0; s < d.nsrc; ++s) {
+    if (d.src[s].layout != PBMC_LAYOUT_BLOCKED && d.src[s].layout != PBMC_LAYOUT_STAGED16) return PBMC_ERR_UNSUPPORTED;
+    staged = staged || d.src[s].layout == PBMC_LAYOUT_STAGED16;
+  }
+  if (staged) {
+    // operand images are only understood by the fp16 hi|lo row kernel (which checks the rest: 3x3, replicate, ...)
+    if (impl != PBMC_CONV_AUTO && impl != PBMC_CONV_ROW_F16X2 && impl != PBMC_CONV_MUX_F16X2) return PBMC_ERR_UNSUPPORTED;
+    impl = PBMC_CONV_ROW_F16X2;
+  }
   if (impl == PBMC_CONV_AUTO)
     impl = (d.wpk_row && conv_mux_supported(d) && conv_mux_one_wave(d)) ? PBMC_CONV_MUX_F16X2
            : (d.wpk_row && conv_row_supported(d))   ? PBMC_CONV_ROW_F16X2
@@ -196,7 +208,7 @@ int make_plan(const pbmc_net& n, int B, int H, int W, Plan& P) {
     P.pooled[l] = l ? take((size_t)B * P.CB * pl * 16) : 0;
     P.ping[l][0] = take((size_t)B * P.CB * pl * 16);
     P.ping[l][1] = take((size_t)B * P.CB * pl * 16);
-    P.up[l] = l ? take((size_t)B * P.CB * px * 16) : 0;
+    P.up[l] = l ? take(std::max((size_t)B * P.CB * px * 16, pbmc_staged_bytes(B, H, W))) : 0;  // blocked fp32 or staged fp16 hi|lo
   }
   P.h1 = take((size_t)B * P.CB * px * 16);
   P.h2 = take((size_t)B * P.CB * px * 16);
@@ -214,7 +226,7 @@ int make_plan(const pbmc_net& n, int B, int H, int W, Plan& P) {
 inline pbmc_src make_src(const float* ptr, int nblk, int xform, const double* stats, const pbmc_layer* producer,
                          double inv_count) {
   pbmc_src s;
-  s.ptr = ptr; s.nblk = nblk; s.xform = xform; s.stats = stats;
+  s.ptr = ptr; s.nblk = nblk; s.xform = xform; s.stats = stats; s.layout = PBMC_LAYOUT_BLOCKED; s.reserved = 0;
   s.gamma = producer ? producer->gamma : nullptr;
   s.beta = producer ? producer->beta : nullptr;
   s.inv_count = inv_count;
@@ -300,6 +312,24 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
       cta_budget[l] = L > 1 ? want : 0;
     }
   }
+  // conv[1] is the only reader of the up-sampled levels: when it runs on the fp16 hi|lo row kernel (3x3, replicate
+  // padding, 16 hidden channels) they are written directly as its operand image and staged by bulk copies
+  bool up_staged = n.pad_mode == PBMC_PAD_REPLICATE && CB == 4 && n.conv1.ksize == 3 && n.conv1.wpk_row != nullptr &&
+                   (n.conv_impl == PBMC_CONV_AUTO || n.conv_impl == PBMC_CONV_ROW_F16X2 || n.conv_impl == PBMC_CONV_MUX_F16X2);
+  if (up_staged) {
+    pbmc_conv_desc t;
+    memset(&t, 0, sizeof(t));
+    t.nsrc = L + 1; t.ksize = 3; t.cout = n.conv1.cout;
+    for (int l = 0; l < L; ++l) t.src[l].nblk = CB;
+    for (int l = 1; l < L; ++l) t.src[l].layout = PBMC_LAYOUT_STAGED16;
+    t.src[L].nblk = P.CIB;
+    up_staged = L + 1 <= PBMC_MAX_SRC && conv_row_supported(t);
+  }
+  // Off by default: measured neutral-to-slower in the whole step (512^2: 0.244-0.260 vs 0.241 ms; 32 x 256^2: 1.47 vs
+  // 1.445 ms) -- conv[1] is paced by its MMA issue loop, not by its producers, and the operand-image writer of the
+  // bicubic kernel stores 2 x 8 B per thread.  PBMC_UP_STAGED=1 turns it on (results are bit-identical).
+  static const int staged_knob = getenv("PBMC_UP_STAGED") ? atoi(getenv("PBMC_UP_STAGED")) : 0;
+  up_staged = up_staged && staged_knob != 0;
   const float* level_in[PBMC_MAX_LEVELS];
   level_in[0] = F(P.x0);
   for (int l = 0; l < L; ++l) {
@@ -332,7 +362,10 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
     if (l > 0) {
       pbmc_src us = make_src(F(P.ping[l][(R - 1) & 1]), CB, PBMC_XFORM_GN_GELU, S(1 + l * R + R - 1),
                              &n.trunk[l * PBMC_MAX_REPEATS + R - 1], invc);
-      RC(pbmc_bicubic_up(&us, F(P.up[l]), B, Hl, Wl, H, W, sl));
+      if (up_staged)
+        RC(pbmc_bicubic_up_staged(&us, ws + P.up[l], B, Hl, Wl, H, W, sl));
+      else
+        RC(pbmc_bicubic_up(&us, F(P.up[l]), B, Hl, Wl, H, W, sl));
       PBMC_CUDA(cudaEventRecord(ctx->ev_join[l], sl));
     }
   }
@@ -343,7 +376,10 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
   if (L + 1 > PBMC_MAX_SRC) return PBMC_ERR_UNSUPPORTED;
   d.nsrc = L + 1;
   d.src[0] = make_src(F(P.ping[0][(R - 1) & 1]), CB, PBMC_XFORM_GN_GELU, S(1 + R - 1), &n.trunk[R - 1], 1.0 / (4.0 * H * W));
-  for (int l = 1; l < L; ++l) d.src[l] = make_src(F(P.up[l]), CB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
+  for (int l = 1; l < L; ++l) {
+    d.src[l] = make_src(F(P.up[l]), CB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
+    if (up_staged) d.src[l].layout = PBMC_LAYOUT_STAGED16;
+  }
   d.src[L] = make_src(inp, P.CIB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
   RC(conv_enqueue(d, st));
   // gn[0] + act folded into conv[2]'s load; conv[2] + act (:1336-1340)

@@ -572,7 +572,7 @@ bool conv_mux_one_wave(const pbmc_conv_desc& d) {
 
 // one source of at most 16 channels, 3x3, c_out <= 16, input either raw or GroupNorm+GELU of its producer
 bool conv_mux_supported(const pbmc_conv_desc& d) {
-  if (d.ksize != 3 || d.cout > 16 || d.nsrc != 1) return false;
+  if (d.ksize != 3 || d.cout > 16 || d.nsrc != 1 || d.src[0].layout != PBMC_LAYOUT_BLOCKED) return false;
   if (d.src[0].nblk < 1 || d.src[0].nblk > 4) return false;
   if (d.src[0].xform != PBMC_XFORM_NONE && d.src[0].xform != PBMC_XFORM_GN_GELU) return false;
   if (d.out_chan_sum != nullptr && d.cout > 4) return false;  // per-channel sums: head conv only

@@ -37,7 +37,9 @@ namespace pbmc {
 constexpr int CR_EPI_WARPS = 8;                        // two sets of 4 (alternate output rows)
 constexpr int CR_NPG = 3;                              // producer groups (4 warps = 128 positions each)
 constexpr int CR_MMA_WARP = CR_EPI_WARPS + 4 * CR_NPG;  // warps 0-7 epilogue, 8 .. 8+4*NPG-1 producers, then the MMA issuer
-constexpr int CR_THREADS = (CR_MMA_WARP + 1) * 32;
+constexpr int CR_TMA_WARP = CR_MMA_WARP + 1;            // one lane bulk-copies the stages of operand-image (STAGED16) sources
+constexpr int CR_THREADS = (CR_TMA_WARP + 1) * 32;
+constexpr int CR_NT = 8;                                // stages of the bulk-copy ring (power of two)
 constexpr int CR_MAXG = 24;
 constexpr int CR_SMEM_HDR = 2176;
 
@@ -49,6 +51,7 @@ struct ConvRowParams {
   int cin_ch;   // padded channel count of the concatenation (sum nblk * 4)
   int rpc;      // output rows per CTA
   int max_ctas; // CTA budget (0 = whole GPU)
+  int has_staged;  // some source is an operand image: the bulk-copy ring is allocated
   const void* wpk;  // [group][dx][part][2 K-chunks][N = k*16 rows (dy, c_out)][8 c_in] 16-bit
   const float* bias;
   float* out;
@@ -64,7 +67,7 @@ struct RowGroup {
   int nb;             // real 4-channel blocks (1..4); the rest of the 16 channels are zero
   int xform;
   int chan0;          // first channel in the xf_a / xf_b tables
-  int pad;
+  int staged;         // PBMC_LAYOUT_STAGED16: base = this sample's fp16 hi|lo operand image, rows are bulk-copied
 };
 
 template <int KS, int PARTS>
@@ -121,7 +124,7 @@ template <int KS, int PARTS>
 __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_constant__ ConvRowParams p) {
   using G = RowGeom<KS, PARTS>;
   constexpr int P = G::P, N = G::N, NSTAGE = G::NSTAGE, ND = G::ND, PLANE = G::PLANE;
-  static_assert(8 * (2 * NSTAGE + 2 * ND) <= 448, "barrier area");
+  static_assert(8 * (2 * NSTAGE + 2 * ND + 2 * CR_NT) <= 448, "barrier area");
   static_assert((NSTAGE & (NSTAGE - 1)) == 0, "NSTAGE must be a power of two");
   constexpr uint32_t FMT = PARTS == 2 ? 0u : 1u;  // fp16 hi|lo split, or one bf16 pass
   constexpr uint32_t IDESC = row_idesc(FMT, N);
@@ -130,9 +133,11 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
   RowGroup* gtab = reinterpret_cast<RowGroup*>(smem + 512);
   double* red = reinterpret_cast<double*>(smem + 1152);             // 8 warps x 8 doubles
   float* bias_s = reinterpret_cast<float*>(smem + 1152 + 512);      // 16 floats (zero padded)
+  int* nslist = reinterpret_cast<int*>(smem + 1152 + 512 + 64);     // the groups the producer warps stage (not bulk-copied), then their count
+  uint32_t* stg_mask = reinterpret_cast<uint32_t*>(smem + 1152 + 512 + 64 + 4 * (CR_MAXG + 1));  // bit g: group g is an operand image
   unsigned char* Bs = smem + CR_SMEM_HDR;
   unsigned char* As = Bs + (size_t)p.ngroups * G::B_GROUP;
-  float* xf_a = reinterpret_cast<float*>(As + NSTAGE * G::STAGE_BYTES);
+  float* xf_a = reinterpret_cast<float*>(As + (size_t)(NSTAGE + (p.has_staged ? CR_NT : 0)) * G::STAGE_BYTES);
   float* xf_b = xf_a + p.cin_ch;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -150,6 +155,10 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
   auto a_empty = [&](uint32_t s) { return bar0 + (uint32_t)(NSTAGE + s) * 8u; };
   auto d_full = [&](uint32_t d) { return bar0 + (uint32_t)(2 * NSTAGE + d) * 8u; };
   auto d_empty = [&](uint32_t d) { return bar0 + (uint32_t)(2 * NSTAGE + ND + d) * 8u; };
+  // Operand-image sources get their own ring (stages NSTAGE .. NSTAGE+CR_NT-1) and barriers: every barrier then has one
+  // kind of waiter that sees all of its phases in order (a parity wait is unsound for a waiter that skips phases).
+  auto t_full = [&](uint32_t s) { return bar0 + (uint32_t)(2 * NSTAGE + 2 * ND + s) * 8u; };
+  auto t_empty = [&](uint32_t s) { return bar0 + (uint32_t)(2 * NSTAGE + 2 * ND + CR_NT + s) * 8u; };
 
   // ---- one-time setup
   if (tid == 0) {
@@ -162,6 +171,10 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
       mbar_init(d_full(d), 1);        // tcgen05.commit
       mbar_init(d_empty(d), 4 * KS);  // 4 epilogue warps x the KS output rows that read D_d
     }
+    for (int s = 0; s < CR_NT; ++s) {
+      mbar_init(t_full(s), 1);   // arrive.expect_tx of the copying lane (+ the bytes of the four bulk copies)
+      mbar_init(t_empty(s), 1);  // tcgen05.commit
+    }
     fence_mbar_init();
     int g = 0, c0 = 0;
     for (int s = 0; s < p.nsrc; ++s) {
@@ -172,11 +185,22 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         gi.nb = min(4, S.nblk - cb);
         gi.xform = S.xform;
         gi.chan0 = c0 + cb * 4;
-        gi.pad = 0;
+        gi.staged = S.layout == PBMC_LAYOUT_STAGED16;
+        if (gi.staged)  // [H][part][chunk][Wp][8] halves per sample
+          gi.base = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(S.ptr) +
+                                                   (size_t)b * H * 4 * (size_t)((W + 127) / 128 * 128 + 2) * 16);
         gtab[g] = gi;
       }
       c0 += S.nblk * 4;
     }
+    int nns = 0;
+    uint32_t mask = 0;
+    for (int q = 0; q < g; ++q) {
+      if (gtab[q].staged) mask |= 1u << q;
+      else nslist[nns++] = q;
+    }
+    nslist[CR_MAXG] = nns;
+    *stg_mask = mask;
   }
   if (warp == CR_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), G::TMEM_COLS);
   {
@@ -470,7 +494,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     // of a forward).  A stage is then simply an input row; everything that does not change from row to row is
     // hoisted, the body is straight-line: the generic loop below spends ~330 instructions per stage on
     // bookkeeping and the stage rate of a CTA is bounded by exactly this serial, single-warp chain.
-    if (NG == 1 && gtab[0].nb == 4 && (gtab[0].xform == PBMC_XFORM_NONE || gtab[0].xform == PBMC_XFORM_GN_GELU)) {
+    if (NG == 1 && gtab[0].nb == 4 && !gtab[0].staged && (gtab[0].xform == PBMC_XFORM_NONE || gtab[0].xform == PBMC_XFORM_GN_GELU)) {
       const RowGroup gi = gtab[0];
       const bool do_x = gi.xform == PBMC_XFORM_GN_GELU;
       const size_t pstride = plane_px * 4;
@@ -674,21 +698,23 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full(slot));
         };
+        // The producer warps stage the groups that are not operand images (nslist), in (row, group) order, the k-th
+        // such stage in slot k % NSTAGE of their own ring; group pg takes k = pg, pg + NPG, ...
+        const int nns = nslist[CR_MAXG];
+        const int total_ns = nin * nns;
         GBuf g0, g1;
-        int lg = pg, lri = 0;  // (row, group) of the stage loaded next
-        while (lg >= NG) { lg -= NG; ++lri; }
-        if (pg < total) gload(lri, lg, g0);
-        advance(lri, lg);
-        if (pg + CR_NPG < total) gload(lri, lg, g1);
-        advance(lri, lg);
-        for (int st = pg; st < total; st += 2 * CR_NPG) {
-          gproc(st, g0);
-          if (st + 2 * CR_NPG < total) gload(lri, lg, g0);
-          advance(lri, lg);
-          if (st + CR_NPG < total) {
-            gproc(st + CR_NPG, g1);
-            if (st + 3 * CR_NPG < total) gload(lri, lg, g1);
-            advance(lri, lg);
+        auto kload = [&](int k, GBuf& B) {
+          const int ri = k / nns;
+          gload(ri, nslist[k - ri * nns], B);
+        };
+        if (pg < total_ns) kload(pg, g0);
+        if (pg + CR_NPG < total_ns) kload(pg + CR_NPG, g1);
+        for (int k = pg; k < total_ns; k += 2 * CR_NPG) {
+          gproc(k, g0);
+          if (k + 2 * CR_NPG < total_ns) kload(k + 2 * CR_NPG, g0);
+          if (k + CR_NPG < total_ns) {
+            gproc(k + CR_NPG, g1);
+            if (k + 3 * CR_NPG < total_ns) kload(k + 3 * CR_NPG, g1);
           }
         }
         goto producer_done;
@@ -717,13 +743,15 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     }
     }
   producer_done:;
-  } else {
+  } else if (warp == CR_MMA_WARP) {
     // ================================================================ MMA issuer
     // The whole warp walks the (uniform) pipeline state; one elected lane issues tcgen05.mma / commit.
     // This warp's serial instruction stream bounds the stage rate, so everything is incremental: descriptors
     // are base + small constant (the 14-bit address field cannot carry: smem < 256 KB), and the barrier of
     // the NEXT stage is tested (non-blocking) before the current stage's MMAs are issued, so its latency hides
     // behind the (back-pressured, ~400 clk) issue of 9 MMAs.
+    // Stage (ri, g) lives in the producers' ring (its pk-th stage) or, for an operand-image group, in the bulk-copy
+    // ring (its tk-th stage); with no such group pk is simply the stage number.
     const bool leader = elect_one();
     constexpr uint32_t A_LBO = PLANE * 16, B_LBO = N * 16, SBO = 128;
     const uint64_t a_desc0 = umma_desc(smem_u32(As), A_LBO, SBO), b_desc0 = umma_desc(smem_u32(Bs), B_LBO, SBO);
@@ -732,38 +760,124 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
 #else
     constexpr uint32_t dx_step = 1;  // one position = 16 B
 #endif
-    uint32_t ds = 0, d_par = 0;
-    int st = 0;
-    bool ready = total > 0 && mbar_test(a_full(0), 0u);
-    for (int ri = 0; ri < nin; ++ri) {
-      if (ri >= ND) mbar_wait(d_empty(ds), d_par ^ 1u);  // first ND rows: the ring is free
-      const uint32_t dcol = tmem_base + ds * (uint32_t)N;
-      for (int g = 0; g < NG; ++g, ++st) {
-        const uint32_t slot = (uint32_t)st & (NSTAGE - 1);
-        if (!ready) mbar_wait(a_full(slot), ((uint32_t)st / NSTAGE) & 1u);
-        tc_fence_after();
-        ready = (st + 1 < total) && mbar_test(a_full((uint32_t)(st + 1) & (NSTAGE - 1)), ((uint32_t)(st + 1) / NSTAGE) & 1u);
-        if (leader) {
-          CR_TR(1400 + 2 * st);
-          const uint64_t a_s = a_desc0 + (uint64_t)(slot * (uint32_t)(G::STAGE_BYTES >> 4));
-          const uint64_t b_s = b_desc0 + (uint64_t)((uint32_t)g * (uint32_t)(G::B_GROUP >> 4));
+    const uint32_t smask = *stg_mask;
+    auto sel = [&](int g, uint32_t pk, uint32_t tk, uint32_t& full, uint32_t& par, uint32_t& sidx, uint32_t& empty) {
+      if ((smask >> g) & 1u) {
+        const uint32_t s = tk & (CR_NT - 1);
+        full = t_full(s); par = (tk / CR_NT) & 1u; sidx = NSTAGE + s; empty = t_empty(s);
+      } else {
+        const uint32_t s = pk & (NSTAGE - 1);
+        full = a_full(s); par = (pk / NSTAGE) & 1u; sidx = s; empty = a_empty(s);
+      }
+    };
+    if (smask == 0u) {
+      // no operand-image group: the stage number is the ring position (this loop is the pace-maker of every plain
+      // conv; the general one below costs ~10 % more per stage)
+      uint32_t ds = 0, d_par = 0;
+      int st = 0;
+      bool ready = total > 0 && mbar_test(a_full(0), 0u);
+      for (int ri = 0; ri < nin; ++ri) {
+        if (ri >= ND) mbar_wait(d_empty(ds), d_par ^ 1u);  // first ND rows: the ring is free
+        const uint32_t dcol = tmem_base + ds * (uint32_t)N;
+        for (int g = 0; g < NG; ++g, ++st) {
+          const uint32_t slot = (uint32_t)st & (NSTAGE - 1);
+          if (!ready) mbar_wait(a_full(slot), ((uint32_t)st / NSTAGE) & 1u);
+          tc_fence_after();
+          ready = (st + 1 < total) && mbar_test(a_full((uint32_t)(st + 1) & (NSTAGE - 1)), ((uint32_t)(st + 1) / NSTAGE) & 1u);
+          if (leader) {
+            CR_TR(1400 + 2 * st);
+            const uint64_t a_s = a_desc0 + (uint64_t)(slot * (uint32_t)(G::STAGE_BYTES >> 4));
+            const uint64_t b_s = b_desc0 + (uint64_t)((uint32_t)g * (uint32_t)(G::B_GROUP >> 4));
 #pragma unroll
-          for (int dx = 0; dx < KS; ++dx) {
-            const uint64_t a_hi = a_s + (uint64_t)(dx * dx_step);
-            const uint64_t b_hi = b_s + (uint64_t)(dx * PARTS * (G::B_TILE >> 4));
-            if (CR_DBG(1)) continue;
-            umma_ss<1>(dcol, a_hi, b_hi, IDESC, (uint32_t)(g | dx));
-            if (PARTS == 2) {
-              umma_ss<1>(dcol, a_hi + (uint64_t)(G::PART_BYTES >> 4), b_hi, IDESC, 1u);
-              umma_ss<1>(dcol, a_hi, b_hi + (uint64_t)(G::B_TILE >> 4), IDESC, 1u);
+            for (int dx = 0; dx < KS; ++dx) {
+              const uint64_t a_hi = a_s + (uint64_t)(dx * dx_step);
+              const uint64_t b_hi = b_s + (uint64_t)(dx * PARTS * (G::B_TILE >> 4));
+              if (CR_DBG(1)) continue;
+              umma_ss<1>(dcol, a_hi, b_hi, IDESC, (uint32_t)(g | dx));
+              if (PARTS == 2) {
+                umma_ss<1>(dcol, a_hi + (uint64_t)(G::PART_BYTES >> 4), b_hi, IDESC, 1u);
+                umma_ss<1>(dcol, a_hi, b_hi + (uint64_t)(G::B_TILE >> 4), IDESC, 1u);
+              }
             }
+            umma_commit(a_empty(slot));                // frees the smem stage once these MMAs have read it
+            if (g == NG - 1) umma_commit(d_full(ds));  // D_ri complete
+            CR_TR(1401 + 2 * st);
           }
-          umma_commit(a_empty(slot));                // frees the smem stage once these MMAs have read it
-          if (g == NG - 1) umma_commit(d_full(ds));  // D_ri complete
-          CR_TR(1401 + 2 * st);
+        }
+        if (++ds == (uint32_t)ND) { ds = 0; d_par ^= 1u; }
+      }
+    } else {
+      uint32_t ds = 0, d_par = 0, pk = 0, tk = 0;
+      int st = 0;
+      uint32_t full = 0, par = 0, sidx = 0, empty = 0;
+      if (total > 0) sel(0, 0u, 0u, full, par, sidx, empty);
+      bool ready = total > 0 && mbar_test(full, par);
+      for (int ri = 0; ri < nin; ++ri) {
+        if (ri >= ND) mbar_wait(d_empty(ds), d_par ^ 1u);  // first ND rows: the ring is free
+        const uint32_t dcol = tmem_base + ds * (uint32_t)N;
+        for (int g = 0; g < NG; ++g, ++st) {
+          if (!ready) mbar_wait(full, par);
+          tc_fence_after();
+          const uint32_t c_sidx = sidx, c_empty = empty;
+          if ((smask >> g) & 1u) ++tk; else ++pk;
+          if (st + 1 < total) {
+            sel(g + 1 == NG ? 0 : g + 1, pk, tk, full, par, sidx, empty);
+            ready = mbar_test(full, par);
+          }
+          if (leader) {
+            CR_TR(1400 + 2 * st);
+            const uint64_t a_s = a_desc0 + (uint64_t)(c_sidx * (uint32_t)(G::STAGE_BYTES >> 4));
+            const uint64_t b_s = b_desc0 + (uint64_t)((uint32_t)g * (uint32_t)(G::B_GROUP >> 4));
+  #pragma unroll
+            for (int dx = 0; dx < KS; ++dx) {
+              const uint64_t a_hi = a_s + (uint64_t)(dx * dx_step);
+              const uint64_t b_hi = b_s + (uint64_t)(dx * PARTS * (G::B_TILE >> 4));
+              if (CR_DBG(1)) continue;
+              umma_ss<1>(dcol, a_hi, b_hi, IDESC, (uint32_t)(g | dx));
+              if (PARTS == 2) {
+                umma_ss<1>(dcol, a_hi + (uint64_t)(G::PART_BYTES >> 4), b_hi, IDESC, 1u);
+                umma_ss<1>(dcol, a_hi, b_hi + (uint64_t)(G::B_TILE >> 4), IDESC, 1u);
+              }
+            }
+            umma_commit(c_empty);                      // frees the smem stage once these MMAs have read it
+            if (g == NG - 1) umma_commit(d_full(ds));  // D_ri complete
+            CR_TR(1401 + 2 * st);
+          }
+        }
+        if (++ds == (uint32_t)ND) { ds = 0; d_par ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ bulk-copy lane: operand-image (STAGED16) groups
+    // The TMA engine copies a row's four operand planes (128 + 2 positions x 16 B each) from the source straight into
+    // a stage of the second ring: no thread touches the data, no proxy fence (async proxy on both sides), and the
+    // copies run up to CR_NT stages ahead of the MMAs.  Replicate padding only (checked on the host): the padded
+    // columns are part of the image, a padded row is the clamped row.
+    const uint32_t smask = *stg_mask;
+    if (lane == 0 && smask != 0u) {
+      constexpr uint32_t ROW_BYTES = (uint32_t)G::PWS * 16u;
+      const size_t wp16 = (size_t)((W + 127) / 128 * 128 + 2) * 16;  // bytes of one plane row of an operand image
+      uint32_t tk = 0;
+      for (int ri = 0; ri < nin; ++ri) {
+        const int sy = min(max(y0 - P + ri, 0), H - 1);
+        for (int g = 0; g < NG; ++g) {
+          if (!((smask >> g) & 1u)) continue;
+          const uint32_t s = tk & (CR_NT - 1);
+          if (tk >= (uint32_t)CR_NT) mbar_wait_parked(t_empty(s), ((tk / CR_NT) & 1u) ^ 1u);
+          const uint32_t bar = t_full(s);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * PARTS * ROW_BYTES) : "memory");
+          const unsigned char* srow = reinterpret_cast<const unsigned char*>(gtab[g].base) + (size_t)sy * 4 * wp16 + (size_t)x0 * 16;
+          const uint32_t sa0 = smem_u32(As) + (uint32_t)(NSTAGE + s) * (uint32_t)G::STAGE_BYTES;
+#pragma unroll
+          for (int pl = 0; pl < 2 * PARTS; ++pl)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             sa0 + (uint32_t)(pl * PLANE * 16)),
+                         "l"(srow + (size_t)pl * wp16), "r"(ROW_BYTES), "r"(bar)
+                         : "memory");
+          ++tk;
         }
       }
-      if (++ds == (uint32_t)ND) { ds = 0; d_par ^= 1u; }
     }
     __syncwarp();
   }
@@ -806,7 +920,8 @@ static int choose_rpc(int units, int H, int ks, int max_ctas) {
 template <int KS, int PARTS>
 static int launch_row(ConvRowParams& p, cudaStream_t st) {
   using G = RowGeom<KS, PARTS>;
-  const size_t smem = CR_SMEM_HDR + (size_t)p.ngroups * G::B_GROUP + (size_t)G::NSTAGE * G::STAGE_BYTES + (size_t)p.cin_ch * 8;
+  const size_t smem = CR_SMEM_HDR + (size_t)p.ngroups * G::B_GROUP + (size_t)(G::NSTAGE + (p.has_staged ? CR_NT : 0)) * G::STAGE_BYTES +
+                      (size_t)p.cin_ch * 8;
   if (smem > 227 * 1024) return PBMC_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
@@ -852,7 +967,9 @@ bool conv_row_supported(const pbmc_conv_desc& d) {
   for (int s = 0; s < d.nsrc; ++s) cin += d.src[s].nblk * 4;
   const size_t n = (size_t)d.ksize * 16, b_group = (size_t)d.ksize * 2 * (2 * n * 16);
   const size_t plane = ((128 + d.ksize - 1) + 7) / 8 * 8;
-  const size_t smem = CR_SMEM_HDR + ng * b_group + 8 * (2 * 2 * plane * 16) + (size_t)cin * 8;
+  bool staged = false;
+  for (int s = 0; s < d.nsrc; ++s) staged = staged || d.src[s].layout == PBMC_LAYOUT_STAGED16;
+  const size_t smem = CR_SMEM_HDR + ng * b_group + (size_t)(8 + (staged ? CR_NT : 0)) * (2 * 2 * plane * 16) + (size_t)cin * 8;
   return smem <= 227 * 1024;
 }
 
@@ -872,6 +989,8 @@ int conv_row_dispatch(const pbmc_conv_desc& d, cudaStream_t st) {
   p.cin_ch = cin;
   p.rpc = 1;
   p.max_ctas = d.max_ctas;
+  p.has_staged = 0;
+  for (int s = 0; s < d.nsrc; ++s) p.has_staged |= d.src[s].layout == PBMC_LAYOUT_STAGED16;
   p.trace = nullptr;
   p.dbg_dx = getenv("PBMC_ROW_DBG_DX") ? atoi(getenv("PBMC_ROW_DBG_DX")) : 16;
   p.dbg_flags = getenv("PBMC_ROW_DBG_FLAGS") ? atoi(getenv("PBMC_ROW_DBG_FLAGS")) : 0;
@@ -879,6 +998,15 @@ int conv_row_dispatch(const pbmc_conv_desc& d, cudaStream_t st) {
   p.trace = g_row_trace;
 #endif
   p.bias = d.bias; p.out = d.out; p.out_stats = d.out_stats; p.out_chan_sum = d.out_chan_sum;
+  for (int s = 0; s < d.nsrc; ++s) {
+    if (d.src[s].layout == PBMC_LAYOUT_BLOCKED) continue;
+    // staged operand images go through the lean multi-group producer path of the fp16 hi|lo kernel only
+    if (d.src[s].layout != PBMC_LAYOUT_STAGED16 || d.ksize != 3 || d.pad_mode != PBMC_PAD_REPLICATE || d.impl != PBMC_CONV_ROW_F16X2 ||
+        d.src[s].nblk != 4 || d.src[s].xform != PBMC_XFORM_NONE)
+      return PBMC_ERR_UNSUPPORTED;
+    for (int t = 0; t < d.nsrc; ++t)
+      if (d.src[t].xform != PBMC_XFORM_NONE && d.src[t].xform != PBMC_XFORM_GN_GELU) return PBMC_ERR_UNSUPPORTED;
+  }
   const char* base = reinterpret_cast<const char*>(d.wpk_row);
   if (!base) return PBMC_ERR_NULL_POINTER;
   if (!aligned16(base)) return PBMC_ERR_MISALIGNED;

@@ -1,4 +1,6 @@
 // Layout conversion, network-input synthesis, AvgPool2d(2,2) and bicubic up-sampling.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace pbmc {
@@ -132,6 +134,10 @@ __device__ __forceinline__ int src_floor(int d, float scale, float& t) {
 //   pass 1  colv[r][c] = sum_ky wy_r[ky] * src[cy_r[ky]][c]      for the 8 output rows x the tile's source columns
 //   pass 2  out[r][x]  = sum_kx wx_x[kx] * colv[r][cx_x[kx]]
 // i.e. 4 + <=4 shared-memory reads per output instead of 16 (the first version was shared-memory bound: 16.6 us per level).
+// STAGED: the output is written as the conv[1] operand image (PBMC_LAYOUT_STAGED16, include/pbmc.h) instead of
+// blocked fp32: fp16 hi | lo of every value, [row][part][chunk][position][8 channels], with the replicate-padded
+// columns -1 / W at positions 0 / W+1, so that the row conv kernel stages it with four bulk copies per row.
+template <bool STAGED>
 __global__ void __launch_bounds__(256) bicubic_kernel(const pbmc_src S, float* __restrict__ dst, int Hs, int Ws, int H, int W,
                                                       float sy_scale, float sx_scale) {
   __shared__ float4 tile[BU_MAX_SH][BU_MAX_SW];
@@ -203,7 +209,30 @@ __global__ void __launch_bounds__(256) bicubic_kernel(const pbmc_src S, float* _
       const float4 v = colv[ty_][min(max(ix - 1 + kx, 0), Ws - 1) - fx0];
       o.x = fmaf(wx[kx], v.x, o.x); o.y = fmaf(wx[kx], v.y, o.y); o.z = fmaf(wx[kx], v.z, o.z); o.w = fmaf(wx[kx], v.w, o.w);
     }
-    *reinterpret_cast<float4*>(dst + (((size_t)b * S.nblk + cb) * (size_t)H * W + (size_t)oy * W + ox) * 4) = o;
+    if (!STAGED) {
+      *reinterpret_cast<float4*>(dst + (((size_t)b * S.nblk + cb) * (size_t)H * W + (size_t)oy * W + ox) * 4) = o;
+    } else {
+      // channels cb*4 .. cb*4+3 of chunk cb>>1: 8 bytes at byte (cb&1)*8 of the position's 16-byte cell
+      const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(o.x - f01.x, o.y - f01.y), l23 = __floats2half2_rn(o.z - f23.x, o.w - f23.y);
+      const uint2 hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      const uint2 lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      const size_t Wp = (size_t)((W + 127) / 128 * 128 + 2);
+      unsigned char* row = reinterpret_cast<unsigned char*>(dst) + ((size_t)b * H + oy) * 4 * Wp * 16;
+      const size_t plane_hi = (size_t)(cb >> 1) * Wp * 16, plane_lo = (size_t)(2 + (cb >> 1)) * Wp * 16;
+      const size_t cell = (size_t)(ox + 1) * 16 + (size_t)(cb & 1) * 8;
+      *reinterpret_cast<uint2*>(row + plane_hi + cell) = hi;
+      *reinterpret_cast<uint2*>(row + plane_lo + cell) = lo;
+      if (ox == 0) {
+        *reinterpret_cast<uint2*>(row + plane_hi + cell - 16) = hi;
+        *reinterpret_cast<uint2*>(row + plane_lo + cell - 16) = lo;
+      }
+      if (ox == W - 1) {
+        *reinterpret_cast<uint2*>(row + plane_hi + cell + 16) = hi;
+        *reinterpret_cast<uint2*>(row + plane_lo + cell + 16) = lo;
+      }
+    }
   }
 }
 
@@ -235,6 +264,7 @@ extern "C" int pbmc_unpack_nchw(const float* src, float* dst, int B, int C, int 
 
 extern "C" int pbmc_finalize_nchw(const pbmc_src* S, float* dst, int B, int C, int H, int W, void* stream) {
   if (!S || !S->ptr || !dst) return PBMC_ERR_NULL_POINTER;
+  if (S->layout != PBMC_LAYOUT_BLOCKED) return PBMC_ERR_UNSUPPORTED;
   if ((S->xform == PBMC_XFORM_GN_GELU || S->xform == PBMC_XFORM_GN) && (!S->stats || !S->gamma || !S->beta)) return PBMC_ERR_NULL_POINTER;
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || S->nblk != (C + 3) / 4) return PBMC_ERR_BAD_SHAPE;
   if (!aligned16(S->ptr)) return PBMC_ERR_MISALIGNED;
@@ -259,6 +289,7 @@ extern "C" int pbmc_build_input(const float* T, const float* xc, const float* yc
 
 extern "C" int pbmc_avgpool2(const pbmc_src* S, float* dst, int B, int H, int W, void* stream) {
   if (!S || !S->ptr || !dst) return PBMC_ERR_NULL_POINTER;
+  if (S->layout != PBMC_LAYOUT_BLOCKED) return PBMC_ERR_UNSUPPORTED;
   if ((S->xform == PBMC_XFORM_GN_GELU || S->xform == PBMC_XFORM_GN) && (!S->stats || !S->gamma || !S->beta)) return PBMC_ERR_NULL_POINTER;
   const int Ho = H / 2, Wo = W / 2;
   if (B <= 0 || Ho <= 0 || Wo <= 0 || S->nblk <= 0) return PBMC_ERR_BAD_SHAPE;
@@ -269,15 +300,32 @@ extern "C" int pbmc_avgpool2(const pbmc_src* S, float* dst, int B, int H, int W,
   return PBMC_OK;
 }
 
-extern "C" int pbmc_bicubic_up(const pbmc_src* S, float* dst, int B, int Hs, int Ws, int H, int W, void* stream) {
+static int bicubic_launch(const pbmc_src* S, void* dst, int B, int Hs, int Ws, int H, int W, bool staged, void* stream) {
   if (!S || !S->ptr || !dst) return PBMC_ERR_NULL_POINTER;
   if ((S->xform == PBMC_XFORM_GN_GELU || S->xform == PBMC_XFORM_GN) && (!S->stats || !S->gamma || !S->beta)) return PBMC_ERR_NULL_POINTER;
   if (B <= 0 || Hs <= 0 || Ws <= 0 || H < Hs || W < Ws || S->nblk <= 0) return PBMC_ERR_BAD_SHAPE;  // up-sampling only
+  if (S->layout != PBMC_LAYOUT_BLOCKED) return PBMC_ERR_UNSUPPORTED;
+  if (staged && S->nblk != 4) return PBMC_ERR_UNSUPPORTED;  // the staged image is one 16-channel K group
   if (!aligned16(S->ptr) || !aligned16(dst)) return PBMC_ERR_MISALIGNED;
   dim3 grid(cdiv(W, BU_TW), cdiv(H, BU_TH), B * S->nblk);
   if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
-  bicubic_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*S, dst, Hs, Ws, H, W, (float)Hs / (float)H,
-                                                                       (float)Ws / (float)W);
+  if (staged)
+    bicubic_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*S, reinterpret_cast<float*>(dst), Hs, Ws, H, W, (float)Hs / (float)H,
+                                                                 (float)Ws / (float)W);
+  else
+    bicubic_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*S, reinterpret_cast<float*>(dst), Hs, Ws, H, W, (float)Hs / (float)H,
+                                                                  (float)Ws / (float)W);
   PBMC_CHECK_LAUNCH("bicubic_kernel");
   return PBMC_OK;
+}
+
+extern "C" int pbmc_bicubic_up(const pbmc_src* S, float* dst, int B, int Hs, int Ws, int H, int W, void* stream) {
+  return bicubic_launch(S, dst, B, Hs, Ws, H, W, false, stream);
+}
+extern "C" int pbmc_bicubic_up_staged(const pbmc_src* S, void* dst, int B, int Hs, int Ws, int H, int W, void* stream) {
+  return bicubic_launch(S, dst, B, Hs, Ws, H, W, true, stream);
+}
+extern "C" int pbmc_staged_width(int W) { return W > 0 ? (W + 127) / 128 * 128 + 2 : 0; }
+extern "C" size_t pbmc_staged_bytes(int B, int H, int W) {
+  return (B > 0 && H > 0 && W > 0) ? (size_t)B * H * 4 * (size_t)pbmc_staged_width(W) * 16 : 0;
 }

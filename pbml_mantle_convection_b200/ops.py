@@ -180,6 +180,18 @@ class Source:
         return L.make_src(self.t, self.nblk, self.xform, self.stats, self.gamma, self.beta, self.inv_count)
 
 
+class StagedSource:
+    """A 16-channel conv input in PBMC_LAYOUT_STAGED16 (fp16 hi|lo operand image, see include/pbmc.h): what
+    `bicubic_up(..., staged=True)` returns.  Only the row conv kernel reads it (3x3, replicate padding)."""
+
+    def __init__(self, buf, B, H, W):
+        self.t, self.B, self.H, self.W = buf, B, H, W
+        self.nblk, self.xform = 4, L.XFORM_NONE
+
+    def c(self):
+        return L.make_src(self.t, 4, L.XFORM_NONE, layout=L.LAYOUT_STAGED16)
+
+
 def finalize_nchw(src: Source, Cc: int) -> torch.Tensor:
     B, CB, H, W, _ = src.t.shape
     out = torch.empty(B, Cc, H, W, dtype=torch.float32, device=src.t.device)
@@ -226,10 +238,15 @@ def avgpool2(src: Source) -> torch.Tensor:
     return out
 
 
-def bicubic_up(src: Source, H: int, W: int) -> torch.Tensor:
+def bicubic_up(src: Source, H: int, W: int, staged: bool = False):
     B, CB, Hs, Ws, _ = src.t.shape
-    out = torch.empty(B, CB, H, W, 4, dtype=torch.float32, device=src.t.device)
     s = src.c()
+    if staged:
+        lib = L.load()
+        buf = torch.zeros(lib.pbmc_staged_bytes(B, H, W), dtype=torch.uint8, device=src.t.device)
+        L.check(lib.pbmc_bicubic_up_staged(C.byref(s), L.ptr(buf), B, Hs, Ws, H, W, L.stream_ptr(buf.device)), "pbmc_bicubic_up_staged")
+        return StagedSource(buf, B, H, W)
+    out = torch.empty(B, CB, H, W, 4, dtype=torch.float32, device=src.t.device)
     L.check(L.load().pbmc_bicubic_up(C.byref(s), L.ptr(out), B, Hs, Ws, H, W, L.stream_ptr(out.device)), "pbmc_bicubic_up")
     return out
 

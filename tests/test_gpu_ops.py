@@ -325,6 +325,64 @@ def test_fluid_layer_chain_with_fused_groupnorm_and_concat(impl):
     assert relerr(fin, a1) < 3e-6
 
 
+def _decode_staged(buf, B, H, W):
+    """PBMC_LAYOUT_STAGED16 -> (hi + lo) as [B, 16, H, W+2] float64 (columns -1 .. W) and the raw halves."""
+    Wp = (W + 127) // 128 * 128 + 2
+    h = buf.view(torch.float16).view(B, H, 2, 2, Wp, 8)[:, :, :, :, :W + 2]          # [B, H, part, chunk, pos, 8]
+    v = h.double().permute(0, 2, 3, 5, 1, 4).reshape(B, 2, 16, H, W + 2)            # [B, part, ch, H, pos]
+    return (v[:, 0] + v[:, 1]).cpu().numpy(), h
+
+
+@pytest.mark.parametrize("hs,ws,H,W", [(15, 31, 50, 77), (64, 64, 128, 128), (63, 126, 128, 506), (8, 8, 8, 8)])
+def test_bicubic_staged_layout(hs, ws, H, W):
+    """The up-sampled levels written as conv[1]'s operand image: hi + lo reproduces the blocked fp32 result to fp16^2
+    precision, and positions 0 / W+1 hold the replicate-padded columns."""
+    r = rng(41)
+    x = r.standard_normal((2, 16, hs, ws))
+    src = ops.Source(ops.pack_nchw(cu(x)))
+    ref = ops.unpack_nchw(ops.bicubic_up(src, H, W), 16).cpu().numpy().astype(np.float64)
+    st = ops.bicubic_up(src, H, W, staged=True)
+    got, _ = _decode_staged(st.t, 2, H, W)
+    assert np.abs(got[..., 1:W + 1] - ref).max() <= 2.0 ** -21 * max(1.0, np.abs(ref).max())
+    assert np.array_equal(got[..., 0], got[..., 1]) and np.array_equal(got[..., W + 1], got[..., W])
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 40, 130), (2, 33, 256), (1, 70, 300)])
+def test_conv_row_staged_sources_bit_identical(B, H, W):
+    """conv[1]'s shape: [GN+GELU level 0, up-sampled levels, raw inputs].  With the up-sampled levels given as
+    operand images (bulk-copied into the stage by the TMA engine) the result is bit-identical to the blocked path,
+    and both match the float64 oracle."""
+    r = rng(43)
+    x0 = r.standard_normal((B, 16, H, W))
+    lv = [r.standard_normal((B, 16, H // 2, W // 2)), r.standard_normal((B, 16, H // 4, W // 4))]
+    xin = r.standard_normal((B, 7, H, W))
+    g0, be0 = 1 + 0.2 * r.standard_normal(16), 0.2 * r.standard_normal(16)
+    w, b = r.standard_normal((16, 55, 3, 3)) / 22, r.standard_normal(16)
+    x0b = ops.pack_nchw(cu(x0))
+    st0 = torch.stack([x0b.double().sum((2, 3, 4)), (x0b.double() ** 2).sum((2, 3, 4))], -1).contiguous()
+    lsrc = [ops.Source(ops.pack_nchw(cu(a))) for a in lv]
+    ups_b = [ops.Source(ops.bicubic_up(s_, H, W)) for s_ in lsrc]
+    ups_s = [ops.bicubic_up(s_, H, W, staged=True) for s_ in lsrc]
+    first, last = ops.Source(x0b, L.XFORM_GN_GELU, st0, cu(g0), cu(be0)), ops.Source(ops.pack_nchw(cu(xin)))
+    ch = [16, 16, 16, 7]
+    wpk, wrow = ops.pack_conv_weight(cu(w), ch), ops.pack_conv_weight_row(cu(w), ch)
+    outs = []
+    for ups in (ups_b, ups_s):
+        o, stt, _ = ops.conv_fwd([first, *ups, last], wpk, ops.pad_vec(cu(b), 16, DEV), 16, 3, "replicate", want_stats=True,
+                                 impl="row_f16x2", wpk_row=wrow)
+        outs.append((o.clone(), stt.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    a0 = RN.gelu(RN.group_norm(x0, g0, be0, 4))
+    upr = [ops.unpack_nchw(u_.t, 16).cpu().numpy().astype(np.float64) for u_ in ups_b]
+    ref = RN.conv2d_same(np.concatenate([a0, *upr, xin], 1), w, b, "replicate")
+    assert relerr(ops.unpack_nchw(outs[1][0], 16).cpu().numpy(), ref) < 5e-6
+    # the other kernels refuse the operand-image layout instead of misreading it
+    with pytest.raises(L.PbmcError):
+        ops.conv_fwd([first, *ups_s, last], wpk, ops.pad_vec(cu(b), 16, DEV), 16, 3, "replicate", impl="ffma")
+    with pytest.raises(L.PbmcError):
+        ops.conv_fwd([first, *ups_s, last], wpk, ops.pad_vec(cu(b), 16, DEV), 16, 3, "zeros", impl="row_f16x2", wpk_row=wrow)
+
+
 @pytest.mark.parametrize("H,W", [(16, 16), (15, 31), (50, 77), (2, 3)])
 def test_avgpool_floor(H, W):
     x = rng(4).standard_normal((2, 16, H, W))

@@ -66,6 +66,15 @@ def main():
                 cells = B * H * W
                 print(f"conv1 103->16      B{B} {H}x{W} {impl:12s} cold {cold:8.1f} us  warm {warm:8.1f} us (best {best:.1f})  "
                       f"{cells * 29664 / warm / 1e6:6.1f} TF/s", flush=True)
+            if "row_f16x2" in impls:
+                # the five up-sampled levels as fp16 hi|lo operand images (bulk-copied into the stage)
+                half = ops.Source(torch.randn(B, 4, H // 2, W // 2, 4, device=dev, generator=g))
+                ssrcs = [srcs[0]] + [ops.bicubic_up(half, H, W, staged=True) for _ in range(5)] + [srcs[-1]]
+                f = lambda: ops.conv_fwd(ssrcs, pk1["wpk"], bias, 16, 3, "replicate", impl="row_f16x2", wpk_row=pk1["wpk_row"], out=o, stats=st)
+                cold, _ = timeit(f, flush=flush)
+                warm, best = timeit(f)
+                print(f"conv1 103->16 TMA  B{B} {H}x{W} row_f16x2    cold {cold:8.1f} us  warm {warm:8.1f} us (best {best:.1f})  "
+                      f"{B * H * W * 29664 / warm / 1e6:6.1f} TF/s", flush=True)
 
 
 if __name__ == "__main__":
