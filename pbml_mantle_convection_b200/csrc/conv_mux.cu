@@ -117,8 +117,8 @@ __device__ __forceinline__ void gelu_erf2n(float* x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
     const float a = x[2 * k], b = x[2 * k + 1];
-    x[2 * k] = a * (a > 0.f ? 1.0f - e0 : e0);
-    x[2 * k + 1] = b * (b > 0.f ? 1.0f - e1 : e1);
+    x[2 * k] = fmaf(-fabsf(a), e0, fmaxf(a, 0.f));
+    x[2 * k + 1] = fmaf(-fabsf(b), e1, fmaxf(b, 0.f));
   }
 }
 
@@ -249,6 +249,7 @@ __global__ void __maxnreg__(CM_MAXNREG) conv_mux_kernel(const __grid_constant__ 
       if (do_x) {
         // GroupNorm + GELU, branch-free: out-of-image taps are masked back to zero afterwards
         const bool keep = R.ok && col_ok;
+        const bool all_keep = __all_sync(0xffffffffu, keep) && nb == 4;  // interior warp: nothing to mask (warp-uniform)
 #pragma unroll
         for (int j = 0; j < 4; j += 2) {
           if (j < nb) {
@@ -263,11 +264,16 @@ __global__ void __maxnreg__(CM_MAXNREG) conv_mux_kernel(const __grid_constant__ 
             x8[4] = fmaf(v[4 * j + 4], a1.x, b1.x); x8[5] = fmaf(v[4 * j + 5], a1.y, b1.y);
             x8[6] = fmaf(v[4 * j + 6], a1.z, b1.z); x8[7] = fmaf(v[4 * j + 7], a1.w, b1.w);
             gelu_erf2n<4>(x8);
-            const bool keep1 = keep && j + 1 < nb;  // absent blocks of a partial group stay exactly zero
+            if (all_keep) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[4 * j + e] = keep ? x8[e] : 0.f;
-              v[4 * j + 4 + e] = keep1 ? x8[4 + e] : 0.f;
+              for (int e = 0; e < 8; ++e) v[4 * j + e] = x8[e];
+            } else {
+              const bool keep1 = keep && j + 1 < nb;  // absent blocks of a partial group stay exactly zero
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[4 * j + e] = keep ? x8[e] : 0.f;
+                v[4 * j + 4 + e] = keep1 ? x8[4 + e] : 0.f;
+              }
             }
           }
         }

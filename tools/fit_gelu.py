@@ -47,8 +47,8 @@ def gelu_new(x):
     for k in range(len(mono)-2,-1,-1):
         q = (q*t + np.float32(mono[k])).astype(np.float32)   # not fused but close
     e = np.exp2(q.astype(np.float32)).astype(np.float32)
-    phi = np.where(x>0, np.float32(1)-e, e).astype(np.float32)
-    return (x*phi).astype(np.float32)
+    # the kernels' tail: x * Phi(x) = max(x, 0) - |x| * Phi(-|x|)  (one FMA; float64 product rounded once ~ fmaf)
+    return (np.maximum(x, 0).astype(np.float64) - np.abs(x).astype(np.float64) * e.astype(np.float64)).astype(np.float32)
 xx = np.linspace(-8,8,2000001)
 xx = xx.astype(np.float32).astype(np.float64)
 ref = xx*0.5*(1+erf(xx/np.sqrt(2)))
