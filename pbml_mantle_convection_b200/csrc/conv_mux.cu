@@ -96,19 +96,18 @@ __device__ __forceinline__ void gelu_erf2n(float* x) {
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
     t[k] = f2_pack(fminf(fabsf(x[2 * k]), 6.6f), fminf(fabsf(x[2 * k + 1]), 6.6f));
-    q[k] = f2_pack(4.4101555806984697e-07f, 4.4101555806984697e-07f);
+    q[k] = f2_pack(-2.2756834377020336e-06f, -2.2756834377020336e-06f);
   }
 #define PBMC_F2STEP(c)                                          \
   _Pragma("unroll") for (int k = 0; k < NP; ++k) q[k] = f2_fma(q[k], t[k], f2_pack(c, c));
-  PBMC_F2STEP(-8.559724437379595e-06f)
-  PBMC_F2STEP(6.932390970346009e-05f)
-  PBMC_F2STEP(-0.00026762983147764706f)
-  PBMC_F2STEP(-1.2973447695787885e-05f)
-  PBMC_F2STEP(0.006957729551776724f)
-  PBMC_F2STEP(-0.05244853666847913f)
-  PBMC_F2STEP(-0.4592179744839059f)
-  PBMC_F2STEP(-1.1511046056807646f)
-  PBMC_F2STEP(-0.9999999933766083f)
+  PBMC_F2STEP(3.296563960267106e-05f)
+  PBMC_F2STEP(-0.000157266929481836f)
+  PBMC_F2STEP(-0.0002025088577467934f)
+  PBMC_F2STEP(0.007142822415561599f)
+  PBMC_F2STEP(-0.05254646501180134f)
+  PBMC_F2STEP(-0.4591930475265861f)
+  PBMC_F2STEP(-1.1511069423662477f)
+  PBMC_F2STEP(-0.9999999590055544f)
 #undef PBMC_F2STEP
 #pragma unroll
   for (int k = 0; k < NP; ++k) {

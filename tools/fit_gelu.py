@@ -25,7 +25,7 @@ for deg in range(6,13):
     err_e = np.abs(np.exp2(q)-e)
     err_g = t*err_e
     print(deg, "max abs err e: %.3e  t*e: %.3e"%(err_e.max(), err_g.max()))
-    if best is None and max(err_e.max(),err_g.max())<1.2e-8: best=(deg,c)
+    if best is None and max(err_e.max(),err_g.max())<2e-8: best=(deg,c)  # fp32 rounding of x*Phi is 6e-8 |x|: 1.4e-8 (degree 8) is below it
 deg,c=best
 # convert to monomial in t
 p = C.cheb2poly(c)  # in x
