@@ -47,6 +47,9 @@ constexpr int CM_HDR = 2048;
 #ifndef CM_MAXNREG
 #define CM_MAXNREG (CM_NSETS >= 5 ? 80 : 96)
 #endif
+#ifndef CM_PREFETCH
+#define CM_PREFETCH (CM_NSETS < 5)  // a second row buffer needs the 96-register budget
+#endif
 
 struct ConvMuxParams {
   const float* in;      // [B][nblk][H][W][4]
@@ -399,6 +402,28 @@ __global__ void __maxnreg__(CM_MAXNREG) conv_mux_kernel(const __grid_constant__ 
         if (tr_lane) CM_TR(1202 + 3 * yo);
       };
       int ri = g, yo = g;
+#if CM_PREFETCH
+      // two row buffers: the loads of the row after next are issued as soon as a buffer has been staged (96 registers)
+      Row rb;
+      if (ri + CM_SETS < nin) load_row(ri + CM_SETS, rb);
+      while (ri < nin) {
+        stage_row(ri, ra);
+        if (ri + 2 * CM_SETS < nin) load_row(ri + 2 * CM_SETS, ra);
+        ri += CM_SETS;
+        if (yo < nrows && epi_ready(yo)) {
+          epi_row(yo);
+          yo += CM_SETS;
+        }
+        if (ri >= nin) break;
+        stage_row(ri, rb);
+        if (ri + 2 * CM_SETS < nin) load_row(ri + 2 * CM_SETS, rb);
+        ri += CM_SETS;
+        if (yo < nrows && epi_ready(yo)) {
+          epi_row(yo);
+          yo += CM_SETS;
+        }
+      }
+#else
       while (ri < nin) {
         stage_row(ri, ra);
         ri += CM_SETS;
@@ -408,6 +433,7 @@ __global__ void __maxnreg__(CM_MAXNREG) conv_mux_kernel(const __grid_constant__ 
           yo += CM_SETS;
         }
       }
+#endif
       for (; yo < nrows; yo += CM_SETS) epi_row(yo);
     };
     if (cout_blks == 4 && !epi_gelu && !want_cs)
@@ -490,7 +516,9 @@ __global__ void __maxnreg__(CM_MAXNREG) conv_mux_kernel(const __grid_constant__ 
 
 }  // namespace pbmc
 
+#if CM_NSETS == 5
 #include "conv_mux_ts.cuh"
+#endif
 
 namespace pbmc {
 
@@ -553,6 +581,7 @@ static int choose_rpc_ts(int units, int H, int max_ctas) {
   return best;
 }
 
+#if CM_NSETS == 5
 template <int PARTS>
 static int launch_ts(ConvMuxParams& p, int max_ctas, cudaStream_t st) {
   constexpr int B_GROUP = 3 * PARTS * (2 * CM_N * 16);
@@ -565,6 +594,10 @@ static int launch_ts(ConvMuxParams& p, int max_ctas, cudaStream_t st) {
   PBMC_CHECK_LAUNCH("conv_ts_kernel");
   return PBMC_OK;
 }
+#else  // the TMEM-operand variant is written for five worker groups (one operand slot per group)
+template <int PARTS>
+static int launch_ts(ConvMuxParams&, int, cudaStream_t) { return PBMC_ERR_UNSUPPORTED; }
+#endif
 
 // AUTO picks the mux kernel only when its whole grid is resident at once (<= one CTA per SM of the budget): it was
 // built for the short strips of a single 512^2 field; for batches that run in waves the pipelined row kernel is faster
