@@ -330,6 +330,18 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
   // bicubic kernel stores 2 x 8 B per thread.  PBMC_UP_STAGED=1 turns it on (results are bit-identical).
   static const int staged_knob = getenv("PBMC_UP_STAGED") ? atoi(getenv("PBMC_UP_STAGED")) : 0;
   up_staged = up_staged && staged_knob != 0;
+  {
+    // developer knob: PBMC_BUDGETS="116,24,6,3,2,1" overrides the per-level CTA budgets
+    static const char* bud = getenv("PBMC_BUDGETS");
+    if (bud != nullptr && L > 1) {
+      const char* q = bud;
+      for (int l = 0; l < L && *q; ++l) {
+        cta_budget[l] = atoi(q);
+        while (*q && *q != ',') ++q;
+        if (*q == ',') ++q;
+      }
+    }
+  }
   const float* level_in[PBMC_MAX_LEVELS];
   level_in[0] = F(P.x0);
   for (int l = 0; l < L; ++l) {

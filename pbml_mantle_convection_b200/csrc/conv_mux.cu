@@ -528,7 +528,7 @@ extern "C" void pbmc_debug_set_mux_trace(void* dev_buf) { g_mux_trace = reinterp
 #endif
 
 // Output rows per CTA: minimise waves x (fixed cost + staging rounds + epilogue rounds), in clocks measured with
-// tools/muxtrace.py (a staging round = 5 groups x 2 rows, an epilogue round = 5 rows).
+// tools/muxtrace.py (a staging round = 5 groups x 1 row, an epilogue round = 5 rows).
 static int choose_rpc_mux(int units, int H, int max_ctas, bool gelu) {
   static const int forced = getenv("PBMC_MUX_RPC") ? atoi(getenv("PBMC_MUX_RPC")) : 0;  // developer knob
   if (forced > 0) return forced < H ? (forced < CM_MAXR - 2 ? forced : CM_MAXR - 2) : (H < CM_MAXR - 2 ? H : CM_MAXR - 2);
@@ -538,7 +538,7 @@ static int choose_rpc_mux(int units, int H, int max_ctas, bool gelu) {
   for (int r = 1; r <= CM_MAXR - 2 && r <= H; ++r) {
     const long ctas = (long)units * cdiv(H, r);
     const long waves = (ctas + avail - 1) / avail;
-    const int rounds1 = cdiv(cdiv(r + 2, 2), CM_SETS), rounds2 = cdiv(r, CM_SETS);
+    const int rounds1 = cdiv(r + 2, CM_SETS), rounds2 = cdiv(r, CM_SETS);  // one row per group and round
     const double cost = (double)waves * (4000.0 + rounds1 * (gelu ? 2800.0 : 1800.0) + rounds2 * 1000.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = r; }
   }
