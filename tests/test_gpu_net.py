@@ -316,3 +316,25 @@ def test_driver_per_step_and_resident_agree(tmp_path):
     assert snap_b["ML"]["v"][-1].shape == (H * W, 3) and len(snap_b["ML"]["T"]) == 1 + 3  # initial + one per block
     for sub in ("a", "b"):
         assert (tmp_path / sub / "snapshots_ML.pkl").exists() and (tmp_path / sub / "T_vec_ML.pkl").exists()
+
+
+def test_forward_with_tma_staged_levels_is_bit_identical():
+    """PBMC_UP_STAGED=1: the up-sampled levels are written as conv[1]'s fp16 hi|lo operand image and staged by TMA
+    bulk copies (api.cu / conv_row.cu bulk-copy lane).  Same arithmetic, so the forward must not change by one bit."""
+    import hashlib, os, subprocess, sys
+    code = (
+        "import torch, hashlib\n"
+        "import pbml_mantle_convection_b200 as P\n"
+        "torch.manual_seed(0)\n"
+        "net = P.NewFluidNet(4, 7, 16, 2, 'cuda:0', act_fn='gelu', r_p='replicate', loss_type='curl', use_symm=True, a_bound=10, repeats=2, f=3, p_pred=True).to('cuda:0').eval()\n"
+        "x = torch.randn(2, 7, 70, 150, generator=torch.Generator().manual_seed(1)).to('cuda:0')\n"
+        "u, v, p = net(x)\n"
+        "h = hashlib.sha256(); [h.update(t.float().cpu().numpy().tobytes()) for t in (u, v, p)]; print('HASH', h.hexdigest())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = []
+    for flag in ("0", "1"):
+        res = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, PBMC_UP_STAGED=flag), capture_output=True,
+                             text=True, timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+        out.append([ln for ln in res.stdout.splitlines() if ln.startswith("HASH")][0])
+    assert out[0] == out[1]
