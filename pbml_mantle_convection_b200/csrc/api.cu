@@ -25,6 +25,7 @@ bool conv_row_supported(const pbmc_conv_desc& d);
 int conv_mux_dispatch(const pbmc_conv_desc& d, cudaStream_t st);  // conv_mux.cu
 bool conv_mux_supported(const pbmc_conv_desc& d);
 bool conv_mux_one_wave(const pbmc_conv_desc& d);
+extern thread_local int g_conv_pdl_next;  // conv_mux.cu: the next mux launch uses programmatic dependent launch
 
 }  // namespace pbmc
 
@@ -276,6 +277,11 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
                                 const pbmc_member* members, float* u, float* v, float* p, uint32_t* uvmax, int B, int H,
                                 int W, cudaStream_t st) {
   const int L = P.L, R = P.R, CB = P.CB;
+  // Programmatic dependent launch on the critical chain, bit 1: conv[2], conv[3] (on: nothing else runs then, the
+  // set-up of the next conv overlaps the drain of the previous one: 0.2348 -> 0.2331 ms/step at 512^2); bit 2: the
+  // level-0 trunk (off: 0.27 ms -- an early-resident CTA parked in griddepcontrol.wait takes an SM from the other
+  // levels' streams).  PBMC_CHAIN_PDL overrides.
+  static const int chain_pdl = getenv("PBMC_CHAIN_PDL") ? atoi(getenv("PBMC_CHAIN_PDL")) : 1;
   auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto S = [&](int slot) { return reinterpret_cast<double*>(ws + P.stat_off(slot, B)); };
   double* chan_sum = reinterpret_cast<double*>(ws + P.chan_sum);
@@ -369,7 +375,12 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
         d.src[0] = make_src(F(P.ping[l][(r - 1) & 1]), CB, PBMC_XFORM_GN_GELU, S(1 + l * R + r - 1),
                             &n.trunk[l * PBMC_MAX_REPEATS + r - 1], invc);
       }
-      RC(conv_enqueue(d, sl));
+      g_conv_pdl_next = l == 0 ? (chain_pdl & 2) : 0;
+      {
+        const int rct = conv_enqueue(d, sl);
+        g_conv_pdl_next = 0;
+        RC(rct);
+      }
     }
     if (l > 0) {
       pbmc_src us = make_src(F(P.ping[l][(R - 1) & 1]), CB, PBMC_XFORM_GN_GELU, S(1 + l * R + R - 1),
@@ -398,12 +409,22 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
   fill_conv(d, n, n.conv2, B, H, W, F(P.h2), nullptr, nullptr, PBMC_ACT_GELU);
   d.nsrc = 1;
   d.src[0] = make_src(F(P.h1), CB, PBMC_XFORM_GN_GELU, S(1 + L * R), &n.conv1, 1.0 / (4.0 * H * W));
-  RC(conv_enqueue(d, st));
+  g_conv_pdl_next = chain_pdl & 1;
+  {
+    const int rc2 = conv_enqueue(d, st);
+    g_conv_pdl_next = 0;
+    RC(rc2);
+  }
   // conv[3] (:1342) with per-channel sums for the zero-mean (:1343)
   fill_conv(d, n, n.conv3, B, H, W, F(P.h3), nullptr, chan_sum, PBMC_ACT_NONE);
   d.nsrc = 1;
   d.src[0] = make_src(F(P.h2), CB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
-  RC(conv_enqueue(d, st));
+  g_conv_pdl_next = chain_pdl & 1;
+  {
+    const int rc3 = conv_enqueue(d, st);
+    g_conv_pdl_next = 0;
+    RC(rc3);
+  }
   RC(pbmc_head(F(P.h3), chan_sum, members, n.a_bound, n.head_kind, n.p_pred, u, v, p, uvmax, B, H, W, st));
   return PBMC_OK;
 }

@@ -522,6 +522,8 @@ __global__ void __maxnreg__(CM_MAXNREG) conv_mux_kernel(const __grid_constant__ 
 
 namespace pbmc {
 
+thread_local int g_conv_pdl_next = 0;  // set by api.cu right before the launch it applies to
+
 #ifdef PBMC_ROW_TRACE
 static unsigned long long* g_mux_trace = nullptr;
 extern "C" void pbmc_debug_set_mux_trace(void* dev_buf) { g_mux_trace = reinterpret_cast<unsigned long long*>(dev_buf); }
@@ -559,7 +561,21 @@ static int launch_mux(ConvMuxParams& p, int max_ctas, cudaStream_t st) {
   if (smem > 227 * 1024) return PBMC_ERR_UNSUPPORTED;
   dim3 grid(cdiv(p.H, p.rpc), nstrips, p.B);
   if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
-  conv_mux_kernel<PARTS><<<grid, CM_THREADS, smem, st>>>(p);
+  // Programmatic dependent launch for the convs that api.cu marks (conv[2], conv[3]: no other stream is busy then, so
+  // an early-resident CTA waiting in griddepcontrol.wait starves nobody): the set-up (barriers, TMEM, filters) runs
+  // while the producer kernel drains; the kernel reads its producer's outputs only after griddepcontrol.wait.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(CM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_conv_pdl_next ? 1 : 0;
+  g_conv_pdl_next = 0;
+  PBMC_CUDA(cudaLaunchKernelEx(&cfg, conv_mux_kernel<PARTS>, p));
   PBMC_CHECK_LAUNCH("conv_mux_kernel");
   return PBMC_OK;
 }
