@@ -277,11 +277,13 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
                                 const pbmc_member* members, float* u, float* v, float* p, uint32_t* uvmax, int B, int H,
                                 int W, cudaStream_t st) {
   const int L = P.L, R = P.R, CB = P.CB;
-  // Programmatic dependent launch on the critical chain, bit 1: conv[2], conv[3] (on: nothing else runs then, the
-  // set-up of the next conv overlaps the drain of the previous one: 0.2348 -> 0.2331 ms/step at 512^2); bit 2: the
-  // level-0 trunk (off: 0.27 ms -- an early-resident CTA parked in griddepcontrol.wait takes an SM from the other
-  // levels' streams).  PBMC_CHAIN_PDL overrides.
-  static const int chain_pdl = getenv("PBMC_CHAIN_PDL") ? atoi(getenv("PBMC_CHAIN_PDL")) : 1;
+  // Programmatic dependent launch on the critical chain (PBMC_CHAIN_PDL overrides the mask; default 1 | 4):
+  //   1  conv[2], conv[3]   on: nothing else runs then; the next conv's set-up overlaps the previous one's drain
+  //   4  conv[1]            on  (0.2348 -> 0.2331 -> 0.2311 ms/step at 512^2 with 1, then 1 | 4)
+  //   8  head kernel        off: no measurable change
+  //   2  level-0 trunk      off: 0.27 ms -- an early-resident CTA parked in griddepcontrol.wait takes an SM from
+  //                              the other levels' streams
+  static const int chain_pdl = getenv("PBMC_CHAIN_PDL") ? atoi(getenv("PBMC_CHAIN_PDL")) : 5;
   auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto S = [&](int slot) { return reinterpret_cast<double*>(ws + P.stat_off(slot, B)); };
   double* chan_sum = reinterpret_cast<double*>(ws + P.chan_sum);
@@ -404,7 +406,12 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
     if (up_staged) d.src[l].layout = PBMC_LAYOUT_STAGED16;
   }
   d.src[L] = make_src(inp, P.CIB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
-  RC(conv_enqueue(d, st));
+  g_conv_pdl_next = chain_pdl & 4;
+  {
+    const int rc1 = conv_enqueue(d, st);
+    g_conv_pdl_next = 0;
+    RC(rc1);
+  }
   // gn[0] + act folded into conv[2]'s load; conv[2] + act (:1336-1340)
   fill_conv(d, n, n.conv2, B, H, W, F(P.h2), nullptr, nullptr, PBMC_ACT_GELU);
   d.nsrc = 1;
@@ -425,7 +432,12 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
     g_conv_pdl_next = 0;
     RC(rc3);
   }
-  RC(pbmc_head(F(P.h3), chan_sum, members, n.a_bound, n.head_kind, n.p_pred, u, v, p, uvmax, B, H, W, st));
+  g_conv_pdl_next = chain_pdl & 8;
+  {
+    const int rch = pbmc_head(F(P.h3), chan_sum, members, n.a_bound, n.head_kind, n.p_pred, u, v, p, uvmax, B, H, W, st);
+    g_conv_pdl_next = 0;
+    RC(rch);
+  }
   return PBMC_OK;
 }
 

@@ -34,6 +34,8 @@
 
 namespace pbmc {
 
+extern thread_local int g_conv_pdl_next;  // conv_mux.cu: set by api.cu right before the launch it applies to
+
 constexpr int CR_EPI_WARPS = 8;                        // two sets of 4 (alternate output rows)
 constexpr int CR_NPG = 3;                              // producer groups (4 warps = 128 positions each)
 constexpr int CR_MMA_WARP = CR_EPI_WARPS + 4 * CR_NPG;  // warps 0-7 epilogue, 8 .. 8+4*NPG-1 producers, then the MMA issuer
@@ -945,7 +947,8 @@ static int launch_row(ConvRowParams& p, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = (pdl || g_conv_pdl_next) ? 1 : 0;
+  g_conv_pdl_next = 0;
   PBMC_CUDA(cudaLaunchKernelEx(&cfg, conv_row_kernel<KS, PARTS>, p));
   PBMC_CHECK_LAUNCH("conv_row_kernel");
   return PBMC_OK;

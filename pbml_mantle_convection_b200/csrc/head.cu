@@ -9,10 +9,15 @@
 
 namespace pbmc {
 
+extern thread_local int g_conv_pdl_next;  // conv_mux.cu: set by api.cu right before the launch it applies to
+
 __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ y, const double* __restrict__ chan_sum,
                                                    const pbmc_member* __restrict__ mem, float a_bound, int head_kind,
                                                    int p_pred, float* __restrict__ u, float* __restrict__ v,
                                                    float* __restrict__ p, uint32_t* __restrict__ uvmax, int H, int W) {
+  // no-ops unless launched with programmatic stream serialization (api.cu does, behind conv[3])
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int b = blockIdx.z;
   const int gx = blockIdx.x * 32 + threadIdx.x;
   const int gy = blockIdx.y * 8 + threadIdx.y;
@@ -77,8 +82,17 @@ extern "C" int pbmc_head(const float* y, const double* chan_sum, const pbmc_memb
   if (!aligned16(y)) return PBMC_ERR_MISALIGNED;
   dim3 grid(cdiv(W, 32), cdiv(H, 8), B);
   if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
-  head_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(y, chan_sum, members, a_bound, head_kind, p_pred, u, v, p,
-                                                             uvmax, H, W);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(32, 8);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pbmc::g_conv_pdl_next ? 1 : 0;
+  pbmc::g_conv_pdl_next = 0;
+  PBMC_CUDA(cudaLaunchKernelEx(&cfg, head_kernel, y, chan_sum, members, a_bound, head_kind, p_pred, u, v, p, uvmax, H, W));
   PBMC_CHECK_LAUNCH("head_kernel");
   return PBMC_OK;
 }
