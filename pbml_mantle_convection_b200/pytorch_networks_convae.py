@@ -345,6 +345,7 @@ class TS(nn.Module):
         self.advection_scheme, self.scale, self.p_pred, self.net = advection_scheme, scale, p_pred, net
         self._grid_key, self._grid = None, None
         self._plan_key, self._plan = None, None
+        self._early_plan = None
         self.use_cuda_graph = True  # replay the whole call (convert in, ts steps, convert out) as one CUDA graph
 
     def _get_grid(self, xc, yc, ycc, dev):
@@ -363,14 +364,16 @@ class TS(nn.Module):
         return self._grid
 
     # ------------------------------------------------------------------ fused, device-resident path
-    def _forward_fused(self, T_prev, grid, prm, prm_nd, B, H, W, dev, cn_max):
+    def _forward_fused(self, T_prev, grid, prm, prm_nd, B, H, W, dev, cn_max, early_copied=False):
         """`ts` steps of build-input -> surrogate -> un-scale -> advect/diffuse -> BCs through pbmc_rollout.
         All device buffers of one (shape, ts, dtype, weights) configuration are cached in a plan; from the
         second call on, the dtype conversions and the ts steps replay as ONE CUDA graph, so a call costs one
         host->device copy of T, one graph launch and the result clones -- no allocation, no per-kernel launch."""
         stokes, n, dtype = self.stokes, self.ts, T_prev.dtype
         eng = stokes._engine(dev)
-        stokes._check_fused(torch.empty(1, stokes.c_i, 1, 1, device=dev))
+        _require_gelu(stokes)  # (the per-call part of stokes._check_fused; the input here is built on the device)
+        if stokes.training and any(m.dropout.p != 0.0 for m in stokes.modules() if isinstance(m, FluidLayer)):
+            raise NotImplementedError("dropout>0 in training mode is outside the inference path")
         eng.refresh()
         key = (B, H, W, n, dtype, id(grid), id(eng), eng._key, float(cn_max), bool(stokes.p_pred))
         pl = self._plan if key == self._plan_key else None
@@ -381,15 +384,22 @@ class TS(nn.Module):
             pl.state = RolloutState(grid, pl.members, B, n + 1, n, cn_max, per_member_dt=False, p_pred=stokes.p_pred,
                                     device=dev)
             pl.T_in = torch.empty(B, H, W, dtype=dtype, device=dev)
-            pl.T_out = torch.empty(n, B, 1, H, W, dtype=dtype, device=dev)
-            pl.dt_out = torch.empty(n, dtype=dtype, device=dev)
-            pl.f_out = torch.empty(4 if stokes.p_pred else 3, B, 1, H, W, dtype=dtype, device=dev)  # u, v, V, (p)
+            # all results of a call live in ONE buffer (T of every step | u, v, V, (p) | dt of every step), so that
+            # handing the caller its own copy is one clone instead of three
+            nf = 4 if stokes.p_pred else 3
+            pl.n_T, pl.n_f = n * B * H * W, nf * B * H * W
+            pl.out = torch.empty(pl.n_T + pl.n_f + n, dtype=dtype, device=dev)
+            pl.split = lambda buf: (buf[:pl.n_T].view(n, B, 1, H, W), buf[pl.n_T + pl.n_f:],
+                                    buf[pl.n_T:pl.n_T + pl.n_f].view(nf, B, 1, H, W))
+            pl.T_out, pl.dt_out, pl.f_out = pl.split(pl.out)
             pl.graph, pl.calls = None, 0
             self._plan, self._plan_key = pl, key
         if (prm, prm_nd) != pl.members_key:
             pl.members.copy_(ops.make_members([prm] * B, "cpu", nd_override=[prm_nd] * B))
             pl.members_key = (prm, prm_nd)
-        pl.T_in.copy_(T_prev.reshape(B, H, W), non_blocking=True)
+        if not early_copied or pl is not self._early_plan:
+            pl.T_in.copy_(T_prev.reshape(B, H, W), non_blocking=True)
+        self._early_plan = None
 
         def body():
             st = pl.state
@@ -414,7 +424,7 @@ class TS(nn.Module):
                     body()
                 pl.graph = g
             pl.graph.replay()
-        T_all, dt_all, f_all = pl.T_out.clone(), pl.dt_out.clone(), pl.f_out.clone()  # callers own what they get
+        T_all, dt_all, f_all = pl.split(pl.out.clone())  # callers own what they get
         x = {0: T_prev if T_prev.is_cuda else pl.T_in.clone().view(T_prev.shape)}
         dts = {}
         for i in range(1, n + 1):
@@ -439,6 +449,13 @@ class TS(nn.Module):
         dtype = T_prev.dtype
         B = T_prev.shape[0] if T_prev.dim() == 4 else 1
         H, W = T_prev.shape[-2:]
+        # The host->device copy of T is the first thing the device needs: if the cached plan fits this call's shape and
+        # dtype it is enqueued before the (tens of microseconds of) host-side bookkeeping below, which then overlaps it.
+        early, pl0 = False, self._plan
+        if pl0 is not None and pl0.T_in.dtype == dtype and tuple(pl0.T_in.shape) == (B, H, W) and T_prev.numel() == B * H * W:
+            pl0.T_in.copy_(T_prev.reshape(B, H, W), non_blocking=True)
+            early = True
+        self._early_plan = pl0 if early else None
         grid = self._get_grid(xc, yc, ycc, dev)
         fl = lambda t: float(t)
         advect = self.ad is not None and self.net == "newfluidnet"
@@ -448,7 +465,7 @@ class TS(nn.Module):
         if fused and advect:
             # whole loop device-resident: one C call enqueues ts steps (batch-global dt like ADNet, :556)
             return self._forward_fused(T_prev, grid, (fl(raq), fl(fkt), fl(fkp)), (fl(raq_nd), fl(fkt_nd), fl(fkp_nd)), B, H, W,
-                                       dev, cn_max)
+                                       dev, cn_max, early_copied=early)
         members = ops.make_members([(fl(raq), fl(fkt), fl(fkp))] * B, dev, nd_override=[(fl(raq_nd), fl(fkt_nd), fl(fkp_nd))] * B)
         T0 = T_prev.to(dev)
         x, dts = {0: T0}, {}
