@@ -71,7 +71,8 @@ struct ConvMuxParams {
   int stagger;  // TS kernel: start delay per worker group, clocks
 };
 
-// developer experiments (trace builds only; results become WRONG): 1 = no proxy fence after staging a row, 2 = no global loads
+// developer experiments (trace builds only; results become WRONG): 1 = no proxy fence after staging a row, 2 = no global loads,
+// 4 = GroupNorm coefficients from immediates instead of ld.shared, 8 = no MMAs (commit only), 16 = no GELU
 #ifdef PBMC_ROW_TRACE
 #define CM_DBG(flag) ((p.dbg_flags & (flag)) != 0)
 #else
@@ -256,16 +257,21 @@ __global__ void __maxnreg__(CM_MAXNREG) conv_mux_kernel(const __grid_constant__ 
         for (int j = 0; j < 4; j += 2) {
           if (j < nb) {
             float4 a0, b0, a1, b1;
+            if (CM_DBG(4)) {
+              a0 = a1 = make_float4(1.01f, 0.99f, 1.02f, 0.98f);
+              b0 = b1 = make_float4(0.01f, -0.01f, 0.02f, -0.02f);
+            } else {
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a0.x), "=f"(a0.y), "=f"(a0.z), "=f"(a0.w) : "r"(xfa_addr + j * 16));
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(xfb_addr + j * 16));
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a1.x), "=f"(a1.y), "=f"(a1.z), "=f"(a1.w) : "r"(xfa_addr + j * 16 + 16));
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(xfb_addr + j * 16 + 16));
+            }
             float x8[8];
             x8[0] = fmaf(v[4 * j + 0], a0.x, b0.x); x8[1] = fmaf(v[4 * j + 1], a0.y, b0.y);
             x8[2] = fmaf(v[4 * j + 2], a0.z, b0.z); x8[3] = fmaf(v[4 * j + 3], a0.w, b0.w);
             x8[4] = fmaf(v[4 * j + 4], a1.x, b1.x); x8[5] = fmaf(v[4 * j + 5], a1.y, b1.y);
             x8[6] = fmaf(v[4 * j + 6], a1.z, b1.z); x8[7] = fmaf(v[4 * j + 7], a1.w, b1.w);
-            gelu_erf2n<4>(x8);
+            if (!CM_DBG(16)) gelu_erf2n<4>(x8);
             if (all_keep) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[4 * j + e] = x8[e];
@@ -488,7 +494,7 @@ __global__ void __maxnreg__(CM_MAXNREG) conv_mux_kernel(const __grid_constant__ 
         const uint32_t dcol = tmem_base + ds * (uint32_t)N;
         const uint64_t a_s = a_desc0 + (uint64_t)((uint32_t)ri * (uint32_t)(STAGE_BYTES >> 4));
 #pragma unroll
-        for (int dx = 0; dx < KS; ++dx) {
+        for (int dx = 0; dx < KS && !CM_DBG(8); ++dx) {
           const uint64_t a_hi = a_s + (uint64_t)dx;  // one position = 16 B
           const uint64_t b_hi = b_desc0 + (uint64_t)(dx * PARTS * (B_TILE >> 4));
           umma_ss<1>(dcol, a_hi, b_hi, IDESC, (uint32_t)dx);
