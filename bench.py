@@ -156,7 +156,7 @@ def run_reference(args, wl):
         "e2e": {"value": rate, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------- GPU arm
@@ -462,7 +462,7 @@ def run_ours(args, wl):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def run_slab(args, wl):
@@ -524,13 +524,34 @@ def run_slab(args, wl):
                              "frac": gbs / hbm, "traffic": None, "peak_source": which,
                              "note": "per GPU, 16 algorithmic B/cell; the step also holds the dt all-reduce(MAX) and the halo exchange"},
                 "cpu_baseline": None, "e2e": None, "gpu_launches": K, "clocks": clk.summary(), "finite": finite}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _own_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner to
+    fd 1 when NCCL_DEBUG is set on the box), so fd 1 is pointed at stderr for the whole run and the JSON line goes to
+    a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
