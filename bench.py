@@ -526,8 +526,14 @@ def run_slab(args, wl):
                 "cpu_baseline": None, "e2e": None, "gpu_launches": K, "clocks": clk.summary(), "finite": finite}
         emit(line)
     if world > 1:
+        # The 8-rank run of this workload printed its line and then never exited (tearing down the process group with
+        # captured NCCL all-reduces and the symmetric-memory rendezvous alive; 2 ranks were fine).  Nothing is left to
+        # do after the line: synchronise, meet at a barrier so that no rank still needs the store, and leave without
+        # running the destructors.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 _REAL_STDOUT = None
