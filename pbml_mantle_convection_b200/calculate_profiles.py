@@ -21,28 +21,21 @@ def selu(x):
     return scale * (np.maximum(0, x) + np.minimum(alpha * (np.exp(x) - 1), 0))
 
 
-def non_dimensionalize_raq(x):
-    return (x - _RAQ[0]) / (_RAQ[1] - _RAQ[0])
+def _to_unit(rng, log):
+    lo, span = rng[0], rng[1] - rng[0]
+    return (lambda x: (np.log10(x) - lo) / span) if log else (lambda x: (x - lo) / span)
 
 
-def non_dimensionalize_fkt(x):
-    return (np.log10(x) - _FKT[0]) / (_FKT[1] - _FKT[0])
+def _from_unit(rng, log):
+    lo, span = rng[0], rng[1] - rng[0]
+    return (lambda x: 10 ** (x * span + lo)) if log else (lambda x: x * span + lo)
 
 
-def non_dimensionalize_fkv(x):
-    return (np.log10(x) - _FKV[0]) / (_FKV[1] - _FKV[0])
-
-
-def dimensionalize_raq(x):
-    return x * (_RAQ[1] - _RAQ[0]) + _RAQ[0]
-
-
-def dimensionalize_fkt(x):
-    return 10 ** (x * (_FKT[1] - _FKT[0]) + _FKT[0])
-
-
-def dimensionalize_fkv(x):
-    return 10 ** (x * (_FKV[1] - _FKV[0]) + _FKV[0])
+# the reference's six public helpers (calculate_profiles.py:13-36): RaQ is scaled linearly, the two viscosity
+# contrasts in log10; the ranges are those of its 130 training simulations
+non_dimensionalize_raq, dimensionalize_raq = _to_unit(_RAQ, False), _from_unit(_RAQ, False)
+non_dimensionalize_fkt, dimensionalize_fkt = _to_unit(_FKT, True), _from_unit(_FKT, True)
+non_dimensionalize_fkv, dimensionalize_fkv = _to_unit(_FKV, True), _from_unit(_FKV, True)
 
 
 def get_input(raq_ra, fkt, fkp, y_prof):
