@@ -45,8 +45,30 @@ def full_weight(m: nn.Conv2d) -> torch.Tensor:
     return torch.cat(out, 0)
 
 
+TENSOR_CORE_MIN_SIDE = 32  # below this a CTA's 128-column strip is mostly padding: the FFMA kernel is used
+
+
+def _packed_filters(m: nn.Conv2d, dev, want_row: bool):
+    """Packed filter images + padded bias of a conv module, cached on the module and rebuilt when the parameters
+    change (in-place updates bump `_version`; `.to()` / `load_state_dict(assign=True)` change the storage)."""
+    w, b = m.weight, m.bias
+    key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version), str(dev))
+    c = m.__dict__.get("_pbmc_pack")
+    if c is None or c["key"] != key:
+        c = {"key": key, "wf": full_weight(m).detach().to(dev, torch.float32), "row": None}
+        c["wpk"] = ops.pack_conv_weight(c["wf"], [m.in_channels])
+        c["bias"] = ops.pad_vec(b, m.out_channels, dev)
+        m.__dict__["_pbmc_pack"] = c  # plain attribute: not a parameter, not a buffer, not in the state_dict
+    if want_row and c["row"] is None:
+        c["row"] = ops.pack_conv_weight_row(c["wf"], [m.in_channels])
+    return c["wpk"], (c["row"] if want_row else None), c["bias"]
+
+
 def conv_module_forward(m: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
-    """Stand-alone forward of an nn.Conv2d-shaped module on an NCHW tensor through libpbmc."""
+    """Stand-alone forward of an nn.Conv2d-shaped module on an NCHW tensor through libpbmc.
+    Images of at least TENSOR_CORE_MIN_SIDE rows and columns with c_out <= 16 go to the tensor-core kernels (fp16 hi+lo, fp32-grade; the library
+    picks the time-multiplexed or the row-streaming one), thin strips (the edge regions of the learned-boundary conv,
+    reference :1022-1065) and wide outputs to the FFMA kernel."""
     _check_conv_supported(m)
     if not x.is_cuda:
         raise L.PbmcError("this layer has no CPU implementation; move the module and input to a CUDA device")
@@ -56,12 +78,12 @@ def conv_module_forward(m: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
         pad = (0, 0)
     elif pad == "same":
         pad = (k // 2, k // 2)
-    w = full_weight(m).detach().to(x.device, torch.float32)
-    wpk = ops.pack_conv_weight(w, [m.in_channels])
-    bias = ops.pad_vec(m.bias, m.out_channels, x.device)
+    tensor_core = m.out_channels <= 16 and min(x.shape[-2:]) >= TENSOR_CORE_MIN_SIDE
+    wpk, wrow, bias = _packed_filters(m, x.device, tensor_core)
     xb = ops.pack_nchw(x)
     mode = m.padding_mode if pad != (0, 0) else "zeros"
-    yb, _, _ = ops.conv_fwd([ops.Source(xb)], wpk, bias, m.out_channels, k, mode, impl="ffma")
+    yb, _, _ = ops.conv_fwd([ops.Source(xb)], wpk, bias, m.out_channels, k, mode, impl="auto" if tensor_core else "ffma",
+                            wpk_row=wrow)
     y = ops.unpack_nchw(yb, m.out_channels)
     # 'same' geometry is computed; smaller paddings are a crop of it (exact for zeros / valid)
     cy, cx = k // 2 - pad[0], k // 2 - pad[1]

@@ -281,6 +281,26 @@ def test_learned_boundary_network_runs_and_matches_oracle_layers():
     assert relerr(net.conv[0](x).cpu().numpy(), ref) < 5e-6
 
 
+@pytest.mark.parametrize("k,ci,co", [(5, 16, 16), (3, 7, 16), (5, 16, 1)])
+def test_learned_boundary_conv_tensor_core_interior(k, ci, co):
+    """At the sizes real grids have (>= 32 rows and columns) the interior region of the 9-region conv runs on the
+    tensor-core kernels (fp16 hi+lo), the strips on the FFMA kernel; packed filters are cached on the modules and
+    follow in-place weight updates."""
+    torch.manual_seed(3)
+    m = P.BoundaryLearnedConvolution2D(ci, co, k).double().to(DEV)
+    with torch.no_grad():
+        m.learnable_bias.normal_()
+    x = torch.randn(2, ci, 40, 48, dtype=torch.float64, device=DEV)
+    sd = {kk: t.detach().cpu().numpy() for kk, t in m.state_dict().items()}
+    ref = RN.boundary_learned_conv(x.cpu().numpy(), sd, "", k, co)
+    assert relerr(m(x).cpu().numpy(), ref) < 5e-6
+    assert relerr(m(x).cpu().numpy(), ref) < 5e-6  # second call: cached filter images
+    with torch.no_grad():
+        m.conv.weight.mul_(0.5)  # in-place update: the cache must notice
+    sd = {kk: t.detach().cpu().numpy() for kk, t in m.state_dict().items()}
+    assert relerr(m(x).cpu().numpy(), RN.boundary_learned_conv(x.cpu().numpy(), sd, "", k, co)) < 5e-6
+
+
 def test_no_silent_fallback_on_gpu_box():
     with pytest.raises(L.PbmcError):
         P.NewFluidNet(2, 7, 16, 2, DEV, act_fn="gelu", r_p="replicate", loss_type="curl", use_symm=True,
