@@ -301,6 +301,35 @@ def test_learned_boundary_conv_tensor_core_interior(k, ci, co):
     assert relerr(m(x).cpu().numpy(), RN.boundary_learned_conv(x.cpu().numpy(), sd, "", k, co)) < 5e-6
 
 
+def test_learned_network_graph_replay_equals_eager_and_tracks_weights():
+    """From the third call on a learned-boundary network replays its forward as one CUDA graph: same bits as the eager
+    calls, new inputs are picked up, and a weight update re-captures."""
+    torch.manual_seed(4)
+    net = P.NewFluidNet(2, 7, 8, 1, DEV, act_fn="gelu", r_p="learned", loss_type="curl", use_symm=False, a_bound=10,
+                        repeats=2, f=5, p_pred=False).to(DEV).eval()
+    x1 = torch.randn(1, 7, 40, 48, device=DEV)
+    x2 = torch.randn(1, 7, 40, 48, device=DEV)
+    net.use_cuda_graph = False
+    e1, e2 = net(x1), net(x2)
+    net.use_cuda_graph = True
+    net(x1), net(x1)  # eager, capture + replay
+    r1, r2 = net(x1), net(x2)
+    plan = net.__dict__["_learned_plan"]
+    assert plan.graph is not None and not plan.failed
+    for a, b in ((e1, r1), (e2, r2)):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2] is None and b[2] is None
+    with torch.no_grad():
+        net.conv[2].conv.weight.mul_(1.5)
+    net.use_cuda_graph = False
+    e3 = net(x1)
+    net.use_cuda_graph = True
+    outs = [net(x1) for _ in range(3)]
+    assert net.__dict__["_learned_plan"] is not plan
+    assert not torch.equal(e3[0], e1[0])
+    for o in outs:
+        assert torch.equal(o[0], e3[0]) and torch.equal(o[1], e3[1])
+
+
 def test_no_silent_fallback_on_gpu_box():
     with pytest.raises(L.PbmcError):
         P.NewFluidNet(2, 7, 16, 2, DEV, act_fn="gelu", r_p="replicate", loss_type="curl", use_symm=True,
