@@ -247,6 +247,71 @@ def newfluidnet_forward(sd, spec: NetSpec, inp):
     return y[:, 0], y[:, 1], (y[:, 2:3] if spec.p_pred else None)
 
 
+def _curl_uv(a):
+    """Central-difference curl of a stream function with the wall BCs of :1356-1388 / :2044-2066 (a: [B,H,W])."""
+    u = np.zeros_like(a)
+    v = np.zeros_like(a)
+    u[:, 1:-1, 1:-1] = 0.5 * (a[:, 2:, 1:-1] - a[:, :-2, 1:-1])
+    v[:, 1:-1, 1:-1] = -0.5 * (a[:, 1:-1, 2:] - a[:, 1:-1, :-2])
+    for f in (u, v):
+        f[:, 0, 1:-1] = f[:, 1, 1:-1]
+        f[:, -1, 1:-1] = f[:, -2, 1:-1]
+        f[:, :, 0] = f[:, :, 1]
+        f[:, :, -1] = f[:, :, -2]
+    u[:, :, 0] = -u[:, :, 1]
+    u[:, :, -1] = -u[:, :, -2]
+    v[:, 0, :] = -v[:, 1, :]
+    v[:, -1, :] = -v[:, -2, :]
+    for f in (u, v):
+        f[:, 0, 0] = f[:, 0, -1] = f[:, -1, 0] = f[:, -1, -1] = 0.0
+    return u, v
+
+
+def unet_channels(levels, c_h):
+    """Channel bookkeeping of Unet.__init__ (pytorch_networks_convae.py:1866-1935): per-level widths of the
+    down path (level l >= 1 has c_h * 2**(l-1) channels, level 0 has c_h) and of each up block's output."""
+    down = [c_h] + [c_h * 2 ** (l - 1) for l in range(1, levels)]
+    top = down[-1]
+    up = []
+    for _ in range(levels - 2, 0, -1):
+        up.append(top // 2)
+        top //= 2
+    return down, up, top
+
+
+def unet_forward(sd, spec: NetSpec, inp):
+    """Unet.forward (pytorch_networks_convae.py:1985-2068), r_p != 'learned' (SURVEY.md section 8f N4).
+    The time-stepper variant of the surrogate: the input is padded by 3 columns each side, goes down `levels`-1
+    poolings with the width doubling from level 2 on, comes back up with skip concatenations, and the head removes
+    the per-channel mean BEFORE the 3 columns are cropped again.  Returns (u, v, p, T) like the reference."""
+    x = {0: np.pad(inp, ((0, 0), (0, 0), (0, 0), (3, 3)), mode=_PAD[spec.r_p])}  # :1990-1991
+    down, up, top = unet_channels(spec.levels, spec.c_h)
+    for r in range(spec.repeats):
+        x[0] = fluid_layer(x[0], sd, f"conv.{r}.", spec.c_h, spec)
+    sizes = {0: x[0].shape[-2:]}
+    for l in range(1, spec.levels):
+        x[l] = avg_pool2(x[l - 1])
+        sizes[l] = x[l].shape[-2:]
+        for r in range(spec.repeats):
+            x[l] = fluid_layer(x[l], sd, f"convs.{l - 1}.{r}.", down[l], spec)
+    xu = x[spec.levels - 1]
+    for l_i, l in enumerate(range(spec.levels - 2, 0, -1)):
+        xu = np.concatenate([x[l], bicubic_upsample(xu, sizes[l])], axis=1)
+        for r in range(spec.repeats):
+            xu = fluid_layer(xu, sd, f"upconvs.{l_i}.{r}.", up[l_i], spec)
+    y = np.concatenate([bicubic_upsample(xu, sizes[0]), x[0]], axis=1)
+    R = spec.repeats
+    y = conv2d_same(y, sd[f"conv.{R}.weight"], sd[f"conv.{R}.bias"], spec.r_p)
+    y = gelu(group_norm(y, sd["gn.0.weight"], sd["gn.0.bias"], int(top / 4)))
+    y = gelu(conv2d_same(y, sd[f"conv.{R + 1}.weight"], sd[f"conv.{R + 1}.bias"], spec.r_p))
+    y = conv2d_same(y, sd[f"conv.{R + 2}.weight"], sd[f"conv.{R + 2}.bias"], spec.r_p)
+    y = (y - y.mean(axis=(2, 3), keepdims=True))[..., 3:-3]  # :2025
+    if spec.loss_type in ("mae", "mass"):  # :2027-2037
+        return y[:, 0:1], y[:, 1:2], (y[:, 3:4] if spec.p_pred else None), y[:, 2:3]
+    u, v = _curl_uv(y[:, 0] * spec.a_bound)  # :2039-2066
+    return u, v, (y[:, 2] if spec.p_pred else None), np.clip(y[:, 1], 0.0, 1.5)
+
+
 # ----------------------------------------------------------------------------- TS / ADNet
 def build_input(T, xc, yc, ycc, raq, fkt, fkp):
     """TS.forward input build, pytorch_networks_convae.py:379-407.  T [B,1,H,W];

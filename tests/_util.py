@@ -34,3 +34,15 @@ def spec_from_variant(d):
 
 
 VARIANTS = ["var_zeros_nosym", "var_reflect_sym", "var_replicate_odd", "var_mae_p", "var_k5"]
+
+
+UNET_CASES = ["unet_curl_p", "unet_curl_k5", "unet_mae"]
+
+
+def load_unet_case(tag):
+    """One case of tests/golden/unet.npz: (spec, input, {name: array for u, v, p, T}, state_dict as numpy)."""
+    g = load("unet")
+    d = {k[len(tag) + 2:]: v for k, v in g.items() if k.startswith(tag + "::")}
+    spec = spec_from_variant(d)
+    outs = {n: d[n] for n in "uvpT" if n in d}
+    return spec, d["inp"], outs, split_weights(d)

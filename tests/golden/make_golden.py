@@ -8,6 +8,7 @@ reference's native precision, advect_wi_gaia.py:348,430,468), and stores inputs,
 outputs as .npz.  The GPU boxes have no /root/reference: the tests there read only the .npz.
 
     python tests/golden/make_golden.py            # regenerate everything
+    python tests/golden/make_golden.py unet       # only the U-Net vectors
 """
 from __future__ import annotations
 
@@ -275,9 +276,45 @@ def golden_ops():
     np.savez_compressed(os.path.join(HERE, "ops.npz"), **out)
 
 
+@torch.no_grad()
+def golden_unet():
+    """The U-Net time-stepper surrogate (pytorch_networks_convae.py:1700-2068), small cases
+    covering the curl head with and without p, the mae head, k=3 and k=5, three padding modes, odd sizes."""
+    cases = {
+        "unet_curl_p": (RN.NetSpec(levels=4, c_i=10, c_h=8, c_o=3, r_p="replicate", use_symm=False, repeats=2, f=3), 36, 50),
+        "unet_curl_k5": (RN.NetSpec(levels=3, c_i=10, c_h=16, c_o=2, r_p="reflect", use_symm=False, repeats=2, f=5, p_pred=False), 40, 53),
+        "unet_mae": (RN.NetSpec(levels=3, c_i=10, c_h=8, c_o=4, r_p="zeros", use_symm=False, repeats=1, f=3, loss_type="mae"), 24, 30),
+    }
+    out = {}
+    for tag, (spec, H, W) in cases.items():
+        net = make_net(spec, seed=5, cls=lambda *a, factor=2, **k: P.Unet(*a, **k))
+        g = torch.Generator().manual_seed(9)
+        inp = torch.randn(2, spec.c_i, H, W, generator=g, dtype=torch.float64)
+        u, v, p_, T = net(inp)
+        sd = sd_numpy(net)
+        res = RN.unet_forward(sd, spec, inp.numpy())
+        print(f"[{tag}] numpy-oracle vs reference: " + " ".join(
+            f"{n} {relerr(a, b.numpy()):.2e}" for n, a, b in zip("uvpT", res, (u, v, p_, T)) if b is not None))
+        out[f"{tag}::inp"] = inp.numpy()
+        for n, t in zip("uvpT", (u, v, p_, T)):
+            if t is not None:
+                out[f"{tag}::{n}"] = t.numpy()
+        out[f"{tag}::spec"] = np.array([spec.levels, spec.c_i, spec.c_h, spec.c_o, spec.repeats, spec.f, int(spec.use_symm), int(spec.p_pred)])
+        out[f"{tag}::r_p"], out[f"{tag}::loss_type"] = np.array(spec.r_p), np.array(spec.loss_type)
+        out[f"{tag}::a_bound"] = np.float64(spec.a_bound)
+        out.update({f"{tag}::w::" + k: v_ for k, v_ in sd.items()})
+    np.savez_compressed(os.path.join(HERE, "unet.npz"), **out)
+
+
+if __name__ == "__main__" and sys.argv[1:] == ["unet"]:
+    torch.set_num_threads(os.cpu_count())
+    golden_unet()
+    sys.exit(0)
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     golden_ops()
+    golden_unet()
     golden_variants()
     golden_rollout("roll128", RN.NetSpec(), 128, 128, keep=(1, 10, 100), n_steps=100)
     golden_rollout("roll64x96", RN.NetSpec(levels=4), 64, 96, keep=(1, 10), n_steps=10)

@@ -6,7 +6,7 @@ import torch
 
 from oracle import ref_numpy as RN
 from oracle import ref_torch as RT
-from tests._util import VARIANTS, load, load_weights, relerr, spec_from_variant, split_weights
+from tests._util import UNET_CASES, VARIANTS, load, load_unet_case, load_weights, relerr, spec_from_variant, split_weights
 
 
 def test_ops_adnet():
@@ -99,3 +99,13 @@ def test_unmodified_TS_128x506():
     assert np.abs(snaps[5][0, 0].numpy() - g["T5"]).max() < 1e-9
     assert relerr(u[0].numpy(), g["u5"]) < 1e-9 and relerr(p[0].numpy(), g["p5"]) < 1e-9
     assert np.abs(V[0, 0].numpy() - g["V5"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("tag", UNET_CASES)
+def test_unet_restatement_against_reference(tag):
+    """the U-Net time-stepper surrogate (reference :1985-2068), float64."""
+    spec, inp, outs, sd = load_unet_case(tag)
+    res = dict(zip("uvpT", RN.unet_forward(sd, spec, inp)))
+    assert (res["p"] is None) == ("p" not in outs)
+    for n, ref in outs.items():
+        assert res[n].shape == ref.shape and relerr(res[n], ref) < 1e-13, n
