@@ -6,7 +6,7 @@ so that `from pbml_mantle_convection_b200.pytorch_networks_convae import NewFlui
 replaces `from pytorch_networks_convae import ...`.
 """
 from .pytorch_networks_convae import (ADNet, BoundaryLearnedConvolution2D, FluidLayer, FluidNet, NewFluidNet, TS,  # noqa: F401
-                                      count_parameters)
+                                      Unet, count_parameters)
 from .symmetric_layers_torch import SymmetricConv2d  # noqa: F401
 from .scaler import scale_var, unscale_var  # noqa: F401
 from .calculate_profiles import calc_mlp_profile  # noqa: F401

@@ -334,6 +334,103 @@ def _forward_learned(net, inputs, head_bc, wall_bcs):
     return u.to(inputs.dtype), v.to(inputs.dtype), (p.to(inputs.dtype) if p is not None else None)
 
 
+class Unet(nn.Module):
+    """U-Net variant of the surrogate used as a time stepper: (x, y, dt, parameters, viscosity, T, u_prev, v_prev) ->
+    (u, v, p, T_next) (reference :1700-2068).  Same constructor, module tree and `state_dict`
+    keys/shapes as the reference.  `forward` runs on the module-level kernels (FluidLayer = conv + GroupNorm + GELU
+    through libpbmc, incremental 2x2 pooling, bicubic up-sampling, curl head); it is not yet one fused DAG like
+    NewFluidNet's, and the learned-boundary variant (which enlarges the input through `bc_x=4`) is not built."""
+
+    def __init__(self, levels: int, c_i: int, c_h: int, c_o: int, device=torch.device("cpu"), act_fn: str = "gelu",
+                 r_p="replicate", loss_type="curl", use_symm=False, dilation=1, a_bound=10.0, use_cosine=False, repeats=2,
+                 use_skip=False, f=5, p_pred=False, spectral_conv=False, blurr=False, drop_rate=0.0):
+        super().__init__()
+        if spectral_conv:
+            raise NotImplementedError("spectral_conv=True is outside the rollout path (advect_wi_gaia.py:253)")
+        if blurr:
+            raise NotImplementedError("blurr=True is outside the rollout path (advect_wi_gaia.py:255)")
+        self.conv, self.gn = nn.ModuleList(), nn.ModuleList()
+        self.levels, self.loss_type, self.a_bound = levels, loss_type, a_bound
+        self.use_cosine, self.repeats, self.use_skip, self.p_pred = use_cosine, repeats, use_skip, p_pred
+        self.c_i, self.c_o, self.f = c_i, c_o, f
+        self.blurrer = None
+        self.r_p = "constant" if r_p == "zeros" else r_p
+        self.act = _make_act(act_fn)
+        layer = lambda ci, co: FluidLayer(ci, co, act_fn, r_p, use_symm, dilation, f=f, drop_rate=drop_rate)
+        for r in range(repeats):
+            self.conv.append(layer(c_i if r == 0 else c_h, c_h))
+        self.pool = nn.AvgPool2d((2, 2), stride=2)
+        # down path: level 1 keeps c_h channels, every further level doubles them (:1866-1895)
+        self.convs = nn.ModuleList()
+        w = c_h
+        for l in range(1, levels):
+            self.convs.append(nn.ModuleList([layer(w // 2 if (r == 0 and l > 1) else w, w) for r in range(repeats)]))
+            w *= 2
+        w //= 2
+        # up path: concat(skip of w/2 channels, up-sampled w channels) -> w/2 (:1897-1935)
+        self.upconvs = nn.ModuleList()
+        for _l in range(levels - 2, 0, -1):
+            self.upconvs.append(nn.ModuleList([layer(w + w // 2 if r == 0 else w // 2, w // 2) for r in range(repeats)]))
+            w //= 2
+        self.c_head = w
+        for ci, co in ((2 * w, w), (w, w), (w, c_o)):
+            if self.r_p != "learned":
+                self.conv.append(nn.Conv2d(ci, co, kernel_size=f, padding="same", dilation=dilation if ci == 2 * w else 1,
+                                           padding_mode=r_p, stride=1))
+            else:
+                self.conv.append(BoundaryLearnedConvolution2D(ci, co, k=f, use_symm=use_symm))
+            if ci == 2 * w:
+                self.gn.append(torch.nn.GroupNorm(int(w / 4), w))
+
+    def forward(self, inputs):
+        _require_gelu(self)
+        if not inputs.is_cuda:
+            raise L.PbmcError("Unet runs on CUDA only: there is no CPU implementation of this path")
+        if inputs.dim() != 4 or inputs.shape[1] != self.c_i:
+            raise ValueError(f"expected inputs [B,{self.c_i},H,W], got {tuple(inputs.shape)}")
+        if self.r_p == "learned":
+            raise NotImplementedError("the learned-boundary U-Net (bc_x=4 enlargement, :1996) is not built")
+        dev, dtype, R = inputs.device, inputs.dtype, self.repeats
+        blocked = lambda t: ops.Source(ops.pack_nchw(t))
+        pool = lambda t: ops.unpack_nchw(ops.avgpool2(blocked(t)), t.shape[1])
+        up = lambda t, size: ops.unpack_nchw(ops.bicubic_up(blocked(t), int(size[0]), int(size[1])), t.shape[1])
+        x = [torch.nn.functional.pad(inputs.float(), (3, 3, 0, 0), mode=self.r_p)]  # :1990-1991
+        for r in range(R):
+            x[0] = self.conv[r](x[0])
+        for l in range(1, self.levels):
+            t = pool(x[l - 1])
+            for r in range(R):
+                t = self.convs[l - 1][r](t)
+            x.append(t)
+        xu = x[-1]
+        for l_i, l in enumerate(range(self.levels - 2, 0, -1)):
+            xu = torch.cat((x[l], up(xu, x[l].shape[-2:])), 1)
+            for r in range(R):
+                xu = self.upconvs[l_i][r](xu)
+        y = torch.cat((up(xu, x[0].shape[-2:]), x[0]), 1)
+        c = self.c_head
+        yb = ops.pack_nchw(conv_module_forward(self.conv[R], y))
+        y = ops.finalize_nchw(ops.Source(yb, L.XFORM_GN_GELU, _stats_of_blocked(yb, c), ops.pad_vec(self.gn[0].weight, c, dev, 1.0),
+                                         ops.pad_vec(self.gn[0].bias, c, dev)), c)
+        y = ops.finalize_nchw(ops.Source(ops.pack_nchw(conv_module_forward(self.conv[R + 1], y)), L.XFORM_GELU), c)
+        y = conv_module_forward(self.conv[R + 2], y)
+        y = (y - y.mean(dim=(2, 3), keepdim=True))[..., 3:-3].contiguous()  # mean over the PADDED width, then crop (:2025)
+        if self.loss_type in ("mae", "mass"):
+            p = y[:, 3:4].to(dtype) if self.p_pred else None
+            return y[:, 0:1].to(dtype), y[:, 1:2].to(dtype), p, y[:, 2:3].to(dtype)
+        if self.loss_type != "curl":
+            raise ValueError(self.loss_type)
+        if self.c_o > 4:
+            raise NotImplementedError("the curl head reads one 4-channel block (a, T, p)")
+        # curl + wall BCs in the head kernel (channel 0 = stream function); with zero channel sums its "p" output is
+        # channel 1 unchanged, which here is the temperature (:2041)
+        yb = ops.pack_nchw(y)
+        zero_sums = torch.zeros(y.shape[0], 4, dtype=torch.float64, device=dev)
+        u, v, T, _ = ops.head(yb, zero_sums, None, self.a_bound, L.HEAD_CURL, True, want_uvmax=False)
+        p = y[:, 2].to(dtype) if self.p_pred else None
+        return u.to(dtype), v.to(dtype), p, torch.clip(T, 0.0, 1.5).to(dtype)
+
+
 class ADNet(nn.Module):
     """Explicit upwind-advection / central-diffusion update with the CFL time step
     (reference :478-568).  `forward(inputs[B,6,H,W], dt=None, T_prev=None) -> (T[B,1,H,W], dt)`;
@@ -478,10 +575,44 @@ class TS(nn.Module):
         return x, dts, f_all[0], f_all[1], p, f_all[2]
 
     @torch.no_grad()
+    def _forward_unet(self, T_prev, ycc, raq_nd, fkt_nd, fkp_nd, raq, fkt, fkp, xc, yc, u_prev, v_prev, dt):
+        """U-Net time stepper (reference :419-451): the network predicts T directly; u_prev, v_prev and dt are inputs and
+        stay what the caller passed for all `ts` steps; no advection kernel, no dt out; u, v are returned as predicted
+        (the caller un-scales them, advect_wi_gaia.py:751-767).  Any grid size (the reference views to 128x506)."""
+        if u_prev is None or v_prev is None or dt is None:
+            raise ValueError("net='unet' needs u_prev, v_prev and dt")
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise L.PbmcError("TS runs on CUDA only: there is no CPU implementation of this path")
+        dtype = T_prev.dtype
+        H, W = T_prev.shape[-2:]
+        grid = self._get_grid(xc, yc, ycc, dev)
+        f32 = lambda t: torch.as_tensor(t).to(dev, torch.float32).reshape(1, 1, H, W)
+        members = ops.make_members([(float(raq), float(fkt), float(fkp))], dev,
+                                   nd_override=[(float(raq_nd), float(fkt_nd), float(fkp_nd))])
+        up, vp, dtf = f32(u_prev), f32(v_prev), f32(dt)
+        x, u, v, V = {0: T_prev.to(dev)}, None, None, None
+        Tc = x[0].reshape(1, H, W).float().contiguous()
+        for i in range(1, self.ts + 1):
+            # channels of the shared input builder: x/4, y/4, log10(clip V)/8, raq_nd, fkt_nd, fkp_nd, T
+            c7 = ops.unpack_nchw(ops.build_input(Tc, grid.xc, grid.yc, grid.ycc, members)[0], 7)
+            V = c7[:, 2:3]
+            inp = torch.cat((c7[:, 0:2], dtf, c7[:, 3:6], V, c7[:, 6:7], up, vp), 1)
+            u, v, _, T = self.stokes(inp)
+            Tn = T.reshape(1, 1, H, W).float().clone()
+            Tn[:, :, 0, :] = 1
+            Tn[:, :, -1, :] = 0
+            Tn[:, :, :, 0:1] = Tn[:, :, :, 1:2]
+            Tn[:, :, :, -1:] = Tn[:, :, :, -2:-1]
+            x[i] = Tn.to(dtype)
+            Tc = Tn.reshape(1, H, W).contiguous()
+        return x, {}, u.reshape(1, 1, H, W).to(dtype), v.reshape(1, 1, H, W).to(dtype), None, V.to(dtype)
+
+    @torch.no_grad()
     def forward(self, T_prev, sdf, sdf2, ycc, raq_nd, fkt_nd, fkp_nd, raq, fkt, fkp, xc, yc, u_prev=None, v_prev=None,
                 dt=None):
         if self.net == "unet":
-            raise NotImplementedError("net='unet' (SURVEY.md section 8f N4) is outside the accelerated path")
+            return self._forward_unet(T_prev, ycc, raq_nd, fkt_nd, fkp_nd, raq, fkt, fkp, xc, yc, u_prev, v_prev, dt)
         if self.net not in ("newfluidnet", "fluidnet"):
             raise ValueError(self.net)
         dev = torch.device(self.device)

@@ -1,0 +1,59 @@
+"""Host logic of the module-level forwards, checked WITHOUT a GPU: the device ops are replaced by CPU stand-ins
+(tests/_emulated_ops.py: float64 NCHW tensors play the blocked layout, ATen/numpy play the kernels), so what is tested
+is the Python side -- channel bookkeeping, sizes, crops, region stitching, head mapping, filter caches -- against the
+vectors produced by the real reference.  The kernels themselves are tested on the GPU (tests/test_gpu_*.py)."""
+import numpy as np
+import pytest
+import torch
+
+import pbml_mantle_convection_b200 as P
+from oracle import ref_numpy as RN
+from pbml_mantle_convection_b200 import ops
+from tests import _emulated_ops as emu
+from tests._util import UNET_CASES, load, load_unet_case, relerr, split_weights
+
+
+@pytest.mark.parametrize("tag", UNET_CASES)
+def test_unet_forward_host_logic(monkeypatch, tag):
+    emu.install(monkeypatch)
+    spec, inp, outs, w = load_unet_case(tag)
+    net = P.Unet(spec.levels, spec.c_i, spec.c_h, spec.c_o, "cpu", act_fn="gelu", r_p=spec.r_p, loss_type=spec.loss_type,
+                 use_symm=False, a_bound=spec.a_bound, repeats=spec.repeats, f=spec.f, p_pred=spec.p_pred).double().eval()
+    net.load_state_dict({k: torch.tensor(v) for k, v in w.items()})
+    res = dict(zip("uvpT", net(torch.tensor(inp))))
+    assert (res["p"] is None) == ("p" not in outs)
+    for n, ref in outs.items():
+        assert tuple(res[n].shape) == ref.shape and res[n].dtype == torch.float64
+        assert relerr(res[n].numpy(), ref) < 1e-6, n  # the forward converts its input to float32 once
+
+
+@pytest.mark.parametrize("tag,k,co,symm", [("blc3", 3, 8, False), ("blc5", 5, 8, False), ("blc3s", 3, 16, True)])
+def test_learned_boundary_conv_host_logic(monkeypatch, tag, k, co, symm):
+    """Nine regions, the reference's row swap (:1060), bc_x = bc_y = 2 enlargement, and which kernel each region goes to."""
+    emu.install(monkeypatch)
+    calls = []
+    inner = ops.conv_fwd
+    monkeypatch.setattr(ops, "conv_fwd", lambda srcs, *a, impl="auto", wpk_row=None, **kw: (
+        calls.append((impl, wpk_row is not None, tuple(srcs[0].t.shape[-2:]))), inner(srcs, *a, impl=impl, wpk_row=wpk_row, **kw))[1])
+    g = load("ops")
+    ci = g[tag + "_x"].shape[1]
+    m = P.BoundaryLearnedConvolution2D(ci, co, k, use_symm=symm).double()
+    m.load_state_dict({kk: torch.tensor(v) for kk, v in split_weights(g, tag + "_w::").items()})
+    y = m(torch.tensor(g[tag + "_x"]))
+    assert tuple(y.shape) == g[tag + "_y"].shape and relerr(y.numpy(), g[tag + "_y"]) < 1e-13
+    assert all(impl == "ffma" and not row for impl, row, _ in calls)  # 20 x 28: below the tensor-core threshold
+    if tag == "blc3":
+        y2 = m(torch.tensor(g[tag + "_x"]), bc_x=2, bc_y=2)
+        assert tuple(y2.shape) == g["blc3_y_bc2"].shape and relerr(y2.numpy(), g["blc3_y_bc2"]) < 1e-13
+    # a grid-sized input: interior region on the tensor-core kernels (row image packed), strips on the FFMA kernel
+    calls.clear()
+    x = torch.randn(1, ci, 40, 48, dtype=torch.float64)
+    sd = {kk: t.detach().numpy() for kk, t in m.state_dict().items()}
+    assert relerr(m(x).numpy(), RN.boundary_learned_conv(x.numpy(), sd, "", k, co, use_symm=symm)) < 1e-13
+    big = [(impl, row) for impl, row, hw in calls if min(hw) >= 32]
+    assert big == [("auto", True)] and all(impl == "ffma" for impl, row, hw in calls if min(hw) < 32)
+    # cached filter images follow in-place updates
+    with torch.no_grad():
+        m.conv.weight.mul_(0.5)
+    sd = {kk: t.detach().numpy() for kk, t in m.state_dict().items()}
+    assert relerr(m(x).numpy(), RN.boundary_learned_conv(x.numpy(), sd, "", k, co, use_symm=symm)) < 1e-13

@@ -11,7 +11,7 @@ import pbml_mantle_convection_b200 as P
 from pbml_mantle_convection_b200 import _lib as L
 from pbml_mantle_convection_b200 import calculate_profiles as CP
 from pbml_mantle_convection_b200 import ops, scaler
-from tests._util import GOLDEN, VARIANTS, load, load_weights, spec_from_variant, split_weights
+from tests._util import GOLDEN, UNET_CASES, VARIANTS, load, load_unet_case, load_weights, spec_from_variant, split_weights
 
 
 def make(spec, cls=P.NewFluidNet):
@@ -160,3 +160,25 @@ def test_synthetic_inputs_match_oracle():
         xb, yb = RN.synthetic_grid(H, W)
         assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
         assert np.array_equal(P.synthetic_T0(H, W, seed=3), RN.synthetic_T0(H, W, seed=3))
+
+
+@pytest.mark.parametrize("tag", UNET_CASES)
+def test_unet_state_dict_layout_and_signature(tag):
+    """the U-Net drop-in has the reference's module tree (keys, order, shapes), loads its
+    weights, keeps its constructor signature (reference :1765-1786) and refuses CPU tensors."""
+    spec, inp, _outs, w = load_unet_case(tag)
+    net = P.Unet(spec.levels, spec.c_i, spec.c_h, spec.c_o, "cpu", act_fn="gelu", r_p=spec.r_p, loss_type=spec.loss_type,
+                 use_symm=False, a_bound=spec.a_bound, repeats=spec.repeats, f=spec.f, p_pred=spec.p_pred).double()
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(w.keys())
+    for k, v in w.items():
+        assert tuple(sd[k].shape) == v.shape, k
+    net.load_state_dict({k: torch.tensor(v) for k, v in w.items()})
+    names = list(inspect.signature(P.Unet.__init__).parameters)[1:]
+    assert names == ["levels", "c_i", "c_h", "c_o", "device", "act_fn", "r_p", "loss_type", "use_symm", "dilation", "a_bound",
+                     "use_cosine", "repeats", "use_skip", "f", "p_pred", "spectral_conv", "blurr", "drop_rate"]
+    d = inspect.signature(P.Unet.__init__).parameters
+    assert (d["act_fn"].default, d["r_p"].default, d["loss_type"].default, d["a_bound"].default, d["repeats"].default,
+            d["f"].default, d["p_pred"].default) == ("gelu", "replicate", "curl", 10.0, 2, 5, False)
+    with pytest.raises(L.PbmcError):
+        net(torch.tensor(inp))
