@@ -444,3 +444,42 @@ def boundary_learned_conv(x, sd, prefix, k, c_out, use_symm=False, bc_x=1, bc_y=
     bottom = np.concatenate([bl, bottom, br], axis=3)
     out = np.concatenate([bottom, mid, top], axis=2)
     return out + sd[prefix + "learnable_bias"]
+
+
+def learned_net_forward(sd, spec: NetSpec, inp, fluidnet=False):
+    """NewFluidNet.forward (pytorch_networks_convae.py:1315-1388) / FluidNet.forward (:1639-1697) with r_p='learned'
+    (SURVEY.md section 8f N1): every conv is the 9-region conv above.  NewFluidNet ends in the wall-BC curl head;
+    FluidNet enlarges the head conv's output by one ring (bc_x = bc_y = 2, :1659-1660) and returns the plain central
+    differences of the stream function, cropped back to the input size, without wall BCs (:1694-1697)."""
+    H, W = inp.shape[-2:]
+    C, k, sym = spec.c_h, spec.f, spec.use_symm
+
+    def layer(x, prefix, c_out):  # FluidLayer with the learned conv (:790-799)
+        y = boundary_learned_conv(x, sd, prefix + "layers.0.", k, c_out, use_symm=sym)
+        return gelu(group_norm(y, sd[prefix + "layers.1.weight"], sd[prefix + "layers.1.bias"], int(c_out / min(4, c_out))))
+
+    x_in = layer(inp, "conv.0.", C)
+    feats = []
+    for l in range(spec.levels):
+        y1 = x_in
+        for _ in range(l):
+            y1 = avg_pool2(y1)
+        for r in range(spec.repeats):
+            y1 = layer(y1, f"convs.{l}.{r}.", C)
+        feats.append(bicubic_upsample(y1, (H, W)) if l > 0 else y1)
+    y = np.concatenate(feats + [inp], axis=1)
+    bc = 2 if fluidnet else 1
+    y = boundary_learned_conv(y, sd, "conv.1.", k, C, use_symm=sym, bc_x=bc, bc_y=bc)
+    y = gelu(group_norm(y, sd["gn.0.weight"], sd["gn.0.bias"], int(C / 4)))
+    y = gelu(boundary_learned_conv(y, sd, "conv.2.", k, C, use_symm=sym))
+    y = boundary_learned_conv(y, sd, "conv.3.", k, spec.c_o, use_symm=sym)
+    if not fluidnet:
+        if spec.loss_type == "curl":
+            return curl_head(y, spec)
+        y = y - y.mean(axis=(2, 3), keepdims=True)
+        return y[:, 0], y[:, 1], (y[:, 2:3] if spec.p_pred else None)
+    y = y - y.mean(axis=(2, 3), keepdims=True)
+    a = y[:, 0] * spec.a_bound
+    u = 0.5 * (a[:, 2:, 1:-1] - a[:, :-2, 1:-1])
+    v = -0.5 * (a[:, 1:-1, 2:] - a[:, 1:-1, :-2])
+    return u, v, (y[:, 1] if spec.p_pred else None)

@@ -39,9 +39,17 @@ VARIANTS = ["var_zeros_nosym", "var_reflect_sym", "var_replicate_odd", "var_mae_
 UNET_CASES = ["unet_curl_p", "unet_curl_k5", "unet_mae"]
 
 
-def load_unet_case(tag):
-    """One case of tests/golden/unet.npz: (spec, input, {name: array for u, v, p, T}, state_dict as numpy)."""
-    g = load("unet")
+LEARNED_CASES = ["learned_k5", "learned_k3_p", "learned_fluidnet"]
+
+
+def load_learned_case(tag):
+    """One case of tests/golden/learned.npz (whole learned-boundary networks): like load_unet_case."""
+    return load_unet_case(tag, "learned")
+
+
+def load_unet_case(tag, file="unet"):
+    """One case of tests/golden/<file>.npz: (spec, input, {name: array for u, v, p, T}, state_dict as numpy)."""
+    g = load(file)
     d = {k[len(tag) + 2:]: v for k, v in g.items() if k.startswith(tag + "::")}
     spec = spec_from_variant(d)
     outs = {n: d[n] for n in "uvpT" if n in d}

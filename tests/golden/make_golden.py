@@ -9,6 +9,7 @@ outputs as .npz.  The GPU boxes have no /root/reference: the tests there read on
 
     python tests/golden/make_golden.py            # regenerate everything
     python tests/golden/make_golden.py unet       # only the U-Net vectors
+    python tests/golden/make_golden.py learned    # only the whole learned-boundary networks
 """
 from __future__ import annotations
 
@@ -306,6 +307,42 @@ def golden_unet():
     np.savez_compressed(os.path.join(HERE, "unet.npz"), **out)
 
 
+@torch.no_grad()
+def golden_learned():
+    """Whole learned-boundary networks: NewFluidNet with the 9-region convs (k=5 and k=3) and
+    FluidNet (head conv enlarged by bc_x = bc_y = 2, raw curl)."""
+    cases = {
+        "learned_k5": (P.NewFluidNet, RN.NetSpec(levels=3, c_h=8, c_o=1, r_p="learned", use_symm=False, repeats=2, f=5, p_pred=False), 40, 56),
+        "learned_k3_p": (P.NewFluidNet, RN.NetSpec(levels=2, c_h=16, c_o=2, r_p="learned", use_symm=False, repeats=1, f=3), 36, 44),
+        "learned_fluidnet": (P.FluidNet, RN.NetSpec(levels=2, c_h=8, c_o=2, r_p="learned", use_symm=False, repeats=2, f=3), 36, 44),
+    }
+    out = {}
+    for tag, (cls, spec, H, W) in cases.items():
+        net = make_net(spec, seed=6, cls=cls)
+        set_grid(net, H, W)
+        g = torch.Generator().manual_seed(10)
+        inp = torch.randn(2, spec.c_i, H, W, generator=g, dtype=torch.float64)
+        u, v, p_ = net(inp)
+        sd = sd_numpy(net)
+        res = RN.learned_net_forward(sd, spec, inp.numpy(), fluidnet=cls is P.FluidNet)
+        print(f"[{tag}] numpy-oracle vs reference: " + " ".join(
+            f"{n} {relerr(a, b.numpy()):.2e}" for n, a, b in zip("uvp", res, (u, v, p_)) if b is not None))
+        out[f"{tag}::inp"] = inp.numpy()
+        for n, t in zip("uvp", (u, v, p_)):
+            if t is not None:
+                out[f"{tag}::{n}"] = t.numpy()
+        out[f"{tag}::spec"] = np.array([spec.levels, spec.c_i, spec.c_h, spec.c_o, spec.repeats, spec.f, int(spec.use_symm), int(spec.p_pred)])
+        out[f"{tag}::r_p"], out[f"{tag}::loss_type"] = np.array(spec.r_p), np.array(spec.loss_type)
+        out[f"{tag}::a_bound"] = np.float64(spec.a_bound)
+        out.update({f"{tag}::w::" + k: v_ for k, v_ in sd.items()})
+    np.savez_compressed(os.path.join(HERE, "learned.npz"), **out)
+
+
+if __name__ == "__main__" and sys.argv[1:] == ["learned"]:
+    torch.set_num_threads(os.cpu_count())
+    golden_learned()
+    sys.exit(0)
+
 if __name__ == "__main__" and sys.argv[1:] == ["unet"]:
     torch.set_num_threads(os.cpu_count())
     golden_unet()
@@ -315,6 +352,7 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     golden_ops()
     golden_unet()
+    golden_learned()
     golden_variants()
     golden_rollout("roll128", RN.NetSpec(), 128, 128, keep=(1, 10, 100), n_steps=100)
     golden_rollout("roll64x96", RN.NetSpec(levels=4), 64, 96, keep=(1, 10), n_steps=10)

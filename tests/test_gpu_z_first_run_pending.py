@@ -1,14 +1,15 @@
-"""SURVEY.md section 8f N4 on the GPU: the U-Net drop-in against the vectors of the real reference, and the `net="unet"`
-branch of TS.  Written after this round's GPU budget was spent: the host logic is covered on the CPU
-(tests/test_host_logic_cpu.py), the kernels it calls by tests/test_gpu_ops.py, but this file has NOT yet run on hardware --
-hence the non-strict xfail, to be removed on its first green run."""
+"""GPU tests written after this round's GPU budget was spent: whole learned-boundary
+networks and the U-Net drop-in against the vectors of the real reference, and the `net="unet"` branch of TS.  Their host
+logic is covered on the CPU against the same vectors (tests/test_host_logic_cpu.py) and the kernels they call by
+tests/test_gpu_ops.py / test_gpu_net.py, but this file has NOT yet run on hardware -- hence the non-strict xfail, to be
+removed on its first green run, and the file name that sorts it after the proven GPU tests."""
 import numpy as np
 import pytest
 import torch
 
 import pbml_mantle_convection_b200 as P
 from oracle import ref_numpy as RN
-from tests._util import UNET_CASES, load_unet_case, relerr
+from tests._util import LEARNED_CASES, UNET_CASES, load_learned_case, load_unet_case, relerr
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="not yet run on hardware (written after the round's GPU budget was spent)")]
@@ -64,3 +65,22 @@ def test_TS_unet_branch():
     T1 = RN.apply_T_bcs(T1[:, None].copy()) if T1.ndim == 3 else T1
     assert np.abs(x[1].cpu().numpy() - T1.reshape(1, 1, H, W)).max() < 5e-5
     assert tuple(u.shape) == (1, 1, H, W) and tuple(V.shape) == (1, 1, H, W)
+
+
+@pytest.mark.parametrize("tag", LEARNED_CASES)
+def test_learned_network_against_reference_golden(tag):
+    """N1 at network level (until now: runs, finite, first layer == oracle): eager call, then the replayed graph."""
+    spec, inp, outs, w = load_learned_case(tag)
+    cls = P.FluidNet if tag == "learned_fluidnet" else P.NewFluidNet
+    net = cls(spec.levels, spec.c_i, spec.c_h, spec.c_o, DEV, act_fn="gelu", r_p="learned", loss_type="curl", use_symm=False,
+              a_bound=spec.a_bound, repeats=spec.repeats, f=spec.f, p_pred=spec.p_pred).double()
+    net.load_state_dict({k: torch.tensor(v) for k, v in w.items()})
+    net = net.to(DEV).eval()
+    x = torch.tensor(inp, device=DEV)
+    for call in range(3):  # eager, capture + replay, replay
+        res = dict(zip("uvp", net(x)))
+        assert (res["p"] is None) == ("p" not in outs)
+        for n, ref in outs.items():
+            assert tuple(res[n].shape) == ref.shape
+            tol = 3e-4 if n in "uv" else 3e-5
+            assert relerr(res[n].cpu().numpy(), ref) < tol, (call, n, relerr(res[n].cpu().numpy(), ref))

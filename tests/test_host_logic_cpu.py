@@ -10,7 +10,7 @@ import pbml_mantle_convection_b200 as P
 from oracle import ref_numpy as RN
 from pbml_mantle_convection_b200 import ops
 from tests import _emulated_ops as emu
-from tests._util import UNET_CASES, load, load_unet_case, relerr, split_weights
+from tests._util import LEARNED_CASES, UNET_CASES, load, load_learned_case, load_unet_case, relerr, split_weights
 
 
 @pytest.mark.parametrize("tag", UNET_CASES)
@@ -57,3 +57,20 @@ def test_learned_boundary_conv_host_logic(monkeypatch, tag, k, co, symm):
         m.conv.weight.mul_(0.5)
     sd = {kk: t.detach().numpy() for kk, t in m.state_dict().items()}
     assert relerr(m(x).numpy(), RN.boundary_learned_conv(x.numpy(), sd, "", k, co, use_symm=symm)) < 1e-13
+
+
+@pytest.mark.parametrize("tag", LEARNED_CASES)
+def test_learned_network_host_logic(monkeypatch, tag):
+    """Whole learned-boundary networks through the module-level forward (pyramid, concat order, head enlargement of
+    FluidNet, curl heads) against the reference's outputs."""
+    emu.install(monkeypatch)
+    spec, inp, outs, w = load_learned_case(tag)
+    cls = P.FluidNet if tag == "learned_fluidnet" else P.NewFluidNet
+    net = cls(spec.levels, spec.c_i, spec.c_h, spec.c_o, "cpu", act_fn="gelu", r_p="learned", loss_type="curl", use_symm=False,
+              a_bound=spec.a_bound, repeats=spec.repeats, f=spec.f, p_pred=spec.p_pred).double().eval()
+    net.load_state_dict({k: torch.tensor(v) for k, v in w.items()})
+    net.use_cuda_graph = False
+    res = dict(zip("uvp", net(torch.tensor(inp))))
+    assert (res["p"] is None) == ("p" not in outs)
+    for n, ref in outs.items():
+        assert tuple(res[n].shape) == ref.shape and relerr(res[n].numpy(), ref) < 1e-6, n

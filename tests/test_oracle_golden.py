@@ -6,7 +6,7 @@ import torch
 
 from oracle import ref_numpy as RN
 from oracle import ref_torch as RT
-from tests._util import UNET_CASES, VARIANTS, load, load_unet_case, load_weights, relerr, spec_from_variant, split_weights
+from tests._util import LEARNED_CASES, UNET_CASES, VARIANTS, load, load_learned_case, load_unet_case, load_weights, relerr, spec_from_variant, split_weights
 
 
 def test_ops_adnet():
@@ -106,6 +106,16 @@ def test_unet_restatement_against_reference(tag):
     """the U-Net time-stepper surrogate (reference :1985-2068), float64."""
     spec, inp, outs, sd = load_unet_case(tag)
     res = dict(zip("uvpT", RN.unet_forward(sd, spec, inp)))
+    assert (res["p"] is None) == ("p" not in outs)
+    for n, ref in outs.items():
+        assert res[n].shape == ref.shape and relerr(res[n], ref) < 1e-13, n
+
+
+@pytest.mark.parametrize("tag", LEARNED_CASES)
+def test_learned_network_restatement_against_reference(tag):
+    """whole learned-boundary networks (NewFluidNet :1315-1388, FluidNet :1639-1697), float64."""
+    spec, inp, outs, sd = load_learned_case(tag)
+    res = dict(zip("uvp", RN.learned_net_forward(sd, spec, inp, fluidnet=tag == "learned_fluidnet")))
     assert (res["p"] is None) == ("p" not in outs)
     for n, ref in outs.items():
         assert res[n].shape == ref.shape and relerr(res[n], ref) < 1e-13, n
