@@ -587,7 +587,10 @@ class TS(nn.Module):
         dtype = T_prev.dtype
         H, W = T_prev.shape[-2:]
         grid = self._get_grid(xc, yc, ycc, dev)
-        f32 = lambda t: torch.as_tensor(t).to(dev, torch.float32).reshape(1, 1, H, W)
+        def f32(t):  # [1,1,H,W] fields as the reference concatenates them (:419-441); a scalar dt is broadcast
+            t = torch.as_tensor(t).to(dev, torch.float32)
+            return t.expand(1, 1, H, W) if t.numel() == 1 else t.reshape(1, 1, H, W)
+
         members = ops.make_members([(float(raq), float(fkt), float(fkp))], dev,
                                    nd_override=[(float(raq_nd), float(fkt_nd), float(fkp_nd))])
         up, vp, dtf = f32(u_prev), f32(v_prev), f32(dt)
