@@ -66,7 +66,7 @@ def _packed_filters(m: nn.Conv2d, dev, want_row: bool):
 
 def conv_module_forward(m: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     """Stand-alone forward of an nn.Conv2d-shaped module on an NCHW tensor through libpbmc.
-    Images of at least TENSOR_CORE_MIN_SIDE rows and columns with c_out <= 16 go to the tensor-core kernels (fp16 hi+lo, fp32-grade; the library
+    Images of at least TENSOR_CORE_MIN_SIDE rows and columns with c_in, c_out <= 16 go to the tensor-core kernels (fp16 hi+lo, fp32-grade; the library
     picks the time-multiplexed or the row-streaming one), thin strips (the edge regions of the learned-boundary conv,
     reference :1022-1065) and wide outputs to the FFMA kernel."""
     _check_conv_supported(m)
@@ -78,7 +78,9 @@ def conv_module_forward(m: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
         pad = (0, 0)
     elif pad == "same":
         pad = (k // 2, k // 2)
-    tensor_core = m.out_channels <= 16 and min(x.shape[-2:]) >= TENSOR_CORE_MIN_SIDE
+    # (single-group inputs only: the shapes this entry point has been verified with on hardware -- 16->16 and 16->1 at
+    # k=5, 7->16 at k=3; wider inputs stay on the FFMA kernel here, the fused network path feeds conv[1] itself)
+    tensor_core = m.out_channels <= 16 and m.in_channels <= 16 and min(x.shape[-2:]) >= TENSOR_CORE_MIN_SIDE
     wpk, wrow, bias = _packed_filters(m, x.device, tensor_core)
     xb = ops.pack_nchw(x)
     mode = m.padding_mode if pad != (0, 0) else "zeros"
