@@ -43,6 +43,11 @@ def _sym_counts(c_o):
     return {"h": int(c_o / 4) if c_o > 4 else int(c_o / 2), "v": 0, "hv": 0}
 
 
+def _require_cuda_device(dev):
+    if dev.type != "cuda":
+        raise L.PbmcError("TS runs on CUDA only: there is no CPU implementation of this path")
+
+
 def _require_gelu(mod):
     if not isinstance(mod.act, nn.GELU):
         raise NotImplementedError("the B200 path fuses exact-erf GELU (act_fn='gelu', advect_wi_gaia.py:247); "
@@ -582,8 +587,7 @@ class TS(nn.Module):
         if u_prev is None or v_prev is None or dt is None:
             raise ValueError("net='unet' needs u_prev, v_prev and dt")
         dev = torch.device(self.device)
-        if dev.type != "cuda":
-            raise L.PbmcError("TS runs on CUDA only: there is no CPU implementation of this path")
+        _require_cuda_device(dev)
         dtype = T_prev.dtype
         H, W = T_prev.shape[-2:]
         grid = self._get_grid(xc, yc, ycc, dev)
@@ -619,8 +623,7 @@ class TS(nn.Module):
         if self.net not in ("newfluidnet", "fluidnet"):
             raise ValueError(self.net)
         dev = torch.device(self.device)
-        if dev.type != "cuda":
-            raise L.PbmcError("TS runs on CUDA only: there is no CPU implementation of this path")
+        _require_cuda_device(dev)
         stokes = self.stokes
         dtype = T_prev.dtype
         B = T_prev.shape[0] if T_prev.dim() == 4 else 1

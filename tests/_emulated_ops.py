@@ -61,3 +61,19 @@ def install(mp):
     from pbml_mantle_convection_b200 import pytorch_networks_convae as M
 
     mp.setattr(M, "_stats_of_blocked", lambda yb, c: None)
+    mp.setattr(M, "_require_cuda_device", lambda dev: None)
+    mp.setattr(ops, "stencil_coefs", lambda coord64, lo, hi: torch.zeros(3, coord64.numel()))
+
+    def build_input(T, xc, yc, ycc, members, want_V=False):
+        # pbmc_member: raq_nd, fkt_nd, fkp_nd, ln fkt, ln fkp, raq, scaler, 0 (ops.member_values)
+        m = members.double()
+        T4 = T.double()[:, None]
+        V = torch.clip(torch.exp(m[:, 3].view(-1, 1, 1, 1) * (0.0 - T4) + m[:, 4].view(-1, 1, 1, 1) * (1.0 - ycc.double())[None, None]),
+                       1e-8, 1.0)
+        one = torch.ones_like(T4)
+        inp = torch.cat([(xc.double() / 4.0)[None, None].expand_as(T4), (yc.double() / 4.0)[None, None].expand_as(T4),
+                         torch.log10(V) / 8, one * m[:, 0].view(-1, 1, 1, 1), one * m[:, 1].view(-1, 1, 1, 1),
+                         one * m[:, 2].view(-1, 1, 1, 1), T4], 1)
+        return inp, (V[:, 0] if want_V else None)
+
+    mp.setattr(ops, "build_input", build_input)

@@ -74,3 +74,42 @@ def test_learned_network_host_logic(monkeypatch, tag):
     assert (res["p"] is None) == ("p" not in outs)
     for n, ref in outs.items():
         assert tuple(res[n].shape) == ref.shape and relerr(res[n].numpy(), ref) < 1e-6, n
+
+
+def test_TS_unet_branch_host_logic(monkeypatch):
+    """`TS(net="unet")` (reference :419-451): channel order of the 10-channel input, u_prev / v_prev / dt passed through,
+    wall BCs on the predicted T, empty dts, p None -- against the oracle's U-Net applied to the oracle's input build."""
+    emu.install(monkeypatch)
+    spec, _inp, _outs, w = load_unet_case("unet_curl_p")
+    net = P.Unet(spec.levels, spec.c_i, spec.c_h, spec.c_o, "cpu", act_fn="gelu", r_p=spec.r_p, loss_type=spec.loss_type,
+                 use_symm=False, a_bound=spec.a_bound, repeats=spec.repeats, f=spec.f, p_pred=spec.p_pred).double().eval()
+    net.load_state_dict({k: torch.tensor(v) for k, v in w.items()})
+    H, W = 36, 50
+    xc, yc = RN.synthetic_grid(H, W)
+    T0 = RN.synthetic_T0(H, W, seed=1)
+    raq, fkt, fkp = 6.79733173, 475523342.0, 2.58574662
+    nd = RN.nondim_params(raq, fkt, fkp)
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    g = torch.Generator().manual_seed(3)
+    up, vp = torch.randn(1, 1, H, W, generator=g, dtype=torch.float64), torch.randn(1, 1, H, W, generator=g, dtype=torch.float64)
+    dt = torch.full((1, 1, H, W), 1e-3, dtype=torch.float64)
+    ts = P.TS(net, None, "cpu", ts=2, scale=True, p_pred=True, net="unet")
+    grid = lambda a: t64(a).view(1, 1, H, W)
+    x, dts, u, v, p, V = ts(grid(T0), None, None, grid(yc), t64(nd[0]), t64(nd[1]), t64(nd[2]), t64(raq), t64(fkt), t64(fkp),
+                            grid(xc), grid(yc), u_prev=up, v_prev=vp, dt=dt)
+    assert sorted(x) == [0, 1, 2] and dts == {} and p is None
+    T = T0[None, None]
+    for i in (1, 2):
+        inp7, _V = RN.build_input(T, xc, yc, yc, raq, fkt, fkp)
+        inp = np.concatenate([inp7[:, 0:2], dt.numpy(), inp7[:, 3:6], inp7[:, 2:3], inp7[:, 6:7], up.numpy(), vp.numpy()], 1)
+        u_ref, v_ref, _p, Tn = RN.unet_forward(w, spec, inp)
+        T = RN.apply_T_bcs(Tn[:, None].copy())
+        assert tuple(x[i].shape) == (1, 1, H, W) and np.abs(x[i].numpy() - T).max() < 1e-6
+    assert relerr(u.numpy()[0], u_ref) < 1e-5 and relerr(v.numpy()[0], v_ref) < 1e-5
+    assert np.abs(V.numpy() - inp7[:, 2:3]).max() < 1e-6
+    # a scalar dt is broadcast
+    x2 = ts(grid(T0), None, None, grid(yc), t64(nd[0]), t64(nd[1]), t64(nd[2]), t64(raq), t64(fkt), t64(fkp), grid(xc), grid(yc),
+            u_prev=up, v_prev=vp, dt=torch.tensor(1e-3, dtype=torch.float64))[0]
+    assert np.abs(x2[2].numpy() - x[2].numpy()).max() < 1e-12
+    with pytest.raises(ValueError):
+        ts(grid(T0), None, None, grid(yc), t64(nd[0]), t64(nd[1]), t64(nd[2]), t64(raq), t64(fkt), t64(fkp), grid(xc), grid(yc))
