@@ -282,6 +282,31 @@ def eng_grid(H, W, dev):
     return Grid(xc, yc, yc, dev)
 
 
+def bind_host_to_gpu_numa_node(local):
+    """Multi-rank runs only: pin this process (and the pinned host buffers it first-touches afterwards) to the CPUs NVML
+    reports as local to its GPU.  Eight unpinned ranks each moving ~10 MB per 0.45 ms step through host memory measured
+    4.5x one rank end to end (profiles/r1_bench_rollout512_8gpu.json).  Best effort: any failure leaves the affinity alone.
+    Returns the number of CPUs bound to, or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(local).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = os.sched_getaffinity(0)
+        if len(after) < 4:  # a degenerate mask would serialise the rank's helper threads: undo
+            os.sched_setaffinity(0, before)
+            return None
+        return len(after)
+    except Exception:
+        return None
+
+
 def launches_per_step(L_, R_):
     # build_input + conv0 + L*R trunk convs + conv1..3 + (L-1) pools + (L-1) bicubic + head + stencil
     return 1 + 1 + L_ * R_ + 3 + 2 * (L_ - 1) + 1 + 1
@@ -299,6 +324,7 @@ def run_ours(args, wl):
         raise SystemExit("bench.py (--impl ours) needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_host_to_gpu_numa_node(local) if world > 1 else None  # N = 1 keeps every core for the CPU baseline
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     H, W, B = wl["H"], wl["W"], wl["B"]
@@ -443,6 +469,7 @@ def run_ours(args, wl):
                        "net": "NewFluidNet(levels=6,c_i=7,c_h=16,c_o=2,k=3,replicate,symm,curl,repeats=4)", "conv_impl": args.conv,
                        "l2": "flushed (256 MiB write, untimed) between timed steps; per-step CUDA-event intervals summed",
                        "parallelism": f"{world} independent rollouts (no collective)" if world > 1 else "single GPU",
+                       "host_affinity": f"rank 0 bound to its GPU's {numa_cpus} NUMA-local CPUs (NVML)" if numa_cpus else "unbound",
                        "graph": "one CUDA graph per time step"},
             "surrogate_steps_per_s": world * K / (dev_ms * 1e-3),
             "gflop_per_step": B * H * W * FLOP_PER_CELL / 1e9,
