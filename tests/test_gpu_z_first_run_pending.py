@@ -30,8 +30,9 @@ def test_unet_forward_against_reference_golden(tag):
     assert (res["p"] is None) == ("p" not in outs)
     for n, ref in outs.items():
         assert tuple(res[n].shape) == ref.shape and res[n].dtype == torch.float64
-        # fp32 kernels; the curl differentiates the stream function (same bound as the NewFluidNet variants)
-        tol = 3e-4 if (n in "uv" and spec.loss_type == "curl") else 3e-5
+        # fp32 kernels against the float64 reference; the reference's own fp32 run is 0.6e-6 .. 1.8e-6 away on these
+        # (random, non-smooth) inputs, so the curl does not amplify anything here
+        tol = 3e-5
         assert relerr(res[n].cpu().numpy(), ref) < tol, (n, relerr(res[n].cpu().numpy(), ref))
 
 
@@ -82,5 +83,5 @@ def test_learned_network_against_reference_golden(tag):
         assert (res["p"] is None) == ("p" not in outs)
         for n, ref in outs.items():
             assert tuple(res[n].shape) == ref.shape
-            tol = 3e-4 if n in "uv" else 3e-5
+            tol = 3e-5  # the reference's own fp32 run: 5e-7 .. 8e-7
             assert relerr(res[n].cpu().numpy(), ref) < tol, (call, n, relerr(res[n].cpu().numpy(), ref))
