@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBMC_VERSION 2
+#define PBMC_VERSION 3
 #define PBMC_MAX_SRC 8
 #define PBMC_MAX_LEVELS 8
 #define PBMC_MAX_REPEATS 8
@@ -254,12 +254,13 @@ int pbmc_surrogate_forward(pbmc_ctx* ctx, const pbmc_net* net_h, const float* in
 
 /* n_steps of: build input -> surrogate -> un-scale -> advect/diffuse -> BCs.
  *   T_seq: [nslots][B][H][W]; step i reads slot (i-1)%nslots and writes slot i%nslots (i = first_step .. first_step+n_steps-1)
- *   dt_seq: [>= first_step+n_steps][B] doubles, entry i-1 written by step i (may be NULL)
+ *   dt_seq: [dt_seq_rows][B] doubles, entry i-1 written by step i (may be NULL); dt_seq_rows >= first_step + n_steps - 1
+ *           is checked (PBMC_ERR_BAD_SHAPE), so a chunked caller cannot write past its history buffer
  *   per_member_dt: 1 = each member has its own CFL dt (independent rollouts); 0 = ADNet's batch-global dt (:556)
  *   u,v,p,V: plain [B][H][W] buffers holding the LAST step's fields (V may be NULL) */
 int pbmc_rollout(pbmc_ctx* ctx, const pbmc_net* net_h, const pbmc_member* members, const float* xc, const float* yc,
                  const float* ycc, const float* xcoef, const float* ycoef, double dx_min, double cn_max, int per_member_dt, float* T_seq,
-                 int nslots, int first_step, int n_steps, double* dt_seq, float* u, float* v, float* p, float* V,
+                 int nslots, int first_step, int n_steps, double* dt_seq, int dt_seq_rows, float* u, float* v, float* p, float* V,
                  void* workspace, size_t workspace_bytes, int B, int H, int W, void* stream);
 
 #ifdef __cplusplus

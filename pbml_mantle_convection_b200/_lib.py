@@ -86,7 +86,7 @@ SIGNATURES = {
     "pbmc_ctx_destroy": (_i, [_vp]),
     "pbmc_workspace_bytes": (_sz, [C.POINTER(Net), _i, _i, _i]),
     "pbmc_surrogate_forward": (_i, [_vp, C.POINTER(Net), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
-    "pbmc_rollout": (_i, [_vp, C.POINTER(Net), _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _vp, _i, _i, _i, _vp, _vp, _vp,
+    "pbmc_rollout": (_i, [_vp, C.POINTER(Net), _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp,
                           _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
 }
 

@@ -467,10 +467,11 @@ extern "C" int pbmc_rollout(pbmc_ctx* ctx, const pbmc_net* net, const pbmc_membe
                             const float* yc, const float* ycc, const float* xcoef, const float* ycoef, double dx_min,
                             double cn_max,
                             int per_member_dt, float* T_seq, int nslots, int first_step, int n_steps, double* dt_seq,
-                            float* u, float* v, float* p, float* V, void* workspace, size_t workspace_bytes, int B, int H,
+                            int dt_seq_rows, float* u, float* v, float* p, float* V, void* workspace, size_t workspace_bytes, int B, int H,
                             int W, void* stream) {
   if (!ctx || !net || !members || !xc || !yc || !ycc || !xcoef || !ycoef || !T_seq || !u || !v || !workspace) return PBMC_ERR_NULL_POINTER;
   if (nslots < 2 || first_step < 1 || n_steps < 0 || !(dx_min > 0.0)) return PBMC_ERR_BAD_SHAPE;
+  if (dt_seq != nullptr && dt_seq_rows < first_step + n_steps - 1) return PBMC_ERR_BAD_SHAPE;  // step i writes row i - 1
   if (net->c_i != 7) return PBMC_ERR_UNSUPPORTED;  // TS builds the 7-channel input (:390-407)
   Plan P;
   RC(make_plan(*net, B, H, W, P));

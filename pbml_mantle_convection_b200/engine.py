@@ -86,8 +86,11 @@ class SurrogateEngine:
                                       "runs through BoundaryLearnedConvolution2D.forward")
         f32 = lambda t: None if t is None else t.detach().to(dev, torch.float32)
 
+        from .symmetric_layers_torch import _check_conv_supported
+
         def fluid(fl, cin):
             conv, gn = fl.layers[0], fl.layers[1]
+            _check_conv_supported(conv)  # dilation / stride / groups != 1 would silently compute another operator
             w = f32(conv.weight)
             if getattr(conv, "symmetry", None) is not None:
                 w = ops.expand_symmetric(w, conv.out_channels)
@@ -96,6 +99,8 @@ class SurrogateEngine:
         self.conv0 = fluid(m.conv[0], m.c_i)
         self.trunk = [[fluid(m.convs[l][r], m.c_h) for r in range(m.repeats)] for l in range(m.levels)]
         c1, c2, c3 = m.conv[1], m.conv[2], m.conv[3]
+        for c in (c1, c2, c3):
+            _check_conv_supported(c)
         self.conv1 = _PackedLayer(f32(c1.weight), f32(c1.bias), f32(m.gn[0].weight), f32(m.gn[0].bias),
                                   [m.c_h] * m.levels + [m.c_i], dev)
         self.conv2 = _PackedLayer(f32(c2.weight), f32(c2.bias), None, None, [m.c_h], dev)
@@ -128,13 +133,26 @@ class SurrogateEngine:
 
     # -------------------------------------------------------------- workspace
     def workspace(self, B, H, W):
+        """One workspace per (B, H, W), kept for the life of the engine: captured CUDA graphs (TS plans, ensemble graphs)
+        hold its raw address, so a buffer is never freed or replaced while the engine lives.  `release_workspaces()` is
+        the explicit way to give the memory back (every graph captured on this engine must be dropped first)."""
         k = (B, H, W)
-        if k not in self._ws:
+        ws = self._ws.get(k)
+        if ws is None:
             nbytes = L.load().pbmc_workspace_bytes(C.byref(self.desc), B, H, W)
             if nbytes == 0:
                 raise L.PbmcError(f"unsupported network/grid configuration for the fused engine: B={B} H={H} W={W}")
-            self._ws = {k: torch.empty(nbytes, dtype=torch.uint8, device=self.device)}  # keep only the latest shape
-        return self._ws[k]
+            ws = self._ws[k] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return ws
+
+    def release_workspaces(self):
+        self._ws = {}
+
+    def graph_key(self, B, H, W):
+        """Everything a captured graph of this engine bakes in besides its own buffers: packed-weight identity, conv
+        implementation, workspace address.  A change in any of them must force a re-capture."""
+        self.refresh()
+        return (self._key, self.conv_impl, self.workspace(B, H, W).data_ptr())
 
     # -------------------------------------------------------------- forward
     def forward_blocked(self, inp_blocked, members=None, want_uvmax=False):
@@ -160,7 +178,7 @@ class SurrogateEngine:
         ws = self.workspace(s.B, s.H, s.W)
         L.check(L.load().pbmc_rollout(self._ctx, C.byref(self.desc), L.ptr(s.members), L.ptr(s.xc), L.ptr(s.yc), L.ptr(s.ycc),
                                       L.ptr(s.xcoef), L.ptr(s.ycoef), float(s.dx_min), float(s.cn_max), int(s.per_member_dt),
-                                      L.ptr(s.T_seq), s.nslots, int(first_step), int(n_steps), L.ptr(s.dt_seq), L.ptr(s.u),
+                                      L.ptr(s.T_seq), s.nslots, int(first_step), int(n_steps), L.ptr(s.dt_seq), int(s.dt_seq.shape[0]), L.ptr(s.u),
                                       L.ptr(s.v), L.ptr(s.p), L.ptr(s.V), L.ptr(ws), ws.numel(), s.B, s.H, s.W,
                                       L.stream_ptr(self.device)), "pbmc_rollout")
 
@@ -203,6 +221,7 @@ class RolloutState:
         self.cn_max, self.per_member_dt = cn_max, per_member_dt
         f = lambda: torch.empty(B, self.H, self.W, dtype=torch.float32, device=device)
         self.T_seq = torch.empty(nslots, B, self.H, self.W, dtype=torch.float32, device=device)
-        self.dt_seq = torch.zeros(max(max_steps, 1), B, dtype=torch.float64, device=device)
+        # step i writes row i - 1; a chunk may start at first_step = 2 (odd slot parity): max_steps + 1 rows
+        self.dt_seq = torch.zeros(max(max_steps, 1) + 1, B, dtype=torch.float64, device=device)
         self.u, self.v, self.V = f(), f(), f()
         self.p = f() if p_pred else None

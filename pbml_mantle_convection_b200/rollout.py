@@ -72,10 +72,12 @@ class EnsembleRollout:
     def step(self, n=1):
         """Enqueue n time steps directly (no graph)."""
         done = 0
+        self.engine = self.net._engine(self.device)  # picks up a changed net.conv_impl
         while done < n:
-            k = min(n - done, self.max_steps)
-            # dt history is written relative to first_step; restart the index every call
+            # dt history is written relative to first_step (rows first-1 .. first-1+k-1 of max_steps + 1); restart the
+            # index every call
             first = 1 + (self.n_done % 2)
+            k = min(n - done, self.max_steps)
             self.engine.rollout(self.state, first, k)
             self.time += self.state.dt_seq[first - 1:first - 1 + k].sum(0)
             self.n_done += k
@@ -87,8 +89,11 @@ class EnsembleRollout:
         k = int(steps_per_graph)
         if k < 1 or k > self.max_steps - 1:
             raise ValueError("steps_per_graph out of range")
+        self.engine = self.net._engine(self.device)  # picks up a changed net.conv_impl
         par = self.n_done % 2
-        if (k, par) not in self._graphs:
+        # the graph bakes in packed-weight and workspace addresses and the conv implementation: key on them too
+        key = (k, par) + self.engine.graph_key(self.B, self.H, self.W)
+        if key not in self._graphs:
             saved = self.state.T_seq.clone()
             self.engine.rollout(self.state, 1 + par, 1)  # eager warm-up: module load + func attributes outside capture
             self.state.T_seq.copy_(saved)
@@ -96,8 +101,8 @@ class EnsembleRollout:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self.engine.rollout(self.state, 1 + par, k)
-            self._graphs[(k, par)] = g
-        return self._graphs[(k, par)]
+            self._graphs[key] = g
+        return self._graphs[key]
 
     def run(self, n_steps, steps_per_graph=None, track_time=True):
         """Advance n_steps.  With steps_per_graph=k (divides n_steps) the work is k-step CUDA-graph replays.

@@ -18,6 +18,20 @@ def split_weights(d, prefix="w::"):
     return {k[len(prefix):]: v for k, v in d.items() if k.startswith(prefix)}
 
 
+def noise(tag):
+    """The reference's OWN float32-vs-float64 distance on golden case `tag` (tests/golden/ref_fp32_noise.json, written by
+    make_golden.py from the real reference): rel-L2 per output field, max-abs for T, relative for dt."""
+    import json
+
+    return json.load(open(os.path.join(GOLDEN, "ref_fp32_noise.json")))[tag]
+
+
+def field_bound(ref_noise, floor=1e-5):
+    """north_star's 1e-5 relative bound, widened to 1.5 x the reference's own fp32 noise where that is larger
+    (no fp32 implementation, PyTorch's included, is closer to the fp64 reference than that)."""
+    return max(floor, 1.5 * float(ref_noise))
+
+
 def relerr(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)

@@ -10,6 +10,8 @@ outputs as .npz.  The GPU boxes have no /root/reference: the tests there read on
     python tests/golden/make_golden.py            # regenerate everything
     python tests/golden/make_golden.py unet       # only the U-Net vectors
     python tests/golden/make_golden.py learned    # only the whole learned-boundary networks
+    python tests/golden/make_golden.py fullsize   # 512^2 (config 2) and 4 x 256^2 (config 4) goldens + their noise floors
+    python tests/golden/make_golden.py noise      # ref_fp32_noise.json: the reference's own fp32-vs-fp64 distance per case
 """
 from __future__ import annotations
 
@@ -338,6 +340,178 @@ def golden_learned():
     np.savez_compressed(os.path.join(HERE, "learned.npz"), **out)
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# Noise floors of the reference itself (its float32 run against its float64 run) for EVERY golden case, and the
+# full-size goldens of BASELINE configs 2 and 4.  The parity bound of the GPU tests is, per field,
+#     rel_L2(new_fp32, ref_fp64) <= max(1e-5, 1.5 * rel_L2(ref_fp32, ref_fp64))          
+# so each case needs its own stored noise: tests/golden/ref_fp32_noise.json.
+import contextlib  # noqa: E402
+import json  # noqa: E402
+
+_FD_KERNELS = ("dx_right_kernel", "dy_bottom_kernel", "dx_left_kernel", "dy_top_kernel", "dx_center_kernel", "dy_center_kernel")
+
+
+@contextlib.contextmanager
+def reference_fp32():
+    """The reference's module-level FD stencils are float64 constants (pytorch_networks_convae.py:183-256): swap them
+    for float32 copies while a float32 ADNet runs (SURVEY.md section 8c "fp32 oracle")."""
+    saved = {k: getattr(P, k) for k in _FD_KERNELS}
+    try:
+        for k in _FD_KERNELS:
+            setattr(P, k, saved[k].float())
+        yield
+    finally:
+        for k, v in saved.items():
+            setattr(P, k, v)
+
+
+def _rollout_ref(net, T0_np, xc_np, yc_np, params, n_steps, dtype):
+    H, W = T0_np.shape
+    ad = P.ADNet(torch.device("cpu"), CN_max=0.99)
+    xc = torch.tensor(xc_np, dtype=dtype).view(1, 1, H, W)
+    yc = torch.tensor(yc_np, dtype=dtype).view(1, 1, H, W)
+    T = torch.tensor(T0_np, dtype=dtype).view(1, 1, H, W)
+    hist = []
+    for _ in range(n_steps):
+        T, dt, u, v, p, V, _inp = ref_step(net, ad, T, xc.clone(), yc.clone(), *params)
+        hist.append(dict(T=T[0, 0].double().numpy().copy(), dt=float(dt), u=u[0, 0].double().numpy().copy(),
+                         v=v[0, 0].double().numpy().copy(), p=None if p is None else p[0].double().numpy().copy(),
+                         V=V[0, 0].double().numpy().copy()))
+    return hist
+
+
+def _rollout_noise(spec, H, W, params, n_steps, T0_np, cls=None):
+    """(fp64 history, fp32 history) of the reference on one case."""
+    xc_np, yc_np = RN.synthetic_grid(H, W)
+    net64 = make_net(spec, cls=cls)
+    set_grid(net64, H, W)
+    h64 = _rollout_ref(net64, T0_np, xc_np, yc_np, params, n_steps, torch.float64)
+    net32 = make_net(spec, cls=cls)
+    set_grid(net32, H, W)
+    set_fp32(net32)
+    with reference_fp32():
+        h32 = _rollout_ref(net32, T0_np, xc_np, yc_np, params, n_steps, torch.float32)
+    return h64, h32, net64
+
+
+def _field_noise(h64, h32, i):
+    a, b = h64[i], h32[i]
+    out = {"u": relerr(b["u"], a["u"]), "v": relerr(b["v"], a["v"])}
+    if a["p"] is not None:
+        out["p"] = relerr(b["p"], a["p"])
+    out["T_maxabs"] = float(np.abs(b["T"] - a["T"]).max())
+    out["V_maxabs"] = float(np.abs(b["V"] - a["V"]).max())
+    out["dt_rel"] = abs(b["dt"] - a["dt"]) / a["dt"]
+    return out
+
+
+@torch.no_grad()
+def golden_noise():
+    """ref_fp32_noise.json: for every network-level golden case, how far the reference's own float32 run is from its
+    float64 run -- rel-L2 per output field, max-abs for T after the stored step counts."""
+    noise = {}
+    # forward-only cases: variants, learned networks, U-Net
+    for tag in ("var_zeros_nosym", "var_reflect_sym", "var_replicate_odd", "var_mae_p", "var_k5"):
+        g = dict(np.load(os.path.join(HERE, tag + ".npz")))
+        s = g["spec"]
+        spec = RN.NetSpec(levels=int(s[0]), c_i=int(s[1]), c_h=int(s[2]), c_o=int(s[3]), repeats=int(s[4]), f=int(s[5]),
+                          use_symm=bool(s[6]), p_pred=bool(s[7]), r_p=str(g["r_p"]), loss_type=str(g["loss_type"]),
+                          a_bound=float(g["a_bound"]))
+        H, W = g["inp"].shape[-2:]
+        net = make_net(spec, seed=3)
+        set_grid(net, H, W)
+        set_fp32(net)
+        res = net(torch.tensor(g["inp"], dtype=torch.float32))
+        noise[tag] = {n: relerr(r.double().numpy(), g[n]) for n, r in zip("uvp", res) if r is not None}
+    for file, cases, seed in (("learned", {"learned_k5": P.NewFluidNet, "learned_k3_p": P.NewFluidNet, "learned_fluidnet": P.FluidNet}, 6),
+                              ("unet", {"unet_curl_p": None, "unet_curl_k5": None, "unet_mae": None}, 5)):
+        g = dict(np.load(os.path.join(HERE, file + ".npz")))
+        for tag, cls in cases.items():
+            d = {k[len(tag) + 2:]: v for k, v in g.items() if k.startswith(tag + "::")}
+            s = d["spec"]
+            spec = RN.NetSpec(levels=int(s[0]), c_i=int(s[1]), c_h=int(s[2]), c_o=int(s[3]), repeats=int(s[4]), f=int(s[5]),
+                              use_symm=bool(s[6]), p_pred=bool(s[7]), r_p=str(d["r_p"]), loss_type=str(d["loss_type"]),
+                              a_bound=float(d["a_bound"]))
+            H, W = d["inp"].shape[-2:]
+            if file == "unet":
+                net = make_net(spec, seed=seed, cls=lambda *a, factor=2, **k: P.Unet(*a, **k))
+                net.float()
+                for attr in ("dx_center_kernel", "dy_center_kernel"):
+                    if hasattr(net, attr):
+                        setattr(net, attr, getattr(net, attr).float())
+            else:
+                net = make_net(spec, seed=seed, cls=cls)
+                set_grid(net, H, W)
+                set_fp32(net)
+            res = net(torch.tensor(d["inp"], dtype=torch.float32))
+            noise[tag] = {n: relerr(r.double().numpy(), d[n]) for n, r in zip("uvpT", res) if r is not None and n in d}
+    # rollouts: 128^2 (1 / 10 / 100 steps), 64x96 (1 / 10), 128x506 through the unmodified TS (5 steps)
+    for tag, spec, H, W, keep in (("roll128", RN.NetSpec(), 128, 128, (1, 10, 100)), ("roll64x96", RN.NetSpec(levels=4), 64, 96, (1, 10)),
+                                  ("ts128x506", RN.NetSpec(), 128, 506, (1, 5))):
+        h64, h32, _ = _rollout_noise(spec, H, W, (RAQ, FKT, FKP), max(keep), RN.synthetic_T0(H, W, seed=1))
+        g = dict(np.load(os.path.join(HERE, tag + ".npz")))
+        assert np.abs(h64[0]["T"] - g["T1"]).max() == 0.0, "noise run does not reproduce the stored golden"
+        noise[tag] = {f"step{i}": _field_noise(h64, h32, i - 1) for i in keep}
+        mT64, Tp64, dTp64 = RN.diagnostics(h64[-1]["T"], RN.synthetic_grid(H, W)[1][:, 0])
+        mT32, Tp32, dTp32 = RN.diagnostics(h32[-1]["T"], RN.synthetic_grid(H, W)[1][:, 0])
+        noise[tag]["diag_last"] = {"meanT": abs(mT64 - mT32), "Tprof_maxabs": float(np.abs(Tp64 - Tp32).max()),
+                                   "dTprof_rel": float(np.abs(dTp64 - dTp32).max() / np.abs(dTp64).max())}
+        print(f"[noise] {tag}: {noise[tag]}")
+    path = os.path.join(HERE, "ref_fp32_noise.json")
+    old = json.load(open(path)) if os.path.exists(path) else {}
+    old.update(noise)
+    json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+    for k, v in noise.items():
+        print(k, v)
+
+
+ENS256_PARAMS = [(RAQ, FKT, FKP), (0.9, 3.0e6, 1.5), (9.1, 5.0e9, 60.0), (4.2, 2.5e8, 12.0)]  # spread over the paper's ranges
+
+
+@torch.no_grad()
+def golden_full_size():
+    """BASELINE config 2 (512x512, batch 1): fields of the first forward + T after 3 steps; config 4 (256x256 ensemble):
+    4 members with different (RaQ, gamma, beta, T0 seed), each a B = 1 run of the reference (SURVEY.md section 8c
+    "Ensembles"), fields and T after 3 steps.  float64, weights = roll128_weights.npz (same spec and seed)."""
+    noise = {}
+    spec = RN.NetSpec()
+    H = W = 512
+    T0 = RN.synthetic_T0(H, W, seed=1)
+    h64, h32, net = _rollout_noise(spec, H, W, (RAQ, FKT, FKP), 3, T0)
+    w128 = dict(np.load(os.path.join(HERE, "roll128_weights.npz")))
+    sd = sd_numpy(net)
+    assert all(np.array_equal(sd[k], w128[k]) for k in sd), "roll512 must share roll128's weights"
+    out = {"params": np.array([RAQ, FKT, FKP]), "T0_seed": np.int64(1), "u1": h64[0]["u"], "v1": h64[0]["v"], "p1": h64[0]["p"],
+           "T1": h64[0]["T"], "T3": h64[2]["T"], "dts": np.array([h["dt"] for h in h64])}
+    np.savez_compressed(os.path.join(HERE, "roll512.npz"), **out)
+    noise["roll512"] = {"step1": _field_noise(h64, h32, 0), "step3": _field_noise(h64, h32, 2)}
+    print("[roll512]", noise["roll512"])
+    H = W = 256
+    out = {"params": np.array(ENS256_PARAMS), "T0_seeds": np.arange(1, 5)}
+    noise["ens256"] = {}
+    for m, prm in enumerate(ENS256_PARAMS):
+        h64, h32, _ = _rollout_noise(spec, H, W, prm, 3, RN.synthetic_T0(H, W, seed=1 + m))
+        out.update({f"m{m}_u3": h64[2]["u"], f"m{m}_v3": h64[2]["v"], f"m{m}_p3": h64[2]["p"], f"m{m}_T3": h64[2]["T"],
+                    f"m{m}_dts": np.array([h["dt"] for h in h64])})
+        noise["ens256"][f"m{m}"] = _field_noise(h64, h32, 2)
+        print(f"[ens256 m{m}]", noise["ens256"][f"m{m}"])
+    np.savez_compressed(os.path.join(HERE, "ens256.npz"), **out)
+    path = os.path.join(HERE, "ref_fp32_noise.json")
+    old = json.load(open(path)) if os.path.exists(path) else {}
+    old.update(noise)
+    json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+
+if __name__ == "__main__" and sys.argv[1:] == ["noise"]:
+    torch.set_num_threads(os.cpu_count())
+    golden_noise()
+    sys.exit(0)
+
+if __name__ == "__main__" and sys.argv[1:] == ["fullsize"]:
+    torch.set_num_threads(os.cpu_count())
+    golden_full_size()
+    sys.exit(0)
+
 if __name__ == "__main__" and sys.argv[1:] == ["learned"]:
     torch.set_num_threads(os.cpu_count())
     golden_learned()
@@ -357,6 +531,8 @@ if __name__ == "__main__":
     golden_rollout("roll128", RN.NetSpec(), 128, 128, keep=(1, 10, 100), n_steps=100)
     golden_rollout("roll64x96", RN.NetSpec(levels=4), 64, 96, keep=(1, 10), n_steps=10)
     golden_ts_unmodified()
+    golden_full_size()
+    golden_noise()
 
 
 def golden_mlp_weights():

@@ -40,7 +40,7 @@ def test_struct_sizes(lib):
 
 
 def test_version_and_errors(lib):
-    assert lib.pbmc_version() == 2
+    assert lib.pbmc_version() == 3
     assert lib.pbmc_error_string(0) == b"ok"
     assert b"workspace" in lib.pbmc_error_string(-5)
 
@@ -58,6 +58,13 @@ def test_argument_validation_without_gpu(lib):
     b2 = lib.pbmc_workspace_bytes(C.byref(n), 2, 512, 512)
     assert b1 > 512 * 512 * 16 * 4 * 10 and b2 > 1.9 * b1
     assert lib.pbmc_workspace_bytes(C.byref(n), 1, 16, 16) == 0  # 6 levels do not fit a 16x16 grid
+    # pbmc_rollout refuses a dt history that the requested steps would overrun (step i writes row i - 1) -- checked
+    # before anything is dereferenced, so dummy non-null addresses are enough here
+    d = C.c_void_p(0x1000)
+    args = lambda first, k, rows: (d, C.byref(n), d, d, d, d, d, d, 0.01, 0.99, 1, d, 2, first, k, d, rows, d, d, d, d, d, 1 << 30,
+                                   1, 512, 512, None)
+    assert lib.pbmc_rollout(*args(2, 8, 8)) == -1   # rows 1..8 of an 8-row buffer: one past the end
+    assert lib.pbmc_rollout(*args(1, 8, 7)) == -1
 
 
 def test_python_wrappers_refuse_cpu_tensors(lib):
