@@ -312,32 +312,18 @@ def launches_per_step(L_, R_):
     return 1 + 1 + L_ * R_ + 3 + 2 * (L_ - 1) + 1 + 1
 
 
-def run_ours(args, wl):
+def timed_rollout(net, H, W, B, rank, world, local, dev, K, Wm, flush, T0=None):
+    """Device-resident rollout of B members per rank: one CUDA graph per time step, L2 flushed (untimed) between steps,
+    per-step CUDA-event intervals summed.  Returns (device ms over K steps on this rank, wall s, finite, clock sampler)."""
     import torch.distributed as dist
 
     import pbml_mantle_convection_b200 as P
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (--impl ours) needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    numa_cpus = bind_host_to_gpu_numa_node(local) if world > 1 else None  # N = 1 keeps every core for the CPU baseline
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    H, W, B = wl["H"], wl["W"], wl["B"]
-    K, Wm = args.steps, max(args.warmup, 3)
-    net = primary_net(dev)
-    net.conv_impl = args.conv
     prm = member_params(B, rank)
     ens = P.EnsembleRollout(net, H, W, prm, dev, cn_max=0.99, per_member_dt=True)
-    T0 = np.stack([P.synthetic_T0(H, W, seed=1 + rank * B + m) for m in range(B)])
+    if T0 is None:
+        T0 = np.stack([P.synthetic_T0(H, W, seed=1 + rank * B + m) for m in range(B)])
     ens.set_T(T0)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-
-    # ---- device-resident rollout: one CUDA graph per time step, L2 flushed (untimed) between steps
     ens.run(Wm + (Wm % 2), steps_per_graph=1)
     torch.cuda.synchronize()
     if world > 1:
@@ -360,6 +346,52 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     finite = bool(torch.isfinite(ens.T).all().item())
+    return dev_ms, wall, finite, clk
+
+
+def ensemble_record(net, rank, world, local, dev, K, Wm, flush):
+    """BASELINE config 4: 32 members of 256x256 per GPU (varied Ra / gamma / beta / initial T), batch-sharded over the
+    ranks, per-member dt, no data-path collective -- weak scaling.  Rank 0 returns the record."""
+    import torch.distributed as dist
+
+    wl = WORKLOADS["ensemble256"]
+    H, W, B = wl["H"], wl["W"], wl["B"]
+    dev_ms, wall, finite, clk = timed_rollout(net, H, W, B, rank, world, local, dev, K, Wm, flush)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    fin = torch.tensor([int(finite)], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+    ms = t.item()
+    return {"metric": "rollout cell-updates/s", "value": world * B * H * W * K / (ms * 1e-3), "unit": "cell-updates/s", "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
+            "config": {"workload": "ensemble256", "desc": wl["desc"], "grid": [H, W], "batch_per_gpu": B, "members_total": world * B,
+                       "parallelism": f"{world * B} independent members, {B} per GPU, no collective in the loop"},
+            "surrogate_steps_per_s": world * B * K / (ms * 1e-3), "finite": bool(fin.item()), "clocks": clk.summary()}
+
+
+def run_ours(args, wl):
+    import torch.distributed as dist
+
+    import pbml_mantle_convection_b200 as P
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (--impl ours) needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa_cpus = bind_host_to_gpu_numa_node(local) if world > 1 else None  # N = 1 keeps every core for the CPU baseline
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, W, B = wl["H"], wl["W"], wl["B"]
+    K, Wm = args.steps, max(args.warmup, 3)
+    net = primary_net(dev)
+    net.conv_impl = args.conv
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    T0 = np.stack([P.synthetic_T0(H, W, seed=1 + rank * B + m) for m in range(B)])
+    dev_ms, wall, finite, clk = timed_rollout(net, H, W, B, rank, world, local, dev, K, Wm, flush, T0)
 
     # ---- end to end through the drop-in TS call with HOST float64 tensors (advect_wi_gaia.py:590-616)
     ts = P.TS(net, P.ADNet(dev, CN_max=0.99), dev, ts=1, scale=True, p_pred=True, net="newfluidnet")
@@ -485,38 +517,102 @@ def run_ours(args, wl):
             "clocks": clk.summary(),
             "finite": finite,
         }
+    # ---- the two multi-GPU workloads of BASELINE.json as sub-records of the same line (every N, so that the driver's
+    # 1/2/4/8 runs carry config 5's strong-scaling curve -- the path WITH a cross-rank exchange -- and config 4's weak one)
+    subs = None
+    if args.workload == "rollout512" and not args.no_sub_records:
+        del ts
+        torch.cuda.empty_cache()
+        subs = {"ensemble256": ensemble_record(net, rank, world, local, dev, min(K, 20), 4, flush)}
+        del flush
+        torch.cuda.empty_cache()
+        wls = WORKLOADS["slab8192"]
+        subs["slab8192"] = slab_record(rank, world, local, dev, wls["H"], wls["W"], 100, 10, "p2p", "flags", wls["desc"])
+        if line is not None:
+            line["sub_records"] = subs
+            line["gpu_launches"] += launches_per_step(6, 4) * subs["ensemble256"]["steps"] + subs["slab8192"]["steps"]
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         emit(line)
+    if subs is not None:
+        sl = subs["slab8192"]
+        if not (sl["finite"] and sl["bounded"] and sl["identical_to_single_gpu"] and subs["ensemble256"]["finite"]):
+            raise SystemExit("sub-record check failed: non-finite / unbounded field, or the decomposed slab run differs from the single-domain run")
 
 
-def run_slab(args, wl):
-    """BASELINE config 5: a single large grid, slab-decomposed over the ranks (strong scaling: total work fixed)."""
-    import torch.distributed as dist
+def slab_velocity(xs, ys, H, W):
+    """Smooth cellular flow for the slab workloads, STABLE for the explicit update on this grid (SURVEY.md section 8d
+    config 3: "advective dt << diffusive dt, stable in both axes").  The reference takes dt from the x spacing only
+    (pytorch_networks_convae.py:555-559), so on an H x W grid over the 4:1 box (dy = dx/4 when H = W) the explicit
+    scheme needs  dt (|u|/dx + |v|/dy + 2/dx^2 + 2/dy^2) <= 1  with dt = 0.495 dx / max|u|:
+      max|u| = 0.495 dx / (0.1 dy^2)  ->  dt 2/dy^2 = 0.2;   max|v| = 0.05 max|u|  ->  dt |v|/dy <= 0.1 dx/dy <= 0.1 * 4
+    (total <= 0.2 + 0.0125 + 0.495 + 0.1 = 0.81 at H = W: a monotone update, T stays inside its initial range).
+    Round 1's field (max|u| = 1e3, max|v| = 750 on 8192^2) violated both limits and blew up."""
+    dx, dy = 4.0 / (W - 2), 1.0 / (H - 2)
+    umax = max(1e3, 0.495 * dx / (0.1 * dy * dy))
+    vmax = 0.05 * umax * min(1.0, 4.0 * dy / dx)
+    pi = 3.141592653589793
+    u = umax * torch.cos(pi * ys)[:, None] * torch.sin(pi * xs / 4 * 3)[None, :]
+    v = -vmax * torch.sin(pi * ys)[:, None] * torch.cos(pi * xs / 4 * 3)[None, :]
+    return u, v
 
+
+def _slab_setup(H, W, rank, world, dev, halo, dt_sync):
     import pbml_mantle_convection_b200 as P
     from pbml_mantle_convection_b200 import multigpu as MG
 
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    H, W = wl["H"], wl["W"]
-    K, Wm = args.steps, max(args.warmup, 3)
     xc, yc = P.synthetic_grid(H, W)
-    st = MG.SlabStencil(H, W, xc[0], yc[:, 0], rank, world, dev, raq=PARAMS0[0], cn_max=0.99, halo=args.halo)
+    st = MG.SlabStencil(H, W, xc[0], yc[:, 0], rank, world, dev, raq=PARAMS0[0], cn_max=0.99, halo=halo, dt_sync=dt_sync)
     s = st.slab
-    g = torch.Generator(device=dev).manual_seed(3 + rank)
     ys = torch.tensor(yc[s.l0:s.l1, 0], dtype=torch.float32, device=dev)
     xs = torch.tensor(xc[0], dtype=torch.float32, device=dev)
-    T = (1.0 - ys)[:, None] + 0.01 * torch.rand(s.rows, W, device=dev, generator=g)
-    psi_x, psi_y = torch.sin(3.14159265 * xs / 4 * 3), torch.sin(3.14159265 * ys)
-    u = 1e3 * torch.cos(3.14159265 * ys)[:, None] * psi_x[None, :]  # smooth, max|u| = 1e3 (SURVEY.md section 8d config 3)
-    v = -1e3 * psi_y[:, None] * torch.cos(3.14159265 * xs / 4 * 3)[None, :] * 0.75
+    # the same T0 on every decomposition: the noise is a function of the GLOBAL cell index
+    rows = torch.arange(s.l0, s.l1, device=dev, dtype=torch.float32)[:, None]
+    cols = torch.arange(W, device=dev, dtype=torch.float32)[None, :]
+    T = (1.0 - ys)[:, None] + 0.01 * (0.5 + 0.5 * torch.sin(12.9898 * rows + 78.233 * cols))
+    u, v = slab_velocity(xs, ys, H, W)
     st.set_local(T, u, v)
+    return st
+
+
+def slab_identity_check(rank, world, dev, halo, dt_sync, steps=6):
+    """Short in-run check of the REAL multi-GPU path (peer stores + flag slots, or NCCL): a 1024-column grid with 64 rows
+    per rank, `steps` steps through SlabStencil.step (graph replay included), gathered and compared BIT FOR BIT with the
+    single-domain kernel run on rank 0."""
+    import torch.distributed as dist
+
+    import pbml_mantle_convection_b200 as P
+    from pbml_mantle_convection_b200 import ops
+    from pbml_mantle_convection_b200.engine import Grid
+
+    H, W = 64 * world, 1024
+    st = _slab_setup(H, W, rank, world, dev, halo, dt_sync)
+    st.step(steps)
+    got = st.gather()
+    dt_last = float(st.last_dt[0])
+    st.close()
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    if rank == 0:
+        one = _slab_setup(H, W, 0, 1, dev, "nccl", "nccl")  # world 1: the plain single-domain kernel
+        one.step(steps)
+        ref = one.gather()
+        ok[0] = int(torch.equal(ref, got) and float(one.last_dt[0]) == dt_last and bool(torch.isfinite(got).all()))
+    if world > 1:
+        dist.broadcast(ok, 0)
+    return bool(ok.item())
+
+
+def slab_record(rank, world, local, dev, H, W, K, Wm, halo, dt_sync, desc):
+    """BASELINE config 5: a single large grid, slab-decomposed over the ranks (strong scaling: total work fixed)."""
+    import torch.distributed as dist
+
+    identical = slab_identity_check(rank, world, dev, halo, dt_sync) if world > 1 else True
+    st = _slab_setup(H, W, rank, world, dev, halo, dt_sync)
+    s = st.slab
+    Wm += Wm % 2
+    K += K % 2  # whole ping-pong periods (graph replays of two steps)
     st.step(Wm)
     torch.cuda.synchronize()
     if world > 1:
@@ -530,37 +626,49 @@ def run_slab(args, wl):
         if world > 1:
             dist.barrier()
     t_ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    fin = torch.tensor([int(torch.isfinite(st.T).all().item()), int(float(st.T.max()) <= 1.02 and float(st.T.min()) >= -0.02)],
+                       dtype=torch.int32, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
     ms = t_ms.item()
-    finite = bool(torch.isfinite(st.T).all().item())
-    if rank == 0:
-        hbm, _, _, which = measured_peaks()
-        rate = H * W * K / (ms * 1e-3)
-        gbs = rate * 16 / world / 1e9  # per rank: T, u, v in, T' out; max|u|,|v| for the next dt comes out of the same pass
-        line = {"metric": "stencil cell-updates/s", "value": rate, "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": Wm,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": args.workload, "desc": wl["desc"], "grid": [H, W], "rows_per_rank": s.hi - s.lo,
-                           "l2": "fields (>= 256 MiB per rank at 8 ranks x 3 fields) exceed L2; no flush",
-                           "parallelism": f"{world} row slabs, halo={args.halo} ("
-                                          + ("rows stored into the neighbours' ghost rows by the update kernel, peer memory"
-                                             if args.halo == "p2p" else "NCCL send/recv of one row each way")
-                                          + ") + all_reduce(MAX) of max|u|,|v| per step"},
-                "roofline": {"kernel": "stencil_march_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
-                             "frac": gbs / hbm, "traffic": None, "peak_source": which,
-                             "note": "per GPU, 16 algorithmic B/cell; the step also holds the dt all-reduce(MAX) and the halo exchange"},
-                "cpu_baseline": None, "e2e": None, "gpu_launches": K, "clocks": clk.summary(), "finite": finite}
-        emit(line)
+    st.close()
+    hbm, _, _, which = measured_peaks()
+    rate = H * W * K / (ms * 1e-3)
+    gbs = rate * 16 / world / 1e9  # per rank: T, u, v in, T' out; max|u|,|v| for the next dt comes out of the same pass
+    mode = ("halo rows stored into the neighbours' ghost rows by the update kernel (peer memory over NVLink); "
+            + ("global max|u|,|v| exchanged through tag|value slots in peer memory INSIDE the kernel: one launch per step, no "
+               "collective call" if dt_sync == "flags" else "NCCL all_reduce(MAX) of max|u|,|v| per step")) if (halo == "p2p" and world > 1) else \
+           ("NCCL send/recv of one row each way + all_reduce(MAX) per step" if world > 1 else "single domain")
+    return {"metric": "stencil cell-updates/s", "value": rate, "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "slab8192" if H == 8192 else f"slab{H}", "desc": desc, "grid": [H, W], "rows_per_rank": s.hi - s.lo,
+                       "l2": "fields (4 x 256 MiB / ranks per rank) exceed L2 up to 8 ranks only marginally: 8192^2 x 4 fields x 4 B = 1 GiB total; no flush",
+                       "parallelism": f"{world} row slabs; {mode}"},
+            "roofline": {"kernel": "stencil_march_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                         "frac": gbs / hbm, "traffic": None, "peak_source": which,
+                         "note": "per GPU, 16 algorithmic B/cell; the step is ONE launch holding the dt reduction and the halo exchange"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": K, "clocks": clk.summary(),
+            "finite": bool(fin[0].item()), "bounded": bool(fin[1].item()), "identical_to_single_gpu": identical}
+
+
+def run_slab(args, wl):
+    import torch.distributed as dist
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        # The 8-rank run of this workload printed its line and then never exited (tearing down the process group with
-        # captured NCCL all-reduces and the symmetric-memory rendezvous alive; 2 ranks were fine).  Nothing is left to
-        # do after the line: synchronise, meet at a barrier so that no rank still needs the store, and leave without
-        # running the destructors.
-        torch.cuda.synchronize()
+        dist.init_process_group("nccl", device_id=dev)
+    rec = slab_record(rank, world, local, dev, wl["H"], wl["W"], args.steps, max(args.warmup, 3), args.halo, args.dt_sync, wl["desc"])
+    if world > 1:
         dist.barrier()
-        sys.stderr.flush()
-        os._exit(0)
+        dist.destroy_process_group()
+    if rank == 0:
+        emit(rec)
+    if not (rec["finite"] and rec["bounded"] and rec["identical_to_single_gpu"]):
+        raise SystemExit("slab workload: non-finite / unbounded field or the decomposed run differs from the single-domain run")
 
 
 _REAL_STDOUT = None
@@ -594,6 +702,9 @@ def main():
     ap.add_argument("--conv", default="auto", choices=["auto", "ffma", "umma_3xtf32", "umma_bf16", "umma_f16x2", "row_f16x2", "row_bf16", "mux_f16x2", "mux_bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p"], help="slab workloads: how the one-row T halo moves")
+    ap.add_argument("--dt-sync", dest="dt_sync", default="flags", choices=["flags", "nccl"],
+                    help="slab workloads with --halo p2p: global dt reduction inside the kernel (flags) or NCCL all_reduce per step")
+    ap.add_argument("--no-sub-records", action="store_true", help="default workload: skip the slab8192 / ensemble256 sub-records")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

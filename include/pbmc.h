@@ -196,6 +196,33 @@ int pbmc_advect_diffuse_slab(const float* T, const float* u, const float* v, con
                              const pbmc_member* members, const uint32_t* uvmax_in, double dx_min, double cn_max,
                              double dt_fixed, float* T_out, uint32_t* uvmax_out, double* dt_out, int H, int W, int has_up,
                              int has_down, float* peer_up_ghost_row, float* peer_down_ghost_row, void* stream);
+/* Flag-synchronised slab step: the halo exchange AND the global dt reduction happen inside the update kernel, so a time
+ * step of a decomposed grid is ONE kernel launch per rank and no collective call (the reference is single-device; this
+ * replaces what would be ncclAllReduce(max) + ncclSend/Recv per step, SURVEY.md 8b "halo_exchange / dt_allreduce").
+ * Every rank owns one pbmc_slab_sync block in memory ALL ranks can write (CUDA IPC / symmetric memory over NVLink),
+ * zero-initialised; peers_h is a HOST array of the `world` blocks' addresses as mapped into this device (own included).
+ *   slot[par][r] = (step tag << 32) | float bits of rank r's max|u|,|v| over its owned interior rows
+ *   steps_done / ctas_done / local_max: private to the owning rank's kernels
+ * Protocol (step s = steps_done + 1): the kernel waits (ld.acquire.sys) until all `world` slots of parity s & 1 carry
+ * tag s, takes their max -> dt (pytorch_networks_convae.py:554-559: ONE scalar for the whole grid); stores its
+ * boundary rows into the neighbours' ghost rows; the CTA that finishes last publishes (s + 1, local max) into every
+ * rank's slot of parity (s + 1) & 1 with st.release.sys and sets steps_done = s.  pbmc_slab_sync_publish makes the
+ * first publication of a run (tag steps_done + 1) from u, v; call it again -- after a host-side barrier and with the
+ * blocks re-zeroed -- whenever the velocity field changes.  The kernel traps if a peer stays silent for 30 s.
+ * Ranks must run on DIFFERENT devices (or be launched strictly one after the other on one stream, as the
+ * single-GPU tests do): a kernel that waits for a peer's kernel must never share a GPU with it. */
+#define PBMC_MAX_RANKS 16
+typedef struct {
+  unsigned long long slot[2][PBMC_MAX_RANKS];
+  unsigned int steps_done, ctas_done, local_max, reserved;
+} pbmc_slab_sync;
+int pbmc_slab_sync_publish(const float* u, const float* v, int H, int W, pbmc_slab_sync* self,
+                           pbmc_slab_sync* const* peers_h, int rank, int world, void* stream);
+int pbmc_advect_diffuse_slab_sync(const float* T, const float* u, const float* v, const float* xcoef, const float* ycoef,
+                                  const pbmc_member* members, double dx_min, double cn_max, float* T_out, double* dt_out,
+                                  int H, int W, int has_up, int has_down, float* peer_up_ghost_row,
+                                  float* peer_down_ghost_row, pbmc_slab_sync* self, pbmc_slab_sync* const* peers_h,
+                                  int rank, int world, void* stream);
 /* max|u|,|v| over the interior as a stand-alone reduction (only needed when nothing upstream produced it) */
 int pbmc_uvmax(const float* u, const float* v, uint32_t* uvmax, int member_stride, int B, int H, int W, void* stream);
 /* general form, exactly ADNet's inputs tensor: xc, yc as [H][W] fields (coord_batch_stride = 0) or

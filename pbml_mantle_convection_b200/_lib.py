@@ -54,7 +54,15 @@ class Net(C.Structure):
                 ("trunk", Layer * (MAX_LEVELS * MAX_REPEATS)), ("conv1", Layer), ("conv2", Layer), ("conv3", Layer)]
 
 
-_STRUCTS = {"pbmc_member": Member, "pbmc_src": Src, "pbmc_conv_desc": ConvDesc, "pbmc_layer": Layer, "pbmc_net": Net}
+MAX_RANKS = 16
+
+
+class SlabSync(C.Structure):
+    _fields_ = [("slot", (C.c_uint64 * MAX_RANKS) * 2), ("steps_done", C.c_uint), ("ctas_done", C.c_uint),
+                ("local_max", C.c_uint), ("reserved", C.c_uint)]
+
+
+_STRUCTS = {"pbmc_slab_sync": SlabSync, "pbmc_member": Member, "pbmc_src": Src, "pbmc_conv_desc": ConvDesc, "pbmc_layer": Layer, "pbmc_net": Net}
 
 # name -> (restype, argtypes); every symbol declared in include/pbmc.h
 _vp, _i, _d, _f, _sz = C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_size_t
@@ -75,6 +83,9 @@ SIGNATURES = {
     "pbmc_head": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pbmc_advect_diffuse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pbmc_advect_diffuse_slab": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pbmc_slab_sync_publish": (_i, [_vp, _vp, _i, _i, _vp, C.POINTER(C.c_void_p), _i, _i, _vp]),
+    "pbmc_advect_diffuse_slab_sync": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp,
+                                           C.POINTER(C.c_void_p), _i, _i, _vp]),
     "pbmc_stencil_coefs": (_i, [_vp, _i, _d, _d, _vp, _vp]),
     "pbmc_uvmax": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "pbmc_advect_diffuse_fields": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _i, _vp, _d, _vp, _vp, _vp, _i, _i,

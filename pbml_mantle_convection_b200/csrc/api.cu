@@ -61,6 +61,7 @@ extern "C" size_t pbmc_sizeof(const char* name) {
   if (!strcmp(name, "pbmc_conv_desc")) return sizeof(pbmc_conv_desc);
   if (!strcmp(name, "pbmc_layer")) return sizeof(pbmc_layer);
   if (!strcmp(name, "pbmc_net")) return sizeof(pbmc_net);
+  if (!strcmp(name, "pbmc_slab_sync")) return sizeof(pbmc_slab_sync);
   return 0;
 }
 

@@ -28,6 +28,60 @@ struct StencilParams {
   float* push_down;
 };
 
+// Cross-rank state of the flag-synchronised slab step (pbmc_advect_diffuse_slab_sync): the global CFL reduction and the
+// ordering of the halo pushes happen INSIDE the update kernel, through 8-byte slots in peer-mapped memory.
+struct SlabSyncArgs {
+  pbmc_slab_sync* self;
+  pbmc_slab_sync* peer[PBMC_MAX_RANKS];  // every rank's block (own included), as mapped into this device's address space
+  int rank, world;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Wait until every rank has published its max|u|,|v| for step `s` (tag == s) in THIS rank's slots and return the
+// global maximum (float bits).  Lane r polls rank r's slot; the acquire also orders the neighbours' ghost-row stores
+// of step s - 1 (issued before their release) before this step's reads.  Whole warp calls it.
+__device__ __forceinline__ uint32_t slab_wait_global_max(const pbmc_slab_sync* self, uint32_t s, int world) {
+  const int lane = threadIdx.x & 31;
+  uint32_t bits = 0u;
+  if (lane < world) {
+    const unsigned long long* slot = &self->slot[s & 1u][lane];
+    unsigned long long v = ld_acquire_sys_u64(slot);
+    if ((uint32_t)(v >> 32) != s) {
+      const unsigned long long t0 = globaltimer_ns();
+      do {
+        __nanosleep(64);
+        v = ld_acquire_sys_u64(slot);
+        if ((uint32_t)(v >> 32) != s && globaltimer_ns() - t0 > 30000000000ull) __trap();  // 30 s: a peer died; fail loudly
+      } while ((uint32_t)(v >> 32) != s);
+    }
+    bits = (uint32_t)v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+  return bits;
+}
+
+// Publish `bits` as this rank's max for step `s` into slot[s & 1][rank] of every rank (threads 0 .. world-1 of a CTA).
+__device__ __forceinline__ void slab_publish(const SlabSyncArgs& a, uint32_t s, uint32_t bits) {
+  if ((int)threadIdx.x < a.world) {
+    __threadfence_system();
+    st_release_sys_u64(&a.peer[threadIdx.x]->slot[s & 1u][a.rank], ((unsigned long long)s << 32) | (unsigned long long)bits);
+  }
+}
+
 __device__ __forceinline__ double cfl_dt(double uvm, double dx_min, double cn_max) {
   // :557-559 verbatim (dt_diffuse reduces to dx_min^2/4)
   const double dt_adv = 0.5 * cn_max * dx_min / uvm;
@@ -192,12 +246,27 @@ __global__ void __launch_bounds__(ST_BX* ST_BY) stencil_kernel(const StencilPara
 // columns by one predicated scalar load each).  No shared memory, no block barrier: every row is one 128-bit
 // load of T, u and v and one 128-bit store, with the next row's loads in flight during the arithmetic --
 // 16 B per cell-update of HBM traffic plus 2/rpw of a row of T for the strip's top and bottom halo.
-__global__ void __launch_bounds__(128) stencil_march_kernel(const StencilParams p, int rpw) {
+//
+// SYNC (pbmc_advect_diffuse_slab_sync, one rank of a row-decomposed grid): no collective call surrounds the kernel.
+//   start  every warp waits until all ranks' maxima for THIS step (tag = steps_done + 1) stand in this rank's slots
+//          -> global max -> dt; the same acquire makes the neighbours' ghost rows of the previous step visible;
+//   end    warp maxima -> local accumulator; the CTA that finishes last publishes (tag + 1, local max) into every
+//          rank's slot of the other parity and advances steps_done.  Two parities suffice: a rank can only
+//          overwrite parity (s & 1) at the end of step s + 1, which it enters only after every rank has published
+//          step s + 1's value, i.e. after every rank has finished step s and consumed the tags of step s.
+template <bool SYNC>
+__global__ void __launch_bounds__(128) stencil_march_kernel(const StencilParams p, int rpw, const SlabSyncArgs sa) {
   const int H = p.H, W = p.W, b = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = (blockIdx.x * 32 + lane) * 4;
   const int y0 = (blockIdx.y * 4 + warp) * rpw;
-  if (y0 >= H) return;  // whole warp
+  uint32_t step = 0u, gmax_bits = 0u;
+  if (SYNC) {
+    step = *reinterpret_cast<volatile const unsigned int*>(&sa.self->steps_done) + 1u;
+    gmax_bits = slab_wait_global_max(sa.self, step, sa.world);
+  }
+  if (!SYNC && y0 >= H) return;  // whole warp
+  const bool warp_on = y0 < H;
   const int y1 = min(y0 + rpw, H);
   const bool act = x0 < W;              // W % 4 == 0: a lane's four columns are all inside or all outside
   const int xs = act ? x0 : W - 4;      // inactive lanes shadow the last float4 (they take part in the shuffles)
@@ -208,10 +277,13 @@ __global__ void __launch_bounds__(128) stencil_march_kernel(const StencilParams 
   float* To = p.T_out + (size_t)b * plane;
 
   double dtd = p.dt_fixed;
-  if (!(dtd > 0.0)) dtd = cfl_dt((double)__uint_as_float(__ldg(p.uvmax_in + (size_t)b * p.member_stride)), p.dx_min, p.cn_max);
+  if (!(dtd > 0.0))
+    dtd = cfl_dt((double)__uint_as_float(SYNC ? gmax_bits : __ldg(p.uvmax_in + (size_t)b * p.member_stride)), p.dx_min, p.cn_max);
   const float dt = (float)dtd;
   if (p.dt_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dt_out[b] = dtd;
   const float raq = p.mem ? p.mem[b].raq : 0.f;
+  float m = 0.f;
+  if (warp_on) {
   const float4 ixl = ldg4(p.xcoef + xs), ixr = ldg4(p.xcoef + W + xs), ixc = ldg4(p.xcoef + 2 * W + xs);
   const float xl[4] = {ixl.x, ixl.y, ixl.z, ixl.w}, xr[4] = {ixr.x, ixr.y, ixr.z, ixr.w}, xcn[4] = {ixc.x, ixc.y, ixc.z, ixc.w};
   const bool need_l = lane == 0 && x0 > 0, need_r = (lane == 31 || x0 + 4 >= W) && x0 + 4 < W;
@@ -224,7 +296,6 @@ __global__ void __launch_bounds__(128) stencil_march_kernel(const StencilParams 
   float4 uc = row4(ub, y0), vc = row4(vb, y0);
   float hl = need_l ? __ldg(Tb + (size_t)y0 * W + x0 - 1) : 0.f, hr = need_r ? __ldg(Tb + (size_t)y0 * W + x0 + 4) : 0.f;
   float cyt = __ldg(p.ycoef + y0), cyb = __ldg(p.ycoef + H + y0), cyc = __ldg(p.ycoef + 2 * H + y0);
-  float m = 0.f;
   for (int r = y0; r < y1; ++r) {
     // next row's operands first: they are in flight during this row's arithmetic
     const int rn = r + 1;
@@ -283,10 +354,50 @@ __global__ void __launch_bounds__(128) stencil_march_kernel(const StencilParams 
     Tm = Tc; Tc = Tp; Tp = Tn;
     uc = un; vc = vn; hl = hln; hr = hrn; cyt = cytn; cyb = cybn; cyc = cycn;
   }
-  if (p.uvmax_out != nullptr) {
-    m = warp_max(act ? m : 0.f);
-    if (lane == 0 && m > 0.f) atomic_max_nonneg(p.uvmax_out + (size_t)b * p.member_stride, m);
+  if (!act) m = 0.f;
+  }  // warp_on
+  if (!SYNC) {
+    if (p.uvmax_out != nullptr) {
+      m = warp_max(m);
+      if (lane == 0 && m > 0.f) atomic_max_nonneg(p.uvmax_out + (size_t)b * p.member_stride, m);
+    }
+    return;
   }
+  // ---- SYNC epilogue: local max, CTA count, and -- by the CTA that finishes last -- the publication for the next step
+  __shared__ uint32_t s_last, s_bits;
+  m = warp_max(m);
+  if (lane == 0 && m > 0.f) atomic_max_nonneg(&sa.self->local_max, m);
+  __threadfence_system();  // this thread's ghost-row stores into the neighbours (and the atomic) before the CTA is counted
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t total = gridDim.x * gridDim.y * gridDim.z;
+    const uint32_t prev = atomicAdd(&sa.self->ctas_done, 1u);
+    s_last = prev == total - 1u;
+    if (s_last) {
+      __threadfence();
+      s_bits = atomicExch(&sa.self->local_max, 0u);
+      sa.self->ctas_done = 0u;
+    }
+  }
+  __syncthreads();
+  if (s_last) {
+    slab_publish(sa, step + 1u, s_bits);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      *reinterpret_cast<volatile unsigned int*>(&sa.self->steps_done) = step;
+    }
+  }
+}
+
+// First publication of a run (and after every change of the velocity field): this rank's max|u|,|v| -- left in
+// self->local_max by uvmax_kernel -- goes out with tag steps_done + 1.
+__global__ void slab_publish_kernel(const SlabSyncArgs sa) {
+  __shared__ uint32_t s_bits;
+  const uint32_t step = *reinterpret_cast<volatile const unsigned int*>(&sa.self->steps_done) + 1u;
+  if (threadIdx.x == 0) s_bits = atomicExch(&sa.self->local_max, 0u);
+  __syncthreads();
+  slab_publish(sa, step, s_bits);
 }
 
 // ---- stand-alone interior max|u|,|v| (only when no producer supplied it)
@@ -433,12 +544,13 @@ extern "C" int pbmc_stencil_coefs(const double* coord, int n, double wall_lo, do
 static int advect_diffuse_launch(const float* T, const float* u, const float* v, const float* x, const float* y,
                                  const pbmc_member* members, const uint32_t* uvmax_in, int member_stride, double dx_min,
                                  double cn_max, double dt_fixed, float* T_out, uint32_t* uvmax_out, double* dt_out, int B, int H,
-                                 int W, int has_up, int has_down, float* peer_up, float* peer_down, void* stream) {
+                                 int W, int has_up, int has_down, float* peer_up, float* peer_down, void* stream,
+                                 const SlabSyncArgs* sync = nullptr) {
   if (!T || !u || !v || !x || !y || !T_out) return PBMC_ERR_NULL_POINTER;
-  if (!(dt_fixed > 0.0) && !uvmax_in) return PBMC_ERR_NULL_POINTER;
+  if (!(dt_fixed > 0.0) && !uvmax_in && !sync) return PBMC_ERR_NULL_POINTER;
   if (B <= 0 || H < 3 || W < 3 || (member_stride != 0 && member_stride != 1)) return PBMC_ERR_BAD_SHAPE;
   if (T == T_out) return PBMC_ERR_UNSUPPORTED;  // out-of-place only (neighbours are read)
-  const bool slab = has_up || has_down || peer_up || peer_down;
+  const bool slab = has_up || has_down || peer_up || peer_down || sync != nullptr;
   StencilParams p{T, u, v, x, y, members, uvmax_in, uvmax_out, T_out, dt_out, dx_min, cn_max, dt_fixed, member_stride, H, W,
                   has_up ? 1 : 0, has_down ? H - 1 : H, has_up ? 1 : -1, has_down ? H - 2 : -1, peer_up, peer_down};
   const bool vec = (W % 4 == 0) && aligned16(T) && aligned16(u) && aligned16(v) && aligned16(T_out);
@@ -451,11 +563,14 @@ static int advect_diffuse_launch(const float* T, const float* u, const float* v,
     const int rpw = (int)(want < 4 ? 4 : (want > 64 ? 64 : want));
     dim3 grid(strips, cdiv(H, 4 * rpw), B);
     if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
-    stencil_march_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, rpw);
+    if (sync != nullptr)
+      stencil_march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(p, rpw, *sync);
+    else
+      stencil_march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(p, rpw, SlabSyncArgs{});
     PBMC_CHECK_LAUNCH("stencil_march_kernel");
     return PBMC_OK;
   }
-  if (slab) return PBMC_ERR_UNSUPPORTED;  // the slab form needs 16-byte aligned rows (W % 4 == 0)
+  if (slab || sync) return PBMC_ERR_UNSUPPORTED;  // the slab form needs 16-byte aligned rows (W % 4 == 0)
   const int TW = vec ? ST_BX * 4 : ST_BX;
   dim3 grid(cdiv(W, TW), cdiv(H, ST_TH), B);
   if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
@@ -483,6 +598,49 @@ extern "C" int pbmc_advect_diffuse_slab(const float* T, const float* u, const fl
   if ((peer_up_ghost_row && !has_up) || (peer_down_ghost_row && !has_down)) return PBMC_ERR_BAD_SHAPE;
   return advect_diffuse_launch(T, u, v, x, y, members, uvmax_in, 0, dx_min, cn_max, dt_fixed, T_out, uvmax_out, dt_out, 1, H, W,
                                has_up, has_down, peer_up_ghost_row, peer_down_ghost_row, stream);
+}
+
+static int make_sync_args(pbmc_slab_sync* self, pbmc_slab_sync* const* peers_h, int rank, int world, SlabSyncArgs& a) {
+  if (!self || !peers_h) return PBMC_ERR_NULL_POINTER;
+  if (world < 1 || world > PBMC_MAX_RANKS || rank < 0 || rank >= world) return PBMC_ERR_BAD_SHAPE;
+  a.self = self; a.rank = rank; a.world = world;
+  for (int r = 0; r < PBMC_MAX_RANKS; ++r) a.peer[r] = nullptr;
+  for (int r = 0; r < world; ++r) {
+    if (!peers_h[r]) return PBMC_ERR_NULL_POINTER;
+    if (reinterpret_cast<uintptr_t>(peers_h[r]) & 7) return PBMC_ERR_MISALIGNED;
+    a.peer[r] = peers_h[r];
+  }
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_slab_sync_publish(const float* u, const float* v, int H, int W, pbmc_slab_sync* self,
+                                      pbmc_slab_sync* const* peers_h, int rank, int world, void* stream) {
+  if (!u || !v) return PBMC_ERR_NULL_POINTER;
+  if (H < 3 || W < 3) return PBMC_ERR_BAD_SHAPE;
+  SlabSyncArgs a;
+  const int rc = make_sync_args(self, peers_h, rank, world, a);
+  if (rc != PBMC_OK) return rc;
+  // interior rows 1 .. H-2 of the local array = this rank's owned non-wall rows (local rows 0 / H-1 are ghosts or walls)
+  const size_t plane = (size_t)H * W;
+  const unsigned nb = (unsigned)min((size_t)1184, (plane + 255) / 256);
+  uvmax_kernel<<<dim3(nb, 1), 256, 0, (cudaStream_t)stream>>>(u, v, &self->local_max, 0, H, W);
+  PBMC_CHECK_LAUNCH("uvmax_kernel");
+  slab_publish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+  PBMC_CHECK_LAUNCH("slab_publish_kernel");
+  return PBMC_OK;
+}
+
+extern "C" int pbmc_advect_diffuse_slab_sync(const float* T, const float* u, const float* v, const float* x, const float* y,
+                                             const pbmc_member* members, double dx_min, double cn_max, float* T_out,
+                                             double* dt_out, int H, int W, int has_up, int has_down,
+                                             float* peer_up_ghost_row, float* peer_down_ghost_row, pbmc_slab_sync* self,
+                                             pbmc_slab_sync* const* peers_h, int rank, int world, void* stream) {
+  if ((peer_up_ghost_row && !has_up) || (peer_down_ghost_row && !has_down)) return PBMC_ERR_BAD_SHAPE;
+  SlabSyncArgs a;
+  const int rc = make_sync_args(self, peers_h, rank, world, a);
+  if (rc != PBMC_OK) return rc;
+  return advect_diffuse_launch(T, u, v, x, y, members, nullptr, 0, dx_min, cn_max, 0.0, T_out, nullptr, dt_out, 1, H, W, has_up,
+                               has_down, peer_up_ghost_row, peer_down_ghost_row, stream, &a);
 }
 
 extern "C" int pbmc_uvmax(const float* u, const float* v, uint32_t* uvmax, int member_stride, int B, int H, int W,

@@ -352,6 +352,39 @@ def advect_diffuse_slab(T, u, v, xcoef, ycoef, members, uvmax, dx_min, cn_max, T
     return T_out, dt_out
 
 
+SLAB_SYNC_BYTES = C.sizeof(L.SlabSync)
+
+
+def _peer_array(peer_ptrs):
+    return (C.c_void_p * len(peer_ptrs))(*[int(q) for q in peer_ptrs])
+
+
+def slab_sync_publish(u, v, self_ptr, peer_ptrs, rank):
+    """First publication of a flag-synchronised slab run: this rank's max|u|,|v| (owned interior rows of the local
+    [1,rows,W] arrays) goes into every rank's slot with tag steps_done + 1 (pbmc_slab_sync_publish)."""
+    _chk_cuda(u, v)
+    _, H, W = u.shape
+    L.check(L.load().pbmc_slab_sync_publish(L.ptr(u), L.ptr(v), H, W, int(self_ptr), _peer_array(peer_ptrs), int(rank),
+                                            len(peer_ptrs), L.stream_ptr(u.device)), "pbmc_slab_sync_publish")
+
+
+def advect_diffuse_slab_sync(T, u, v, xcoef, ycoef, members, dx_min, cn_max, T_out, dt_out, has_up, has_down,
+                             peer_up_row_ptr, peer_down_row_ptr, self_ptr, peer_ptrs, rank):
+    """One time step of one rank's slab with the dt reduction and the halo exchange inside the kernel
+    (pbmc_advect_diffuse_slab_sync): no collective call, one launch.  self_ptr / peer_ptrs: device addresses of the
+    ranks' pbmc_slab_sync blocks (peer-mapped memory)."""
+    _chk_cuda(T, u, v, xcoef, ycoef, T_out)
+    _, H, W = T.shape
+    assert xcoef.shape == (3, W) and ycoef.shape == (3, H) and T.shape[0] == 1
+    L.check(L.load().pbmc_advect_diffuse_slab_sync(L.ptr(T), L.ptr(u), L.ptr(v), L.ptr(xcoef), L.ptr(ycoef), L.ptr(members),
+                                                   float(dx_min), float(cn_max), L.ptr(T_out), L.ptr(dt_out), H, W,
+                                                   int(bool(has_up)), int(bool(has_down)), int(peer_up_row_ptr) or None,
+                                                   int(peer_down_row_ptr) or None, int(self_ptr), _peer_array(peer_ptrs),
+                                                   int(rank), len(peer_ptrs), L.stream_ptr(T.device)),
+            "pbmc_advect_diffuse_slab_sync")
+    return T_out, dt_out
+
+
 def advect_diffuse_fields(T, u, v, xc, yc, raq_field, members, uvmax, dx_min_dev, cn_max, per_member_dt=False,
                           dt_fixed_dev=None):
     """General form (coordinates as float64 fields, RaQ optionally a field; ADNet.forward semantics)."""

@@ -19,6 +19,7 @@ def main():
     W = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     halo = sys.argv[4] if len(sys.argv) > 4 else "nccl"
+    dt_sync = sys.argv[5] if len(sys.argv) > 5 else "flags"  # p2p only: "flags" = reduction inside the kernel, "nccl" = all_reduce
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -28,7 +29,7 @@ def main():
     psi = np.sin(np.pi * xc / 4 * 3) * np.sin(np.pi * yc)
     u = (np.gradient(psi, axis=0) * 1e3 * H).astype(np.float32)
     v = (-np.gradient(psi, axis=1) * 1e3 * W).astype(np.float32)
-    st = MG.SlabStencil(H, W, xc[0], yc[:, 0], rank, world, dev, raq=2.0, halo=halo)
+    st = MG.SlabStencil(H, W, xc[0], yc[:, 0], rank, world, dev, raq=2.0, halo=halo, dt_sync=dt_sync)
     st.scatter(T, u, v)
     st.step(3)  # warm-up (NCCL communicators, module load)
     st.scatter(T, u, v)
@@ -48,8 +49,9 @@ def main():
         ref.scatter(T, u, v)
         ref.step(steps)
         ok = bool(torch.equal(ref.gather(), full))
-        print(f"slab_check H={H} W={W} world={world} steps={steps} halo={halo}: identical_to_single_gpu={ok} "
+        print(f"slab_check H={H} W={W} world={world} steps={steps} halo={halo} dt_sync={st.dt_sync}: identical_to_single_gpu={ok} "
               f"{H * W * steps / (ms.item() * 1e-3):.4g} cell-updates/s ({ms.item() / steps:.3f} ms/step)", flush=True)
+    st.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
