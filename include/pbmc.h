@@ -54,6 +54,7 @@ enum { PBMC_ACT_NONE = 0, PBMC_ACT_GELU = 1 };
  * padding, xform NONE, nblk = 4, on the ROW_F16X2 kernel (AUTO picks it). */
 enum { PBMC_LAYOUT_BLOCKED = 0, PBMC_LAYOUT_STAGED16 = 1 };
 enum { PBMC_HEAD_CURL = 0, PBMC_HEAD_MAE = 1 };
+enum { PBMC_TRUNK_AUTO = 0, PBMC_TRUNK_PER_LAYER = 1 };
 /* conv implementation selector: FFMA = fp32 CUDA cores; UMMA_* = tcgen05 tensor cores:
  * 3XTF32 / F16X2 split every operand into hi + lo (tf32 resp. fp16) and issue 3 passes --
  * fp32-grade accuracy; BF16 = single pass with bf16 operands (looser, stated bound).
@@ -260,11 +261,35 @@ typedef struct {
 typedef struct {
   int levels, repeats, c_i, c_h, c_o, ksize, pad_mode, head_kind, p_pred, conv_impl;
   float a_bound;
-  int reserved;
+  int trunk_mode; /* PBMC_TRUNK_AUTO: the R layers of a level as one persistent launch where the grid can be resident
+                     (pbmc_trunk_fwd), else one launch per layer; PBMC_TRUNK_PER_LAYER: always one launch per layer */
   pbmc_layer conv0;
   pbmc_layer trunk[PBMC_MAX_LEVELS * PBMC_MAX_REPEATS]; /* [level][repeat] */
   pbmc_layer conv1, conv2, conv3;
 } pbmc_net;
+
+/* ------------------------------------------------------------------ A3/A5: the R FluidLayers of one pyramid level, ONE launch
+ * NewFluidNet.forward pytorch_networks_convae.py:1323-1324 (`for r in range(R): y1 = convs[l][r](y1)`), FluidLayer :790-799.
+ * Persistent kernel (csrc/conv_trunk.cu): a CTA keeps its strip, TMEM and barriers for all R layers; GroupNorm's
+ * whole-image reduction between two layers is a grid-wide arrive/poll counter.  16 hidden channels, 3x3.
+ *   src0    the level's input (xform NONE, or GN_GELU of its producer)
+ *   layers  HOST array [R]: wpk_row, bias and the GroupNorm affine (gamma, beta) of each layer's OUTPUT
+ *   ping    layer r writes its raw output to ping[r & 1]  -> the level's result is ping[(R-1) & 1], to be read with
+ *           GN_GELU(stats + (R-1)*B*8, layers[R-1].gamma/beta) by its consumers
+ *   stats   [R][B][4][2] doubles, sync [B] unsigned: scratch, zeroed by the call unless pre_zeroed != 0
+ *   max_ctas  CTA budget (0 = 148): the WHOLE grid must be resident at once, PBMC_ERR_UNSUPPORTED if it cannot be
+ *           (the caller then runs the layers one by one with pbmc_conv_fwd) */
+typedef struct {
+  pbmc_src src0;
+  const pbmc_layer* layers;
+  float* ping[2];
+  double* stats;
+  unsigned int* sync;
+  int R, B, H, W, pad_mode, impl, max_ctas, pre_zeroed;
+} pbmc_trunk_desc;
+int pbmc_trunk_fwd(const pbmc_trunk_desc* desc_h, void* stream);
+/* 1 if pbmc_trunk_fwd would take this configuration (shape, budget), else 0 */
+int pbmc_trunk_supported(const pbmc_trunk_desc* desc_h);
 
 typedef struct pbmc_ctx pbmc_ctx; /* internal streams + events only; owns no tensor memory */
 int pbmc_ctx_create(pbmc_ctx** out);

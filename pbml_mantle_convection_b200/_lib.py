@@ -20,6 +20,7 @@ XFORM_NONE, XFORM_GN_GELU, XFORM_GN, XFORM_GELU = 0, 1, 2, 3
 LAYOUT_BLOCKED, LAYOUT_STAGED16 = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
 HEAD_CURL, HEAD_MAE = 0, 1
+TRUNK_MODE = {"auto": 0, "per_layer": 1}
 CONV_IMPL = {"auto": 0, "ffma": 1, "umma_3xtf32": 2, "umma_bf16": 3, "umma_f16x2": 4,
              "row_f16x2": 5, "row_bf16": 6, "mux_f16x2": 7, "mux_bf16": 8}
 
@@ -50,7 +51,7 @@ class Layer(C.Structure):
 class Net(C.Structure):
     _fields_ = [("levels", C.c_int), ("repeats", C.c_int), ("c_i", C.c_int), ("c_h", C.c_int), ("c_o", C.c_int),
                 ("ksize", C.c_int), ("pad_mode", C.c_int), ("head_kind", C.c_int), ("p_pred", C.c_int),
-                ("conv_impl", C.c_int), ("a_bound", C.c_float), ("reserved", C.c_int), ("conv0", Layer),
+                ("conv_impl", C.c_int), ("a_bound", C.c_float), ("trunk_mode", C.c_int), ("conv0", Layer),
                 ("trunk", Layer * (MAX_LEVELS * MAX_REPEATS)), ("conv1", Layer), ("conv2", Layer), ("conv3", Layer)]
 
 
@@ -62,7 +63,13 @@ class SlabSync(C.Structure):
                 ("local_max", C.c_uint), ("reserved", C.c_uint)]
 
 
-_STRUCTS = {"pbmc_slab_sync": SlabSync, "pbmc_member": Member, "pbmc_src": Src, "pbmc_conv_desc": ConvDesc, "pbmc_layer": Layer, "pbmc_net": Net}
+class TrunkDesc(C.Structure):
+    _fields_ = [("src0", Src), ("layers", C.POINTER(Layer)), ("ping", C.c_void_p * 2), ("stats", C.c_void_p),
+                ("sync", C.c_void_p), ("R", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("pad_mode", C.c_int),
+                ("impl", C.c_int), ("max_ctas", C.c_int), ("pre_zeroed", C.c_int)]
+
+
+_STRUCTS = {"pbmc_trunk_desc": TrunkDesc, "pbmc_slab_sync": SlabSync, "pbmc_member": Member, "pbmc_src": Src, "pbmc_conv_desc": ConvDesc, "pbmc_layer": Layer, "pbmc_net": Net}
 
 # name -> (restype, argtypes); every symbol declared in include/pbmc.h
 _vp, _i, _d, _f, _sz = C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_size_t
@@ -75,6 +82,8 @@ SIGNATURES = {
     "pbmc_unpack_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "pbmc_build_input": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pbmc_conv_fwd": (_i, [C.POINTER(ConvDesc), _vp]),
+    "pbmc_trunk_fwd": (_i, [C.POINTER(TrunkDesc), _vp]),
+    "pbmc_trunk_supported": (_i, [C.POINTER(TrunkDesc)]),
     "pbmc_avgpool2": (_i, [C.POINTER(Src), _vp, _i, _i, _i, _vp]),
     "pbmc_bicubic_up": (_i, [C.POINTER(Src), _vp, _i, _i, _i, _i, _i, _vp]),
     "pbmc_bicubic_up_staged": (_i, [C.POINTER(Src), _vp, _i, _i, _i, _i, _i, _vp]),

@@ -25,6 +25,8 @@ bool conv_row_supported(const pbmc_conv_desc& d);
 int conv_mux_dispatch(const pbmc_conv_desc& d, cudaStream_t st);  // conv_mux.cu
 bool conv_mux_supported(const pbmc_conv_desc& d);
 bool conv_mux_one_wave(const pbmc_conv_desc& d);
+int conv_trunk_dispatch(const pbmc_trunk_desc& t, cudaStream_t st);  // conv_trunk.cu
+bool conv_trunk_supported(const pbmc_trunk_desc& t);
 extern thread_local int g_conv_pdl_next;  // conv_mux.cu: the next mux launch uses programmatic dependent launch
 
 }  // namespace pbmc
@@ -62,6 +64,7 @@ extern "C" size_t pbmc_sizeof(const char* name) {
   if (!strcmp(name, "pbmc_layer")) return sizeof(pbmc_layer);
   if (!strcmp(name, "pbmc_net")) return sizeof(pbmc_net);
   if (!strcmp(name, "pbmc_slab_sync")) return sizeof(pbmc_slab_sync);
+  if (!strcmp(name, "pbmc_trunk_desc")) return sizeof(pbmc_trunk_desc);
   return 0;
 }
 
@@ -146,6 +149,17 @@ extern "C" int pbmc_conv_fwd(const pbmc_conv_desc* d, void* stream) {
   return conv_enqueue(*d, (cudaStream_t)stream);
 }
 
+extern "C" int pbmc_trunk_fwd(const pbmc_trunk_desc* t, void* stream) {
+  if (!t || !t->layers) return PBMC_ERR_NULL_POINTER;
+  if (t->pad_mode < PBMC_PAD_ZEROS || t->pad_mode > PBMC_PAD_REFLECT) return PBMC_ERR_UNSUPPORTED;
+  if (t->pad_mode == PBMC_PAD_REFLECT && (t->H <= 1 || t->W <= 1)) return PBMC_ERR_BAD_SHAPE;
+  if (!t->ping[0]) return PBMC_ERR_NULL_POINTER;
+  int rc = check_device_ptr(t->ping[0]);
+  if (rc != PBMC_OK) return rc;
+  return conv_trunk_dispatch(*t, (cudaStream_t)stream);
+}
+extern "C" int pbmc_trunk_supported(const pbmc_trunk_desc* t) { return t && t->layers && conv_trunk_supported(*t) ? 1 : 0; }
+
 extern "C" int pbmc_ctx_create(pbmc_ctx** out) {
   if (!out) return PBMC_ERR_NULL_POINTER;
   pbmc_ctx* c = new pbmc_ctx();
@@ -182,7 +196,7 @@ struct Plan {
   int L, R, CB, CIB, COB3;
   int Hl[PBMC_MAX_LEVELS], Wl[PBMC_MAX_LEVELS];
   size_t inp, x0, pooled[PBMC_MAX_LEVELS], ping[PBMC_MAX_LEVELS][2], up[PBMC_MAX_LEVELS], h1, h2, h3;
-  size_t stats, stats_bytes, chan_sum, uvmax, total;
+  size_t stats, stats_bytes, chan_sum, sync, uvmax, total;  // sync: [L][B] grid-barrier counters of the persistent trunk kernels
   // stats slots: 0 = conv0, 1 + l*R + r = trunk, 1 + L*R = conv1
   size_t stat_off(int slot, int B) const { return stats + (size_t)slot * B * CB * 2 * sizeof(double); }
 };
@@ -216,11 +230,13 @@ int make_plan(const pbmc_net& n, int B, int H, int W, Plan& P) {
   P.h2 = take((size_t)B * P.CB * px * 16);
   P.h3 = take((size_t)B * P.COB3 * px * 16);
   const int nslots = 2 + P.L * P.R;
-  P.stats_bytes = (size_t)nslots * B * P.CB * 2 * sizeof(double) + (size_t)B * P.COB3 * 4 * sizeof(double) +
+  const size_t sync_bytes = ((size_t)P.L * B * sizeof(uint32_t) + 7) & ~(size_t)7;
+  P.stats_bytes = (size_t)nslots * B * P.CB * 2 * sizeof(double) + (size_t)B * P.COB3 * 4 * sizeof(double) + sync_bytes +
                   (size_t)2 * B * sizeof(uint32_t);
   P.stats = take(P.stats_bytes);
   P.chan_sum = P.stats + (size_t)nslots * B * P.CB * 2 * sizeof(double);
-  P.uvmax = P.chan_sum + (size_t)B * P.COB3 * 4 * sizeof(double);
+  P.sync = P.chan_sum + (size_t)B * P.COB3 * 4 * sizeof(double);
+  P.uvmax = P.sync + sync_bytes;
   P.total = off;
   return PBMC_OK;
 }
@@ -351,6 +367,23 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
       }
     }
   }
+  // Persistent trunk kernels (csrc/conv_trunk.cu: the R layers of a level in one launch, grid barrier between layers)
+  // need EVERY CTA of EVERY level resident at once: taken only when all levels have a budget and the budgets fit 148 SMs.
+  bool trunk_persistent = n.trunk_mode == PBMC_TRUNK_AUTO && CB == 4 && n.ksize == 3;
+  {
+    int total = 0;
+    for (int l = 0; l < L && trunk_persistent; ++l) {
+      const int bud = L > 1 ? cta_budget[l] : 148;
+      pbmc_trunk_desc t;
+      memset(&t, 0, sizeof(t));
+      t.src0.nblk = CB; t.src0.layout = PBMC_LAYOUT_BLOCKED; t.src0.xform = PBMC_XFORM_NONE;
+      t.layers = &n.trunk[l * PBMC_MAX_REPEATS];
+      t.R = R; t.B = B; t.H = P.Hl[l]; t.W = P.Wl[l]; t.impl = n.conv_impl; t.max_ctas = bud;
+      trunk_persistent = bud > 0 && conv_trunk_supported(t);
+      total += bud;
+    }
+    trunk_persistent = trunk_persistent && total <= 148;
+  }
   const float* level_in[PBMC_MAX_LEVELS];
   level_in[0] = F(P.x0);
   for (int l = 0; l < L; ++l) {
@@ -366,7 +399,21 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
       level_in[l] = F(P.pooled[l]);
     }
     const double invc = 1.0 / (4.0 * Hl * Wl);
-    for (int r = 0; r < R; ++r) {
+    if (trunk_persistent) {
+      pbmc_trunk_desc t;
+      memset(&t, 0, sizeof(t));
+      t.src0 = (l == 0) ? make_src(F(P.x0), CB, PBMC_XFORM_GN_GELU, S(0), &n.conv0, invc)
+                        : make_src(level_in[l], CB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
+      t.layers = &n.trunk[l * PBMC_MAX_REPEATS];
+      t.ping[0] = F(P.ping[l][0]); t.ping[1] = F(P.ping[l][1]);
+      t.stats = S(1 + l * R);
+      t.sync = reinterpret_cast<unsigned int*>(ws + P.sync) + (size_t)l * B;
+      t.R = R; t.B = B; t.H = Hl; t.W = Wl; t.pad_mode = n.pad_mode; t.impl = n.conv_impl;
+      t.max_ctas = L > 1 ? cta_budget[l] : 148;
+      t.pre_zeroed = 1;  // the statistics / counter region was zeroed by the memset at the top of the forward
+      RC(conv_trunk_dispatch(t, sl));
+    }
+    for (int r = 0; r < R && !trunk_persistent; ++r) {
       const pbmc_layer& Lr = n.trunk[l * PBMC_MAX_REPEATS + r];
       fill_conv(d, n, Lr, B, Hl, Wl, F(P.ping[l][r & 1]), S(1 + l * R + r), nullptr, PBMC_ACT_NONE);
       d.max_ctas = cta_budget[l];

@@ -93,6 +93,39 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   x1 = fmaf(-fabsf(x1), e1, fmaxf(x1, 0.f));
 }
 
+// NP packed pairs of exact-erf GELUs in lock step: the same polynomial and rounding as gelu_erf2 (common.cuh),
+// written so that the NP dependent FFMA2 chains are interleaved in program order.
+template <int NP>
+__device__ __forceinline__ void gelu_erf2n(float* x) {
+  uint64_t t[NP], q[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    t[k] = f2_pack(fminf(fabsf(x[2 * k]), 6.6f), fminf(fabsf(x[2 * k + 1]), 6.6f));
+    q[k] = f2_pack(-2.2756834377020336e-06f, -2.2756834377020336e-06f);
+  }
+#define PBMC_F2STEP(c)                                          \
+  _Pragma("unroll") for (int k = 0; k < NP; ++k) q[k] = f2_fma(q[k], t[k], f2_pack(c, c));
+  PBMC_F2STEP(3.296563960267106e-05f)
+  PBMC_F2STEP(-0.000157266929481836f)
+  PBMC_F2STEP(-0.0002025088577467934f)
+  PBMC_F2STEP(0.007142822415561599f)
+  PBMC_F2STEP(-0.05254646501180134f)
+  PBMC_F2STEP(-0.4591930475265861f)
+  PBMC_F2STEP(-1.1511069423662477f)
+  PBMC_F2STEP(-0.9999999590055544f)
+#undef PBMC_F2STEP
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    float q0, q1, e0, e1;
+    f2_unpack(q[k], q0, q1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+    const float a = x[2 * k], b = x[2 * k + 1];
+    x[2 * k] = fmaf(-fabsf(a), e0, fmaxf(a, 0.f));
+    x[2 * k + 1] = fmaf(-fabsf(b), e1, fmaxf(b, 0.f));
+  }
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // source index for a padded coordinate; returns -1 for a zero-padded tap

@@ -53,6 +53,7 @@ class SurrogateEngine:
             L.check(L.load().pbmc_ctx_create(C.byref(self._ctx)), "pbmc_ctx_create")
         self._ws = {}
         self.conv_impl = "auto"
+        self.trunk_mode = "auto"  # "auto": persistent per-level trunk kernel where it fits; "per_layer": one launch per layer
         self.refresh()
 
     def __del__(self):
@@ -117,6 +118,7 @@ class SurrogateEngine:
         n.head_kind = L.HEAD_CURL if m.loss_type == "curl" else L.HEAD_MAE
         n.p_pred = int(bool(m.p_pred))
         n.conv_impl = L.CONV_IMPL[self.conv_impl]
+        n.trunk_mode = L.TRUNK_MODE[self.trunk_mode]
         n.a_bound = float(m.a_bound)
         n.conv0 = self.conv0.c()
         for l in range(m.levels):
@@ -129,6 +131,12 @@ class SurrogateEngine:
         if impl not in L.CONV_IMPL:
             raise ValueError(impl)
         self.conv_impl = impl
+        self._build_desc()
+
+    def set_trunk_mode(self, mode):
+        if mode not in L.TRUNK_MODE:
+            raise ValueError(mode)
+        self.trunk_mode = mode
         self._build_desc()
 
     # -------------------------------------------------------------- workspace
@@ -152,7 +160,7 @@ class SurrogateEngine:
         """Everything a captured graph of this engine bakes in besides its own buffers: packed-weight identity, conv
         implementation, workspace address.  A change in any of them must force a re-capture."""
         self.refresh()
-        return (self._key, self.conv_impl, self.workspace(B, H, W).data_ptr())
+        return (self._key, self.conv_impl, self.trunk_mode, self.workspace(B, H, W).data_ptr())
 
     # -------------------------------------------------------------- forward
     def forward_blocked(self, inp_blocked, members=None, want_uvmax=False):

@@ -229,6 +229,37 @@ def conv_fwd(sources, wpk, bias, cout, ksize, pad_mode, epi_act=L.ACT_NONE, want
     return out, stats, csum
 
 
+def trunk_fwd(src: Source, layers, pad_mode, impl="auto", max_ctas=0, ping=None, stats=None, sync=None):
+    """The R FluidLayers of one pyramid level in ONE persistent launch (pbmc_trunk_fwd, csrc/conv_trunk.cu).
+    `layers`: objects with .wpk_row, .bias, .gamma, .beta, .cout, .ksize, .cin_blks (engine._PackedLayer) -- each layer's
+    GroupNorm affine is applied by ITS consumer.  Returns (raw output of the last layer [B,4,H,W,4], its GroupNorm sums
+    [B,4,2], all sums [R,B,4,2]); raises PbmcError(unsupported) if the grid cannot be resident at once."""
+    t0 = src.t
+    B, CB, H, W, _ = t0.shape
+    dev = t0.device
+    R = len(layers)
+    arr = (L.Layer * R)()
+    for r, lay in enumerate(layers):
+        arr[r].wpk, arr[r].wpk_umma, arr[r].wpk_row = L.ptr(getattr(lay, "wpk", None)), None, L.ptr(lay.wpk_row)
+        arr[r].bias, arr[r].gamma, arr[r].beta = L.ptr(lay.bias), L.ptr(lay.gamma), L.ptr(lay.beta)
+        arr[r].cin_blks, arr[r].cout, arr[r].ksize = lay.cin_blks, lay.cout, lay.ksize
+    if ping is None:
+        ping = [torch.empty(B, 4, H, W, 4, dtype=torch.float32, device=dev) for _ in range(2)]
+    if stats is None:
+        stats = torch.empty(R, B, 4, 2, dtype=torch.float64, device=dev)
+    if sync is None:
+        sync = torch.empty(B, dtype=torch.int32, device=dev)
+    t = L.TrunkDesc()
+    t.src0, t.layers = src.c(), arr
+    t.ping[0], t.ping[1] = L.ptr(ping[0]), L.ptr(ping[1])
+    t.stats, t.sync = L.ptr(stats), L.ptr(sync)
+    t.R, t.B, t.H, t.W = R, B, H, W
+    t.pad_mode = L.PAD[pad_mode] if isinstance(pad_mode, str) else int(pad_mode)
+    t.impl, t.max_ctas, t.pre_zeroed = L.CONV_IMPL[impl], int(max_ctas), 0
+    L.check(L.load().pbmc_trunk_fwd(C.byref(t), L.stream_ptr(dev)), "pbmc_trunk_fwd")
+    return ping[(R - 1) & 1], stats[R - 1], stats
+
+
 # ------------------------------------------------------------------ pyramid
 def avgpool2(src: Source) -> torch.Tensor:
     B, CB, H, W, _ = src.t.shape

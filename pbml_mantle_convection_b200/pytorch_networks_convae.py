@@ -189,6 +189,7 @@ class _FluidNetBase(nn.Module):
                 self.conv.append(BoundaryLearnedConvolution2D(c_h, co, k=f, use_symm=use_symm))
         self._engines = {}
         self.conv_impl = "auto"  # "auto" | "ffma" | "umma_3xtf32" | "umma_bf16"
+        self.trunk_mode = "auto"  # "auto": one persistent launch per pyramid level where it fits | "per_layer"
         self.use_cuda_graph = True  # learned-boundary networks: replay the module-level forward as one CUDA graph
 
     # nn.Module bookkeeping: engines hold device buffers, never parameters
@@ -199,6 +200,8 @@ class _FluidNetBase(nn.Module):
             eng = self._engines[key] = SurrogateEngine(self, device)
         if eng.conv_impl != self.conv_impl:
             eng.set_conv_impl(self.conv_impl)
+        if eng.trunk_mode != self.trunk_mode:
+            eng.set_trunk_mode(self.trunk_mode)
         return eng
 
     def __getstate__(self):  # engines are not picklable / deep-copyable

@@ -602,3 +602,69 @@ def test_error_codes_on_device():
     with pytest.raises(L.PbmcError):  # reflect needs size > pad
         ops.conv_fwd([ops.Source(torch.zeros(1, 1, 1, 8, 4, device=DEV))], torch.zeros(1, 1, 9, 4, 16, device=DEV),
                      torch.zeros(4, device=DEV), 4, 3, "reflect")
+
+
+class _Lay:
+    """Minimal stand-in for engine._PackedLayer (what ops.trunk_fwd reads)."""
+
+    def __init__(self, w, b, g, be):
+        self.wpk = ops.pack_conv_weight(cu(w), [16])
+        self.wpk_row = ops.pack_conv_weight_row(cu(w), [16])
+        self.bias, self.gamma, self.beta = ops.pad_vec(cu(b), 16, DEV), cu(g).float().contiguous(), cu(be).float().contiguous()
+        self.cin_blks, self.cout, self.ksize = 4, 16, 3
+
+
+@pytest.mark.parametrize("B,H,W,R,pad,xform0,max_ctas", [
+    (1, 40, 130, 4, "replicate", True, 0), (2, 33, 256, 3, "zeros", False, 0), (1, 70, 300, 4, "reflect", True, 0),
+    (1, 64, 64, 4, "replicate", True, 3), (1, 7, 9, 2, "replicate", True, 2), (3, 50, 77, 1, "replicate", False, 0),
+    (1, 128, 128, 6, "replicate", True, 0)])
+def test_trunk_persistent_kernel(B, H, W, R, pad, xform0, max_ctas):
+    """pbmc_trunk_fwd: R FluidLayers (conv -> GroupNorm -> GELU, pytorch_networks_convae.py:790-799, :1323-1324) in one
+    persistent launch with a grid-wide barrier per layer, against (a) the float64 numpy oracle and (b) the same layers
+    launched one by one through pbmc_conv_fwd (same arithmetic per output; only the order of the double-precision
+    statistics atomics differs)."""
+    r = rng(100 + H + R)
+    x = r.standard_normal((B, 16, H, W))
+    ws = [r.standard_normal((16, 16, 3, 3)) / 12 for _ in range(R)]
+    bs = [0.3 * r.standard_normal(16) for _ in range(R)]
+    gs = [1 + 0.2 * r.standard_normal(16) for _ in range(R)]
+    bes = [0.2 * r.standard_normal(16) for _ in range(R)]
+    g0, be0 = 1 + 0.2 * r.standard_normal(16), 0.2 * r.standard_normal(16)
+    # oracle
+    a = RN.gelu(RN.group_norm(x, g0, be0, 4)) if xform0 else x
+    raws = []
+    for i in range(R):
+        y = RN.conv2d_same(a, ws[i], bs[i], pad)
+        raws.append(y)
+        a = RN.gelu(RN.group_norm(y, gs[i], bes[i], 4))
+    lays = [_Lay(ws[i], bs[i], gs[i], bes[i]) for i in range(R)]
+    xb = ops.pack_nchw(cu(x))
+    if xform0:
+        st0 = torch.stack([xb.double().sum((2, 3, 4)), (xb.double() ** 2).sum((2, 3, 4))], -1).contiguous()
+        src = ops.Source(xb, L.XFORM_GN_GELU, st0, cu(g0).float(), cu(be0).float())
+    else:
+        src = ops.Source(xb)
+    out, st_last, st_all = ops.trunk_fwd(src, lays, pad, impl="mux_f16x2", max_ctas=max_ctas)
+    got = ops.unpack_nchw(out, 16).cpu().numpy()
+    assert relerr(got, raws[-1]) < 6e-6, relerr(got, raws[-1])
+    ref_st = np.stack([raws[-1].reshape(B, 4, -1).sum(-1), (raws[-1] ** 2).reshape(B, 4, -1).sum(-1)], -1)
+    assert np.allclose(st_last.cpu().numpy(), ref_st, rtol=2e-5, atol=1e-4 * H * W)
+    fin = ops.finalize_nchw(ops.Source(out, L.XFORM_GN_GELU, st_last, lays[-1].gamma, lays[-1].beta), 16).cpu().numpy()
+    assert relerr(fin, a) < 6e-6
+    # layer by layer through pbmc_conv_fwd
+    s = src
+    for i in range(R):
+        yb, sti, _ = ops.conv_fwd([s], lays[i].wpk, lays[i].bias, 16, 3, pad, want_stats=True, impl="mux_f16x2", wpk_row=lays[i].wpk_row)
+        assert np.allclose(st_all[i].cpu().numpy(), sti.cpu().numpy(), rtol=1e-9, atol=1e-7)
+        s = ops.Source(yb, L.XFORM_GN_GELU, sti, lays[i].gamma, lays[i].beta)
+    assert (yb - out).abs().max().item() <= 2e-6 * max(1.0, float(yb.abs().max()))
+    # twice in a row: scratch is re-zeroed by the call, same result bit for bit up to the statistics' atomic order
+    out2, _, _ = ops.trunk_fwd(src, lays, pad, impl="mux_f16x2", max_ctas=max_ctas)
+    assert (out2 - out).abs().max().item() <= 2e-6 * max(1.0, float(out.abs().max()))
+
+
+def test_trunk_refuses_a_grid_that_cannot_be_resident():
+    lays = [_Lay(np.zeros((16, 16, 3, 3)), np.zeros(16), np.ones(16), np.zeros(16))]
+    x = torch.zeros(1, 4, 512, 512, 4, device=DEV)
+    with pytest.raises(L.PbmcError):
+        ops.trunk_fwd(ops.Source(x), lays, "replicate", max_ctas=8)  # 4 strips x >= 24 chunks of <= 22 rows
