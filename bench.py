@@ -297,7 +297,7 @@ def eng_grid(H, W, dev):
     return Grid(xc, yc, yc, dev)
 
 
-def bind_host_to_gpu_numa_node(local):
+def bind_host_to_gpu_numa_node(local, world=1):
     """Multi-rank runs only: pin this process (and the pinned host buffers it first-touches afterwards) to the CPUs NVML
     reports as local to its GPU.  Eight unpinned ranks each moving ~10 MB per 0.45 ms step through host memory measured
     4.5x one rank end to end (profiles/r1_bench_rollout512_8gpu.json).  Best effort: any failure leaves the affinity alone.
@@ -317,6 +317,14 @@ def bind_host_to_gpu_numa_node(local):
         if len(after) < 4:  # a degenerate mask would serialise the rank's helper threads: undo
             os.sched_setaffinity(0, before)
             return None
+        # Several ranks whose GPUs report the SAME CPU set (this pool: all 8 GPUs on NUMA node 0, CPUs 0-31) would
+        # still run on top of each other: give each rank its own contiguous slice of that set (>= 2 CPUs).
+        cpus = sorted(after)
+        per = len(cpus) // max(world, 1)
+        if world > 1 and per >= 2:
+            mine = cpus[(local % world) * per:(local % world + 1) * per]
+            os.sched_setaffinity(0, set(mine))
+            return len(mine)
         return len(after)
     except Exception:
         return None
@@ -397,7 +405,7 @@ def run_ours(args, wl):
         raise SystemExit("bench.py (--impl ours) needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa_cpus = bind_host_to_gpu_numa_node(local) if world > 1 else None  # N = 1 keeps every core for the CPU baseline
+    numa_cpus = bind_host_to_gpu_numa_node(local, world) if world > 1 else None  # N = 1 keeps every core for the CPU baseline
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     H, W, B = wl["H"], wl["W"], wl["B"]
@@ -418,65 +426,72 @@ def run_ours(args, wl):
           (np.log10(PARAMS0[2]) - 0.005251646002323797) / (1.9927988938926755 - 0.005251646002323797))
     args_ts = (None, None, yc_t, t64(nd[0]), t64(nd[1]), t64(nd[2]), t64(PARAMS0[0]), t64(PARAMS0[1]), t64(PARAMS0[2]), xc_t,
                yc_t)
-    Tp = t64(T0[:1]).view(1, 1, H, W).pin_memory()
     K2 = min(K, 50)
 
-    # the driver's per-step readback (advect_wi_gaia.py:595-616 copies u, v, V and T_new to the host every step);
-    # pinned host buffers.  T_new is the next call's (host) input, so it is read back on the main stream and waited
-    # for; u, v, V and dt of step k are read back on a side stream while step k+1 runs (every TS call returns fresh
-    # tensors, double-buffered on the host) -- all of it inside the timed region, drained before the clock stops.
-    pin = lambda: torch.empty(1, 1, H, W, dtype=torch.float64).pin_memory()
-    hostT = [pin(), pin()]  # ping-pong: step k's T is step k+1's (pinned) input
-    hostF = [[pin(), pin(), pin()], [pin(), pin(), pin()]]
-    host_dt = [torch.empty(1, dtype=torch.float64).pin_memory() for _ in range(2)]
-    e2e_calls = [0]
-    side = torch.cuda.Stream(dev)
-    side_done = [torch.cuda.Event(), torch.cuda.Event()]
+    def e2e_measure(host_dtype):
+        """K2 calls of the drop-in TS.forward with a pinned HOST T of `host_dtype` in, and the driver's per-step readback
+        (advect_wi_gaia.py:595-616 copies u, v, V and T_new to the host every step) into pinned host buffers.  T_new is
+        the next call's (host) input, so it is read back on the main stream and waited for; u, v, V and dt of step k are
+        read back on a side stream while step k+1 runs (every TS call returns fresh tensors, double-buffered on the host)
+        -- all of it inside the timed region, drained before the clock stops.  TS returns tensors of its input's dtype
+        (as the reference does), so a float32 host T halves every PCIe transfer; the kernels compute in fp32 either way."""
+        Tp = torch.tensor(T0[:1], dtype=host_dtype).view(1, 1, H, W).pin_memory()
+        pin = lambda: torch.empty(1, 1, H, W, dtype=host_dtype).pin_memory()
+        hostT = [pin(), pin()]  # ping-pong: step k's T is step k+1's (pinned) input
+        hostF = [[pin(), pin(), pin()], [pin(), pin(), pin()]]
+        host_dt = [torch.empty(1, dtype=host_dtype).pin_memory() for _ in range(2)]
+        calls = [0]
+        side = torch.cuda.Stream(dev)
+        side_done = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step(Tp_):
-        k = e2e_calls[0] % 2
-        e2e_calls[0] += 1
-        x, dts, u, v, p, V = ts(Tp_, *args_ts)
-        main = torch.cuda.current_stream(dev)
-        Tn_ = hostT[k]
-        Tn_.copy_(x[1], non_blocking=True)
-        side.wait_stream(main)
-        side_done[k].synchronize()  # the host buffers of two steps ago are free again
-        with torch.cuda.stream(side):
-            for dst, src in zip(hostF[k], (u, v, V)):
-                dst.copy_(src, non_blocking=True)
-                src.record_stream(side)
-            host_dt[k].copy_(dts[1].reshape(1), non_blocking=True)
-            dts[1].record_stream(side)
-            side_done[k].record(side)
-        main.synchronize()
-        return Tn_, sum(o.numel() * o.element_size() for o in (Tn_, *hostF[k], host_dt[k]))
+        def step(Tp_):
+            k = calls[0] % 2
+            calls[0] += 1
+            x, dts, u, v, p, V = ts(Tp_, *args_ts)
+            main = torch.cuda.current_stream(dev)
+            Tn_ = hostT[k]
+            Tn_.copy_(x[1], non_blocking=True)
+            side.wait_stream(main)
+            side_done[k].synchronize()  # the host buffers of two steps ago are free again
+            with torch.cuda.stream(side):
+                for dst, src in zip(hostF[k], (u, v, V)):
+                    dst.copy_(src, non_blocking=True)
+                    src.record_stream(side)
+                host_dt[k].copy_(dts[1].reshape(1), non_blocking=True)
+                dts[1].record_stream(side)
+                side_done[k].record(side)
+            main.synchronize()
+            return Tn_, sum(o.numel() * o.element_size() for o in (Tn_, *hostF[k], host_dt[k]))
 
-    for _ in range(10):
-        Tn, d2h = e2e_step(Tp)
-    # The timed region (K2 steps, drained) is repeated three times and the MEDIAN reported: one run in five on a fresh
-    # box showed a 2x slower first pass (host side: page-ins / link power state), which says nothing about the code.
-    e2e_runs = []
-    for _ in range(3):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        Tc = Tp
-        for _ in range(K2):
-            Tc, d2h = e2e_step(Tc)
-        torch.cuda.synchronize()  # includes the side stream: the last steps' u, v, V are on the host
-        e2e_runs.append(time.perf_counter() - t0)
-    e2e_s = statistics.median(e2e_runs)
+        for _ in range(10):
+            Tn, d2h = step(Tp)
+        # The timed region (K2 steps, drained) is repeated three times and the MEDIAN reported: one run in five on a fresh
+        # box showed a 2x slower first pass (host side: page-ins / link power state), which says nothing about the code.
+        runs = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            Tc = Tp
+            for _ in range(K2):
+                Tc, d2h = step(Tc)
+            torch.cuda.synchronize()  # includes the side stream: the last steps' u, v, V are on the host
+            runs.append(time.perf_counter() - t0)
+        return statistics.median(runs), runs, int(Tp.numel() * Tp.element_size()), int(d2h)
+
+    e2e64_s, e2e64_runs, h2d64, d2h64 = e2e_measure(torch.float64)  # the reference driver's dtype (round-1 number)
+    e2e_s, e2e_runs, h2d, d2h = e2e_measure(torch.float32)          # headline: same API, fp32 host tensors
     e2e_rate = H * W * K2 / e2e_s
 
     # ---- reduce over ranks: total units / max time
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_t = torch.tensor([e2e_s, e2e64_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     dev_ms = t_ms.item()
     value = world * B * H * W * K / (dev_ms * 1e-3)
-    e2e_rate = world * H * W * K2 / e2e_t.item()
+    e2e_rate = world * H * W * K2 / e2e_t[0].item()
+    e2e64_rate = world * H * W * K2 / e2e_t[1].item()
 
     line = None
     if rank == 0:
@@ -521,7 +536,7 @@ def run_ours(args, wl):
                        "net": "NewFluidNet(levels=6,c_i=7,c_h=16,c_o=2,k=3,replicate,symm,curl,repeats=4)", "conv_impl": args.conv,
                        "l2": "flushed (256 MiB write, untimed) between timed steps; per-step CUDA-event intervals summed",
                        "parallelism": f"{world} independent rollouts (no collective)" if world > 1 else "single GPU",
-                       "host_affinity": f"rank 0 bound to its GPU's {numa_cpus} NUMA-local CPUs (NVML)" if numa_cpus else "unbound",
+                       "host_affinity": f"each rank bound to its own {numa_cpus} CPUs out of its GPU's NUMA-local set (NVML)" if numa_cpus else "unbound",
                        "graph": "one CUDA graph per time step"},
             "surrogate_steps_per_s": world * K / (dev_ms * 1e-3),
             "gflop_per_step": B * H * W * FLOP_PER_CELL / 1e9,
@@ -530,9 +545,13 @@ def run_ours(args, wl):
             "kernels": roofs,
             "stencil_sweep": sweep,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_rate, "unit": "cell-updates/s", "h2d_bytes_per_step": int(Tp.numel() * 8), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e_rate, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": K2, "repeats_ms": [round(t_ * 1e3, 3) for t_ in e2e_runs], "value_is": "median of the repeats",
-                    "api": "TS.forward(ts=1) with pinned host float64 T in; every step T read back and waited for (it is the next input), u,v,V,dt read back on a side stream overlapping the next step; all drained inside the timed region"},
+                    "host_dtype": "float32",
+                    "api": "TS.forward(ts=1) with pinned host float32 T in (TS returns its input's dtype, like the reference; the kernels are fp32 either way, so nothing is lost and every PCIe transfer halves); every step T read back and waited for (it is the next input), u,v,V,dt read back on a side stream overlapping the next step; all drained inside the timed region",
+                    "float64_host": {"value": e2e64_rate, "h2d_bytes_per_step": h2d64, "d2h_bytes_per_step": d2h64,
+                                     "repeats_ms": [round(t_ * 1e3, 3) for t_ in e2e64_runs],
+                                     "note": "the same loop with float64 host tensors (the reference driver's dtype, round 1's e2e)"}},
             "gpu_launches": launches_per_step(6, 4, "trunk_l0" in roofs) * K,
             "clocks": clk.summary(),
             "finite": finite,

@@ -54,7 +54,10 @@ enum { PBMC_ACT_NONE = 0, PBMC_ACT_GELU = 1 };
  * padding, xform NONE, nblk = 4, on the ROW_F16X2 kernel (AUTO picks it). */
 enum { PBMC_LAYOUT_BLOCKED = 0, PBMC_LAYOUT_STAGED16 = 1 };
 enum { PBMC_HEAD_CURL = 0, PBMC_HEAD_MAE = 1 };
-enum { PBMC_TRUNK_AUTO = 0, PBMC_TRUNK_PER_LAYER = 1 };
+/* pbmc_net.flags: PER_LAYER = never use the persistent trunk kernel; UP_STAGED = the bicubic kernel writes the up-sampled
+ * levels as conv[1]'s fp16 hi|lo operand image (PBMC_LAYOUT_STAGED16) and conv[1] stages them with TMA bulk copies
+ * (bit-identical results; measured neutral-to-slower, so off by default) */
+enum { PBMC_NET_TRUNK_PER_LAYER = 1, PBMC_NET_UP_STAGED = 2 };
 /* conv implementation selector: FFMA = fp32 CUDA cores; UMMA_* = tcgen05 tensor cores:
  * 3XTF32 / F16X2 split every operand into hi + lo (tf32 resp. fp16) and issue 3 passes --
  * fp32-grade accuracy; BF16 = single pass with bf16 operands (looser, stated bound).
@@ -261,8 +264,8 @@ typedef struct {
 typedef struct {
   int levels, repeats, c_i, c_h, c_o, ksize, pad_mode, head_kind, p_pred, conv_impl;
   float a_bound;
-  int trunk_mode; /* PBMC_TRUNK_AUTO: the R layers of a level as one persistent launch where the grid can be resident
-                     (pbmc_trunk_fwd), else one launch per layer; PBMC_TRUNK_PER_LAYER: always one launch per layer */
+  int flags; /* PBMC_NET_*: 0 = defaults (the R layers of a level as one persistent launch where every level's grid can be
+                resident at once -- pbmc_trunk_fwd -- else one launch per layer; up-sampled levels as blocked fp32) */
   pbmc_layer conv0;
   pbmc_layer trunk[PBMC_MAX_LEVELS * PBMC_MAX_REPEATS]; /* [level][repeat] */
   pbmc_layer conv1, conv2, conv3;

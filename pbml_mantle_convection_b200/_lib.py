@@ -21,6 +21,7 @@ LAYOUT_BLOCKED, LAYOUT_STAGED16 = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
 HEAD_CURL, HEAD_MAE = 0, 1
 TRUNK_MODE = {"auto": 0, "per_layer": 1}
+NET_UP_STAGED = 2
 CONV_IMPL = {"auto": 0, "ffma": 1, "umma_3xtf32": 2, "umma_bf16": 3, "umma_f16x2": 4,
              "row_f16x2": 5, "row_bf16": 6, "mux_f16x2": 7, "mux_bf16": 8}
 
@@ -51,7 +52,7 @@ class Layer(C.Structure):
 class Net(C.Structure):
     _fields_ = [("levels", C.c_int), ("repeats", C.c_int), ("c_i", C.c_int), ("c_h", C.c_int), ("c_o", C.c_int),
                 ("ksize", C.c_int), ("pad_mode", C.c_int), ("head_kind", C.c_int), ("p_pred", C.c_int),
-                ("conv_impl", C.c_int), ("a_bound", C.c_float), ("trunk_mode", C.c_int), ("conv0", Layer),
+                ("conv_impl", C.c_int), ("a_bound", C.c_float), ("flags", C.c_int), ("conv0", Layer),
                 ("trunk", Layer * (MAX_LEVELS * MAX_REPEATS)), ("conv1", Layer), ("conv2", Layer), ("conv3", Layer)]
 
 

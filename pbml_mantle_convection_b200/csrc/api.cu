@@ -300,7 +300,7 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
   //   8  head kernel        off: no measurable change
   //   2  level-0 trunk      off: 0.27 ms -- an early-resident CTA parked in griddepcontrol.wait takes an SM from
   //                              the other levels' streams
-  static const int chain_pdl = getenv("PBMC_CHAIN_PDL") ? atoi(getenv("PBMC_CHAIN_PDL")) : 5;
+  static const int chain_pdl = PBMC_DEV_KNOB("PBMC_CHAIN_PDL", 5);
   auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto S = [&](int slot) { return reinterpret_cast<double*>(ws + P.stat_off(slot, B)); };
   double* chan_sum = reinterpret_cast<double*>(ws + P.chan_sum);
@@ -352,9 +352,9 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
   }
   // Off by default: measured neutral-to-slower in the whole step (512^2: 0.244-0.260 vs 0.241 ms; 32 x 256^2: 1.47 vs
   // 1.445 ms) -- conv[1] is paced by its MMA issue loop, not by its producers, and the operand-image writer of the
-  // bicubic kernel stores 2 x 8 B per thread.  PBMC_UP_STAGED=1 turns it on (results are bit-identical).
-  static const int staged_knob = getenv("PBMC_UP_STAGED") ? atoi(getenv("PBMC_UP_STAGED")) : 0;
-  up_staged = up_staged && staged_knob != 0;
+  // bicubic kernel stores 2 x 8 B per thread.  pbmc_net.flags & PBMC_NET_UP_STAGED turns it on (results are bit-identical).
+  up_staged = up_staged && (n.flags & PBMC_NET_UP_STAGED) != 0;
+#ifdef PBMC_DEV_BUILD
   {
     // developer knob: PBMC_BUDGETS="116,24,6,3,2,1" overrides the per-level CTA budgets
     static const char* bud = getenv("PBMC_BUDGETS");
@@ -367,9 +367,10 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
       }
     }
   }
+#endif
   // Persistent trunk kernels (csrc/conv_trunk.cu: the R layers of a level in one launch, grid barrier between layers)
   // need EVERY CTA of EVERY level resident at once: taken only when all levels have a budget and the budgets fit 148 SMs.
-  bool trunk_persistent = n.trunk_mode == PBMC_TRUNK_AUTO && CB == 4 && n.ksize == 3;
+  bool trunk_persistent = (n.flags & PBMC_NET_TRUNK_PER_LAYER) == 0 && CB == 4 && n.ksize == 3;
   {
     int total = 0;
     for (int l = 0; l < L && trunk_persistent; ++l) {

@@ -489,8 +489,8 @@ __global__ void __maxnreg__(CM_MAXNREG) conv_mux_kernel(const __grid_constant__ 
 
 }  // namespace pbmc
 
-#if CM_NSETS == 5
-#include "conv_mux_ts.cuh"
+#if CM_NSETS == 5 && defined(PBMC_DEV_BUILD)
+#include "conv_mux_ts.cuh"  // TMEM-operand variant: correct, measured slower; development builds only
 #endif
 
 namespace pbmc {
@@ -505,7 +505,7 @@ extern "C" void pbmc_debug_set_mux_trace(void* dev_buf) { g_mux_trace = reinterp
 // Output rows per CTA: minimise waves x (fixed cost + staging rounds + epilogue rounds), in clocks measured with
 // tools/muxtrace.py (a staging round = 5 groups x 1 row, an epilogue round = 5 rows).
 static int choose_rpc_mux(int units, int H, int max_ctas, bool gelu) {
-  static const int forced = getenv("PBMC_MUX_RPC") ? atoi(getenv("PBMC_MUX_RPC")) : 0;  // developer knob
+  static const int forced = PBMC_DEV_KNOB("PBMC_MUX_RPC", 0);  // developer knob
   if (forced > 0) return forced < H ? (forced < CM_MAXR - 2 ? forced : CM_MAXR - 2) : (H < CM_MAXR - 2 ? H : CM_MAXR - 2);
   const long avail = max_ctas > 0 ? max_ctas : 148;
   int best = 1;
@@ -556,7 +556,7 @@ static int launch_mux(ConvMuxParams& p, int max_ctas, cudaStream_t st) {
 // TS variant: nothing but the filters in shared memory, so any number of rows per CTA; cost in clocks per CTA =
 // fixed + (rows + halo) x per-row (tools/muxtrace.py)
 static int choose_rpc_ts(int units, int H, int max_ctas) {
-  static const int forced = getenv("PBMC_MUX_RPC") ? atoi(getenv("PBMC_MUX_RPC")) : 0;  // developer knob
+  static const int forced = PBMC_DEV_KNOB("PBMC_MUX_RPC", 0);  // developer knob
   if (forced > 0) return forced < H ? forced : H;
   const long avail = max_ctas > 0 ? max_ctas : 148;
   int best = 1;
@@ -570,7 +570,7 @@ static int choose_rpc_ts(int units, int H, int max_ctas) {
   return best;
 }
 
-#if CM_NSETS == 5
+#if CM_NSETS == 5 && defined(PBMC_DEV_BUILD)
 template <int PARTS>
 static int launch_ts(ConvMuxParams& p, int max_ctas, cudaStream_t st) {
   constexpr int B_GROUP = 3 * PARTS * (2 * CM_N * 16);
@@ -619,8 +619,8 @@ int conv_mux_dispatch(const pbmc_conv_desc& d, cudaStream_t st) {
   p.rpc = 1;
   p.bias = d.bias; p.out = d.out; p.out_stats = d.out_stats; p.out_chan_sum = d.out_chan_sum;
   p.trace = nullptr;
-  p.dbg_flags = getenv("PBMC_MUX_DBG_FLAGS") ? atoi(getenv("PBMC_MUX_DBG_FLAGS")) : 0;
-  static const int stagger = getenv("PBMC_MUX_STAGGER") ? atoi(getenv("PBMC_MUX_STAGGER")) : 0;  // developer knob
+  p.dbg_flags = PBMC_DEV_KNOB("PBMC_MUX_DBG_FLAGS", 0);
+  static const int stagger = PBMC_DEV_KNOB("PBMC_MUX_STAGGER", 0);  // developer knob
   p.stagger = stagger;
 #ifdef PBMC_ROW_TRACE
   p.trace = g_mux_trace;
@@ -630,7 +630,7 @@ int conv_mux_dispatch(const pbmc_conv_desc& d, cudaStream_t st) {
   if (!aligned16(base)) return PBMC_ERR_MISALIGNED;
   const size_t off_bf16 = (size_t)3 * 2 * (2 * CM_N * 16);
   // PBMC_MUX_TS=1 (developer knob): A operand in TMEM instead of shared memory (conv_mux_ts.cuh; correct, measured slower)
-  static const int use_ts = getenv("PBMC_MUX_TS") ? atoi(getenv("PBMC_MUX_TS")) : 0;
+  static const int use_ts = PBMC_DEV_KNOB("PBMC_MUX_TS", 0);
   if (d.impl == PBMC_CONV_MUX_F16X2) {
     p.wpk = base;
     return use_ts ? launch_ts<2>(p, d.max_ctas, st) : launch_mux<2>(p, d.max_ctas, st);

@@ -901,7 +901,7 @@ extern "C" void pbmc_debug_set_row_trace(void* dev_buf) { g_row_trace = reinterp
 
 // rows per CTA: minimise waves * (rows + halo + fixed per-CTA cost in row units)
 static int choose_rpc(int units, int H, int ks, int max_ctas) {
-  static const int forced = getenv("PBMC_ROW_RPC") ? atoi(getenv("PBMC_ROW_RPC")) : 0;  // developer knob
+  static const int forced = PBMC_DEV_KNOB("PBMC_ROW_RPC", 0);  // developer knob
   if (forced > 0) return forced < H ? forced : H;
   if (max_ctas > 0) {
     // a share of the GPU: the fewest rows per CTA that stay within the CTA budget (the conv runs next to others)
@@ -937,7 +937,7 @@ static int launch_row(ConvRowParams& p, cudaStream_t st) {
   // Programmatic dependent launch is wired but OFF: measured 0.269 vs 0.243 ms/step at 512^2 -- a dependent CTA that
   // becomes resident early sits in griddepcontrol.wait holding an SM (a conv CTA owns one), which starves the
   // other pyramid levels' streams.  (With PDL off griddepcontrol.wait / launch_dependents are no-ops.)
-  static const int pdl = getenv("PBMC_ROW_PDL") ? atoi(getenv("PBMC_ROW_PDL")) : 0;  // developer knob
+  static const int pdl = PBMC_DEV_KNOB("PBMC_ROW_PDL", 0);  // developer knob
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(CR_THREADS);
@@ -995,8 +995,8 @@ int conv_row_dispatch(const pbmc_conv_desc& d, cudaStream_t st) {
   p.has_staged = 0;
   for (int s = 0; s < d.nsrc; ++s) p.has_staged |= d.src[s].layout == PBMC_LAYOUT_STAGED16;
   p.trace = nullptr;
-  p.dbg_dx = getenv("PBMC_ROW_DBG_DX") ? atoi(getenv("PBMC_ROW_DBG_DX")) : 16;
-  p.dbg_flags = getenv("PBMC_ROW_DBG_FLAGS") ? atoi(getenv("PBMC_ROW_DBG_FLAGS")) : 0;
+  p.dbg_dx = PBMC_DEV_KNOB("PBMC_ROW_DBG_DX", 16);
+  p.dbg_flags = PBMC_DEV_KNOB("PBMC_ROW_DBG_FLAGS", 0);
 #ifdef PBMC_ROW_TRACE
   p.trace = g_row_trace;
 #endif

@@ -356,7 +356,7 @@ int conv_umma_dispatch(const pbmc_conv_desc& d, cudaStream_t st) {
     p.wpk = base;
     return d.ksize == 3 ? launch_umma<3, 64, 15, 8, CU_TF32X3>(p, st) : launch_umma<5, 64, 15, 8, CU_TF32X3>(p, st);
   }
-  static const int tile_cfg = getenv("PBMC_UMMA_TILE") ? atoi(getenv("PBMC_UMMA_TILE")) : 0;  // developer knob
+  static const int tile_cfg = PBMC_DEV_KNOB("PBMC_UMMA_TILE", 0);  // developer knob
   if (d.impl == PBMC_CONV_UMMA_F16X2) {
     p.wpk = base + off_f16;
     if (d.ksize == 3 && tile_cfg == 1) return launch_umma<3, 64, 7, 4, CU_F16X2>(p, st);

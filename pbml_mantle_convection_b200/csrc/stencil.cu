@@ -554,7 +554,7 @@ static int advect_diffuse_launch(const float* T, const float* u, const float* v,
   StencilParams p{T, u, v, x, y, members, uvmax_in, uvmax_out, T_out, dt_out, dx_min, cn_max, dt_fixed, member_stride, H, W,
                   has_up ? 1 : 0, has_down ? H - 1 : H, has_up ? 1 : -1, has_down ? H - 2 : -1, peer_up, peer_down};
   const bool vec = (W % 4 == 0) && aligned16(T) && aligned16(u) && aligned16(v) && aligned16(T_out);
-  static const int tiled = getenv("PBMC_STENCIL_TILED") ? atoi(getenv("PBMC_STENCIL_TILED")) : 0;  // developer knob: old kernel
+  static const int tiled = PBMC_DEV_KNOB("PBMC_STENCIL_TILED", 0);  // developer knob: old kernel
   if (vec && aligned16(x) && (!tiled || slab)) {
     if ((peer_up && !aligned16(peer_up)) || (peer_down && !aligned16(peer_down))) return PBMC_ERR_MISALIGNED;
     // rows per warp: enough warps to fill the machine (148 SMs x 16 warps), at most 64 rows (2/rpw halo re-read)

@@ -54,6 +54,7 @@ class SurrogateEngine:
         self._ws = {}
         self.conv_impl = "auto"
         self.trunk_mode = "auto"  # "auto": persistent per-level trunk kernel where it fits; "per_layer": one launch per layer
+        self.up_staged = False    # True: up-sampled levels written as conv[1]'s operand image, staged by TMA bulk copies
         self.refresh()
 
     def __del__(self):
@@ -118,7 +119,7 @@ class SurrogateEngine:
         n.head_kind = L.HEAD_CURL if m.loss_type == "curl" else L.HEAD_MAE
         n.p_pred = int(bool(m.p_pred))
         n.conv_impl = L.CONV_IMPL[self.conv_impl]
-        n.trunk_mode = L.TRUNK_MODE[self.trunk_mode]
+        n.flags = L.TRUNK_MODE[self.trunk_mode] | (L.NET_UP_STAGED if self.up_staged else 0)
         n.a_bound = float(m.a_bound)
         n.conv0 = self.conv0.c()
         for l in range(m.levels):
@@ -133,10 +134,12 @@ class SurrogateEngine:
         self.conv_impl = impl
         self._build_desc()
 
-    def set_trunk_mode(self, mode):
+    def set_trunk_mode(self, mode, up_staged=None):
         if mode not in L.TRUNK_MODE:
             raise ValueError(mode)
         self.trunk_mode = mode
+        if up_staged is not None:
+            self.up_staged = bool(up_staged)
         self._build_desc()
 
     # -------------------------------------------------------------- workspace
@@ -160,7 +163,7 @@ class SurrogateEngine:
         """Everything a captured graph of this engine bakes in besides its own buffers: packed-weight identity, conv
         implementation, workspace address.  A change in any of them must force a re-capture."""
         self.refresh()
-        return (self._key, self.conv_impl, self.trunk_mode, self.workspace(B, H, W).data_ptr())
+        return (self._key, self.conv_impl, self.trunk_mode, self.up_staged, self.workspace(B, H, W).data_ptr())
 
     # -------------------------------------------------------------- forward
     def forward_blocked(self, inp_blocked, members=None, want_uvmax=False):

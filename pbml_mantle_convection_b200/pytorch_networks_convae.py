@@ -190,6 +190,7 @@ class _FluidNetBase(nn.Module):
         self._engines = {}
         self.conv_impl = "auto"  # "auto" | "ffma" | "umma_3xtf32" | "umma_bf16"
         self.trunk_mode = "auto"  # "auto": one persistent launch per pyramid level where it fits | "per_layer"
+        self.up_staged = False    # True: conv[1] stages the up-sampled levels with TMA bulk copies (see include/pbmc.h)
         self.use_cuda_graph = True  # learned-boundary networks: replay the module-level forward as one CUDA graph
 
     # nn.Module bookkeeping: engines hold device buffers, never parameters
@@ -200,8 +201,8 @@ class _FluidNetBase(nn.Module):
             eng = self._engines[key] = SurrogateEngine(self, device)
         if eng.conv_impl != self.conv_impl:
             eng.set_conv_impl(self.conv_impl)
-        if eng.trunk_mode != self.trunk_mode:
-            eng.set_trunk_mode(self.trunk_mode)
+        if eng.trunk_mode != self.trunk_mode or eng.up_staged != bool(self.up_staged):
+            eng.set_trunk_mode(self.trunk_mode, self.up_staged)
         return eng
 
     def __getstate__(self):  # engines are not picklable / deep-copyable

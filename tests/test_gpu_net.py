@@ -413,22 +413,20 @@ def test_driver_per_step_and_resident_agree(tmp_path):
 
 
 def test_forward_with_tma_staged_levels_is_bit_identical():
-    """PBMC_UP_STAGED=1: the up-sampled levels are written as conv[1]'s fp16 hi|lo operand image and staged by TMA
-    bulk copies (api.cu / conv_row.cu bulk-copy lane).  Same arithmetic, so the forward must not change by one bit."""
-    import hashlib, os, subprocess, sys
-    code = (
-        "import torch, hashlib\n"
-        "import pbml_mantle_convection_b200 as P\n"
-        "torch.manual_seed(0)\n"
-        "net = P.NewFluidNet(4, 7, 16, 2, 'cuda:0', act_fn='gelu', r_p='replicate', loss_type='curl', use_symm=True, a_bound=10, repeats=2, f=3, p_pred=True).to('cuda:0').eval()\n"
-        "x = torch.randn(2, 7, 70, 150, generator=torch.Generator().manual_seed(1)).to('cuda:0')\n"
-        "u, v, p = net(x)\n"
-        "h = hashlib.sha256(); [h.update(t.float().cpu().numpy().tobytes()) for t in (u, v, p)]; print('HASH', h.hexdigest())\n")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = []
-    for flag in ("0", "1"):
-        res = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, PBMC_UP_STAGED=flag), capture_output=True,
-                             text=True, timeout=300)
-        assert res.returncode == 0, res.stdout + res.stderr
-        out.append([ln for ln in res.stdout.splitlines() if ln.startswith("HASH")][0])
-    assert out[0] == out[1]
+    """net.up_staged = True (pbmc_net.flags & PBMC_NET_UP_STAGED): the up-sampled levels are written as conv[1]'s fp16
+    hi|lo operand image and staged by TMA bulk copies (api.cu / conv_row.cu bulk-copy lane).  Same arithmetic, so the
+    forward must not change by one bit; the persistent and the per-layer trunk agree to the statistics' atomic order."""
+    torch.manual_seed(0)
+    net = P.NewFluidNet(4, 7, 16, 2, DEV, act_fn="gelu", r_p="replicate", loss_type="curl", use_symm=True, a_bound=10,
+                        repeats=2, f=3, p_pred=True).to(DEV).eval()
+    x = torch.randn(2, 7, 70, 150, generator=torch.Generator().manual_seed(1)).to(DEV)
+    net.trunk_mode = "per_layer"
+    ref = net(x)
+    net.up_staged = True
+    got = net(x)
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
+    net.up_staged, net.trunk_mode = False, "auto"
+    per = net(x)
+    for a, b in zip(ref, per):
+        assert (a - b).abs().max().item() <= 1e-5 * float(a.abs().max())
