@@ -35,7 +35,7 @@ def rng(seed):
 
 def test_library_is_loaded_from_tree():
     lib = L.load()
-    assert lib.pbmc_version() == 2 and L.LIB_PATH.endswith("pbml_mantle_convection_b200/libpbmc.so")
+    assert lib.pbmc_version() == 3 and L.LIB_PATH.endswith("pbml_mantle_convection_b200/libpbmc.so")
 
 
 @pytest.mark.parametrize("shape", [(1, 7, 16, 16), (2, 16, 33, 50), (3, 1, 5, 7), (1, 103, 20, 24)])
