@@ -149,6 +149,31 @@ typedef struct {
 
 int pbmc_conv_fwd(const pbmc_conv_desc* desc_h, void* stream);
 
+/* ------------------------------------------------------------------ A4: learned 9-region boundary convolution
+ * BoundaryLearnedConvolution2D.forward pytorch_networks_convae.py:1022-1065 (bc_x = bc_y = 1) in TWO launches:
+ *   1. pbmc_conv_fwd with the INTERIOR filters (`conv`), bias = learnable_bias, any padding mode (zeros is cheapest),
+ *      over the whole image: correct wherever the k x k window stays inside the image;
+ *   2. pbmc_conv_edge9 overwrites the ring of width (k-1)/2 with the eight edge / corner regions -- per pixel ONE k x k
+ *      window whose position and filter set follow from its row / column class, the reference's row swap included
+ *      (the strip computed from the LAST input rows is output row 0, :1060) -- and repairs out_stats / out_chan_sum
+ *      (subtracts what launch 1 accumulated for the ring pixels, adds the new values).
+ * Same sources (concat order, fused producer transforms), same `out` / statistics buffers in both calls.
+ *   wedge  float [8][cin_blks][k*k][16][4]: region (top_left, top_right, bottom_left, bottom_right, top, bottom, left,
+ *          right -- the reference's names), input-channel block of the concatenation, tap dy*k+dx, c_out, c_in % 4;
+ *          zero padded (ops.pack_edge9_weights).  c_out <= 16, every source <= 64 channels. */
+typedef struct {
+  pbmc_src src[PBMC_MAX_SRC];
+  int nsrc;
+  int B, H, W;
+  int cout, ksize, epi_act, reserved;
+  const float* wedge;
+  const float* bias;      /* [16] learnable_bias, zero padded */
+  float* out;             /* [B][ceil(cout/4)][H][W][4], written by pbmc_conv_fwd before this call */
+  double* out_stats;      /* as passed to pbmc_conv_fwd, or NULL */
+  double* out_chan_sum;   /* as passed to pbmc_conv_fwd, or NULL */
+} pbmc_edge9_desc;
+int pbmc_conv_edge9(const pbmc_edge9_desc* desc_h, void* stream);
+
 /* blocked -> NCHW with the producer's GroupNorm(+GELU) applied: the tail of a stand-alone
  * FluidLayer.forward (pytorch_networks_convae.py:796-797). */
 int pbmc_finalize_nchw(const pbmc_src* src_h, float* dst_nchw, int B, int C, int H, int W, void* stream);

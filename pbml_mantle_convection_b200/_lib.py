@@ -64,13 +64,19 @@ class SlabSync(C.Structure):
                 ("local_max", C.c_uint), ("reserved", C.c_uint)]
 
 
+class Edge9Desc(C.Structure):
+    _fields_ = [("src", Src * MAX_SRC), ("nsrc", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("cout", C.c_int),
+                ("ksize", C.c_int), ("epi_act", C.c_int), ("reserved", C.c_int), ("wedge", C.c_void_p), ("bias", C.c_void_p),
+                ("out", C.c_void_p), ("out_stats", C.c_void_p), ("out_chan_sum", C.c_void_p)]
+
+
 class TrunkDesc(C.Structure):
     _fields_ = [("src0", Src), ("layers", C.POINTER(Layer)), ("ping", C.c_void_p * 2), ("stats", C.c_void_p),
                 ("sync", C.c_void_p), ("R", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("pad_mode", C.c_int),
                 ("impl", C.c_int), ("max_ctas", C.c_int), ("pre_zeroed", C.c_int)]
 
 
-_STRUCTS = {"pbmc_trunk_desc": TrunkDesc, "pbmc_slab_sync": SlabSync, "pbmc_member": Member, "pbmc_src": Src, "pbmc_conv_desc": ConvDesc, "pbmc_layer": Layer, "pbmc_net": Net}
+_STRUCTS = {"pbmc_edge9_desc": Edge9Desc, "pbmc_trunk_desc": TrunkDesc, "pbmc_slab_sync": SlabSync, "pbmc_member": Member, "pbmc_src": Src, "pbmc_conv_desc": ConvDesc, "pbmc_layer": Layer, "pbmc_net": Net}
 
 # name -> (restype, argtypes); every symbol declared in include/pbmc.h
 _vp, _i, _d, _f, _sz = C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_size_t
@@ -83,6 +89,7 @@ SIGNATURES = {
     "pbmc_unpack_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "pbmc_build_input": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pbmc_conv_fwd": (_i, [C.POINTER(ConvDesc), _vp]),
+    "pbmc_conv_edge9": (_i, [C.POINTER(Edge9Desc), _vp]),
     "pbmc_trunk_fwd": (_i, [C.POINTER(TrunkDesc), _vp]),
     "pbmc_trunk_supported": (_i, [C.POINTER(TrunkDesc)]),
     "pbmc_avgpool2": (_i, [C.POINTER(Src), _vp, _i, _i, _i, _vp]),

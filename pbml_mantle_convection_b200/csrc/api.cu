@@ -65,6 +65,7 @@ extern "C" size_t pbmc_sizeof(const char* name) {
   if (!strcmp(name, "pbmc_net")) return sizeof(pbmc_net);
   if (!strcmp(name, "pbmc_slab_sync")) return sizeof(pbmc_slab_sync);
   if (!strcmp(name, "pbmc_trunk_desc")) return sizeof(pbmc_trunk_desc);
+  if (!strcmp(name, "pbmc_edge9_desc")) return sizeof(pbmc_edge9_desc);
   return 0;
 }
 

@@ -229,6 +229,60 @@ def conv_fwd(sources, wpk, bias, cout, ksize, pad_mode, epi_act=L.ACT_NONE, want
     return out, stats, csum
 
 
+EDGE9_REGIONS = ("conv_top_left", "conv_top_right", "conv_bottom_left", "conv_bottom_right", "conv_top", "conv_bottom",
+                 "conv_left", "conv_right")  # order of the filter sets in the edge kernel's image (reference names)
+
+
+def pack_edge9_weights(w_regions, src_channels) -> torch.Tensor:
+    """Eight full filter banks [Co<=16, Ci, k, k] (order EDGE9_REGIONS) -> float32 [8][cin_blks][k*k][16 c_out][4 c_in]
+    for pbmc_conv_edge9; input channels follow the concatenation of the sources, each padded to whole 4-channel blocks."""
+    assert len(w_regions) == 8
+    out = []
+    for w in w_regions:
+        Co, Ci, k, _ = w.shape
+        assert Co <= 16 and sum(src_channels) == Ci
+        parts, c0 = [], 0
+        for c in src_channels:
+            wp = w[:, c0:c0 + c].float()
+            pad = nblk(c) * 4 - c
+            if pad:
+                wp = torch.cat([wp, wp.new_zeros(Co, pad, k, k)], 1)
+            parts.append(wp)
+            c0 += c
+        wf = torch.cat(parts, 1)
+        if Co < 16:
+            wf = torch.cat([wf, wf.new_zeros(16 - Co, wf.shape[1], k, k)], 0)
+        nb = wf.shape[1] // 4
+        # (co, blk, e, dy, dx) -> (blk, tap, co, e)
+        out.append(wf.reshape(16, nb, 4, k * k).permute(1, 3, 0, 2).contiguous())
+    return torch.stack(out, 0).contiguous()
+
+
+def conv_edge9(sources, wedge, bias, cout, ksize, epi_act, out, stats=None, csum=None):
+    """Second launch of the learned 9-region convolution (pbmc_conv_edge9): overwrite the ring of `out` (already holding the
+    interior conv of pbmc_conv_fwd over the same sources) with the eight boundary regions; repair stats / csum."""
+    B, _, H, W, _ = out.shape
+    d = L.Edge9Desc()
+    d.nsrc = len(sources)
+    for i, s in enumerate(sources):
+        d.src[i] = s.c()
+    d.B, d.H, d.W, d.cout, d.ksize, d.epi_act = B, H, W, int(cout), int(ksize), int(epi_act)
+    d.wedge, d.bias, d.out = L.ptr(wedge), L.ptr(bias), L.ptr(out)
+    d.out_stats, d.out_chan_sum = L.ptr(stats), L.ptr(csum)
+    L.check(L.load().pbmc_conv_edge9(C.byref(d), L.stream_ptr(out.device)), "pbmc_conv_edge9")
+    return out
+
+
+def conv_learned9(sources, wpk, wrow, wedge, bias, cout, ksize, epi_act=L.ACT_NONE, want_stats=False, want_chan_sum=False,
+                  impl="auto"):
+    """BoundaryLearnedConvolution2D (bc = 1) over blocked sources in two launches: interior filters through pbmc_conv_fwd
+    (tensor cores where the shape allows), the ring through pbmc_conv_edge9.  Returns (out, stats|None, chan_sum|None)."""
+    out, stats, csum = conv_fwd(sources, wpk, bias, cout, ksize, "zeros", epi_act=epi_act, want_stats=want_stats,
+                                want_chan_sum=want_chan_sum, impl=impl, wpk_row=wrow)
+    conv_edge9(sources, wedge, bias, cout, ksize, epi_act, out, stats, csum)
+    return out, stats, csum
+
+
 def trunk_fwd(src: Source, layers, pad_mode, impl="auto", max_ctas=0, ping=None, stats=None, sync=None):
     """The R FluidLayers of one pyramid level in ONE persistent launch (pbmc_trunk_fwd, csrc/conv_trunk.cu).
     `layers`: objects with .wpk_row, .bias, .gamma, .beta, .cout, .ksize, .cin_blks (engine._PackedLayer) -- each layer's

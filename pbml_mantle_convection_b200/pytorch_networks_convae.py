@@ -73,7 +73,38 @@ class BoundaryLearnedConvolution2D(nn.Module):
             setattr(self, name, conv)
         self.learnable_bias = nn.Parameter(torch.zeros(1, c_o, 1, 1))
 
+    # ---- kernel path (bc_x = bc_y = 1, c_o <= 16): two launches over blocked sources, see include/pbmc.h (A4)
+    def _packed(self, src_channels, dev):
+        """Interior filters as the conv kernels' images, the eight boundary filter sets as the edge kernel's image, the
+        learnable bias -- cached on the module, rebuilt when any parameter changes (in place or by re-assignment)."""
+        ws = [getattr(self, n).weight for n in self._REGIONS]
+        key = (tuple((w.data_ptr(), w._version) for w in ws), self.learnable_bias.data_ptr(), self.learnable_bias._version,
+               tuple(src_channels), str(dev))
+        c = self.__dict__.get("_pbmc_pack9")
+        if c is None or c["key"] != key:
+            wf = [full_weight(getattr(self, n)).detach().to(dev, torch.float32) for n in self._REGIONS]
+            c = {"key": key, "wpk": ops.pack_conv_weight(wf[0], list(src_channels)),
+                 "row": ops.pack_conv_weight_row(wf[0], list(src_channels)) if ops.row_supported(self.c_o, self.k, list(src_channels)) else None,
+                 "wedge": ops.pack_edge9_weights(wf[1:], list(src_channels)),
+                 "bias": ops.pad_vec(self.learnable_bias.detach().reshape(-1), self.c_o, dev)}
+            self.__dict__["_pbmc_pack9"] = c  # plain attribute: not a parameter, not a buffer, not in the state_dict
+        return c
+
+    def kernel_path_ok(self, H, W, src_channels, bc_x=1, bc_y=1):
+        pad = self.k + 1 if self.k == 5 else self.k
+        return (bc_x == 1 and bc_y == 1 and self.c_o <= 16 and self.k in (3, 5) and H >= pad and W >= pad
+                and all(c <= 64 for c in src_channels) and len(src_channels) <= L.MAX_SRC)
+
+    def forward_blocked(self, sources, src_channels, epi_act=L.ACT_NONE, want_stats=True, want_chan_sum=False):
+        """sources: ops.Source list (concat order, producer transforms fused) -> (out blocked, stats, chan_sum)."""
+        pk = self._packed(src_channels, sources[0].t.device)
+        return ops.conv_learned9(sources, pk["wpk"], pk["row"], pk["wedge"], pk["bias"], self.c_o, self.k, epi_act=epi_act,
+                                 want_stats=want_stats, want_chan_sum=want_chan_sum)
+
     def forward(self, x, bc_x=1, bc_y=1):
+        if x.is_cuda and self.kernel_path_ok(x.shape[-2], x.shape[-1], [self.c_i], bc_x, bc_y):
+            yb, _, _ = self.forward_blocked([ops.Source(ops.pack_nchw(x))], [self.c_i], want_stats=False)
+            return ops.unpack_nchw(yb, self.c_o).to(x.dtype)
         k = self.k
         pad_x = k + 1 + (bc_x - 1) if k == 5 else k + (bc_x - 1)
         pad_y = k + 1 + (bc_y - 1) if k == 5 else k + (bc_y - 1)
@@ -116,7 +147,9 @@ class FluidLayer(nn.Module):
         if c_o > 4 and c_o % 4 != 0:
             raise NotImplementedError("GroupNorm groups must coincide with 4-channel blocks (c_o % 4 == 0)")
         dev = inputs.device
-        if self.r_p == "learned":
+        if self.r_p == "learned" and inputs.is_cuda and conv.kernel_path_ok(inputs.shape[-2], inputs.shape[-1], [conv.c_i], bc_x, bc_y):
+            yb, stats, _ = conv.forward_blocked([ops.Source(ops.pack_nchw(inputs))], [conv.c_i])
+        elif self.r_p == "learned":
             y = conv(inputs, bc_x=bc_x, bc_y=bc_y)
             yb = ops.pack_nchw(y)
             # statistics of the stitched tensor: one more pass through the conv-free reduction
@@ -301,10 +334,61 @@ def _forward_learned_replayed(net, inputs, head_bc, wall_bcs):
     return tuple(None if o is None else o.clone() for o in pl.out)  # callers own what they get
 
 
-def _forward_learned(net, inputs, head_bc, wall_bcs):
-    """Learned-boundary networks: every layer runs through the
-    module-level kernels (9-region conv, fused GN/GELU, pool, bicubic); not yet one DAG."""
+def _learned_blocked_ok(net, H, W, head_bc, wall_bcs):
+    """The all-blocked kernel path of a learned-boundary NewFluidNet: every layer's 9-region conv as two launches."""
+    if head_bc != 1 or not wall_bcs or net.c_h % 4 or net.c_h > 16 or net.c_o > 4:
+        return False
+    h, w = H, W
+    for l in range(net.levels):
+        if not net.convs[l][0].layers[0].kernel_path_ok(h, w, [net.c_h]):
+            return False
+        h, w = h // 2, w // 2
+    return net.conv[1].kernel_path_ok(H, W, [net.c_h] * net.levels + [net.c_i])
+
+
+def _forward_learned_blocked(net, inputs):
+    """NewFluidNet with learned boundaries (reference :1315-1388 with BoundaryLearnedConvolution2D layers):
+    activations stay in the blocked layout from the first conv to the head; every FluidLayer is TWO launches (interior
+    conv with the producer's GroupNorm + GELU fused into its load and the statistics in its epilogue, then the ring
+    kernel); pooling is incremental, the up-sampled levels and the raw input are conv[1]'s source list (never
+    concatenated); zero-mean + curl + wall BCs are the head kernel."""
     B, _, H, W = inputs.shape
+    dev, c_h, c_i = inputs.device, net.c_h, net.c_i
+    gnp = lambda gn, c: (ops.pad_vec(gn.weight, c, dev, 1.0), ops.pad_vec(gn.bias, c, dev))
+
+    def fluid(fl, sources, chans):
+        yb, st, _ = fl.layers[0].forward_blocked(sources, chans)
+        g, b_ = gnp(fl.layers[1], c_h)
+        return ops.Source(yb, L.XFORM_GN_GELU, st, g, b_)
+
+    inp_b = ops.pack_nchw(inputs)
+    x_in = fluid(net.conv[0], [ops.Source(inp_b)], [c_i])
+    srcs, level_in = [], x_in
+    for l in range(net.levels):
+        if l > 0:
+            level_in = ops.Source(ops.avgpool2(level_in))  # pool^l(x_in), incrementally (identical composition, :1321-1322)
+        y1 = level_in
+        for r in range(net.repeats):
+            y1 = fluid(net.convs[l][r], [y1], [c_h])
+        srcs.append(y1 if l == 0 else ops.Source(ops.bicubic_up(y1, H, W)))
+    srcs.append(ops.Source(inp_b))
+    y1b, st1, _ = net.conv[1].forward_blocked(srcs, [c_h] * net.levels + [c_i])
+    g0, b0 = gnp(net.gn[0], c_h)
+    y2b, _, _ = net.conv[2].forward_blocked([ops.Source(y1b, L.XFORM_GN_GELU, st1, g0, b0)], [c_h], epi_act=L.ACT_GELU,
+                                            want_stats=False)
+    y3b, _, csum = net.conv[3].forward_blocked([ops.Source(y2b)], [c_h], want_stats=False, want_chan_sum=True)
+    u, v, p, _ = ops.head(y3b, csum, None, net.a_bound, L.HEAD_CURL if net.loss_type == "curl" else L.HEAD_MAE, net.p_pred,
+                          want_uvmax=False)
+    return _shape_outputs(net, u, v, p, inputs.dtype)
+
+
+def _forward_learned(net, inputs, head_bc, wall_bcs):
+    """Learned-boundary networks.  NewFluidNet on grids every level of which holds the
+    reference's boundary strips runs all-blocked (two launches per layer, `_forward_learned_blocked`); FluidNet (head
+    conv enlarged by bc_x = bc_y = 2) and degenerate sizes run layer by layer through the module-level forwards."""
+    B, _, H, W = inputs.shape
+    if _learned_blocked_ok(net, H, W, head_bc, wall_bcs):
+        return _forward_learned_blocked(net, inputs)
     dev = inputs.device
     x_in = net.conv[0](inputs)
     feats = []

@@ -44,6 +44,23 @@ def install(mp):
         return F.conv2d(xp, wpk, bias[:cout]), ("stats" if want_stats else None), None
 
     mp.setattr(ops, "conv_fwd", conv_fwd)
+    # learned 9-region conv (two launches on the device): the "filter images" are the full filter banks themselves and the
+    # stand-in is the numpy oracle of the reference's nine-region stitch over the concatenated, transformed sources
+    mp.setattr(ops, "row_supported", lambda cout, k, ch: True)
+    mp.setattr(ops, "pack_edge9_weights", lambda ws, ch: [w.double() for w in ws])
+
+    def conv_learned9(sources, wpk, wrow, wedge, bias, cout, k, epi_act=0, want_stats=False, want_chan_sum=False, impl="auto"):
+        x = torch.cat([_apply(s) for s in sources], 1)[:, :wpk.shape[1]]
+        sd = {"conv.weight": wpk.numpy(), "learnable_bias": bias[:cout].numpy().reshape(1, cout, 1, 1)}
+        for name, w in zip(ops.EDGE9_REGIONS, wedge):
+            sd[name + ".weight"] = w.numpy()
+        y = torch.tensor(RN.boundary_learned_conv(x.numpy(), sd, "", k, cout))
+        if epi_act == L.ACT_GELU:
+            y = F.gelu(y)
+        csum = y.sum(dim=(2, 3)) if want_chan_sum else None
+        return y, ("stats" if want_stats else None), csum
+
+    mp.setattr(ops, "conv_learned9", conv_learned9)
     mp.setattr(ops, "finalize_nchw", lambda src, c: _apply(src)[:, :c])
     mp.setattr(ops, "avgpool2", lambda src: F.avg_pool2d(_apply(src), 2))
     mp.setattr(ops, "bicubic_up", lambda src, H, W, staged=False: F.interpolate(_apply(src), size=(H, W), mode="bicubic",

@@ -655,7 +655,8 @@ def test_trunk_persistent_kernel(B, H, W, R, pad, xform0, max_ctas):
     s = src
     for i in range(R):
         yb, sti, _ = ops.conv_fwd([s], lays[i].wpk, lays[i].bias, 16, 3, pad, want_stats=True, impl="mux_f16x2", wpk_row=lays[i].wpk_row)
-        assert np.allclose(st_all[i].cpu().numpy(), sti.cpu().numpy(), rtol=1e-9, atol=1e-7)
+        # (per-thread partial sums are float32 and the rows per CTA differ between the two kernels: ~1e-7 relative)
+        assert np.allclose(st_all[i].cpu().numpy(), sti.cpu().numpy(), rtol=3e-6, atol=3e-6 * H * W)
         s = ops.Source(yb, L.XFORM_GN_GELU, sti, lays[i].gamma, lays[i].beta)
     assert (yb - out).abs().max().item() <= 2e-6 * max(1.0, float(yb.abs().max()))
     # twice in a row: scratch is re-zeroed by the call, same result bit for bit up to the statistics' atomic order
@@ -668,3 +669,54 @@ def test_trunk_refuses_a_grid_that_cannot_be_resident():
     x = torch.zeros(1, 4, 512, 512, 4, device=DEV)
     with pytest.raises(L.PbmcError):
         ops.trunk_fwd(ops.Source(x), lays, "replicate", max_ctas=8)  # 4 strips x >= 24 chunks of <= 22 rows
+
+
+@pytest.mark.parametrize("k,chans,cout,B,H,W,epi_gelu,csum", [
+    (3, [16], 16, 2, 40, 52, False, False), (5, [16], 16, 1, 37, 130, False, False), (5, [16, 16, 16, 7], 16, 1, 20, 28, False, False),
+    (3, [7], 16, 2, 9, 11, False, False), (5, [16], 16, 1, 6, 6, True, False), (5, [16], 1, 2, 24, 31, False, True),
+    (3, [16], 2, 1, 33, 140, False, True), (5, [87], 16, 1, 16, 20, False, False)])
+def test_conv_learned9_two_launches(k, chans, cout, B, H, W, epi_gelu, csum):
+    """BoundaryLearnedConvolution2D (pytorch_networks_convae.py:1022-1065, bc = 1) as pbmc_conv_fwd (interior filters, whole
+    image) + pbmc_conv_edge9 (ring of width (k-1)/2 from the eight boundary filter sets, row swap of :1060 included;
+    statistics of the first launch repaired): output, GroupNorm sums and channel sums against the float64 oracle, with
+    multi-source concatenation, a fused producer transform on the first source, wide (> 16 channel) sources, GELU epilogue
+    and the smallest legal image (one strip high)."""
+    r = rng(7 * k + H + cout)
+    ci = sum(chans)
+    xs = [r.standard_normal((B, c, H, W)) for c in chans]
+    g0, be0 = 1 + 0.2 * r.standard_normal(chans[0]), 0.2 * r.standard_normal(chans[0])
+    use_x = chans[0] % 4 == 0
+    x0 = RN.gelu(RN.group_norm(xs[0], g0, be0, chans[0] // 4)) if use_x else xs[0]
+    xcat = np.concatenate([x0] + xs[1:], 1)
+    names = ("conv",) + ops.EDGE9_REGIONS
+    sd = {n + ".weight": r.standard_normal((cout, ci, k, k)) / (k * np.sqrt(ci)) for n in names}
+    sd["learnable_bias"] = 0.3 * r.standard_normal((1, cout, 1, 1))
+    ref = RN.boundary_learned_conv(xcat, sd, "", k, cout)
+    if epi_gelu:
+        ref = RN.gelu(ref)
+    srcs = []
+    for n_, (c, x) in enumerate(zip(chans, xs)):
+        xb = ops.pack_nchw(cu(x))
+        if n_ == 0 and use_x:
+            st = torch.stack([xb.double().sum((2, 3, 4)), (xb.double() ** 2).sum((2, 3, 4))], -1).contiguous()
+            srcs.append(ops.Source(xb, L.XFORM_GN_GELU, st, ops.pad_vec(cu(g0), c, DEV, 1.0), ops.pad_vec(cu(be0), c, DEV)))
+        else:
+            srcs.append(ops.Source(xb))
+    wm = cu(sd["conv.weight"])
+    wedge = ops.pack_edge9_weights([cu(sd[n + ".weight"]) for n in ops.EDGE9_REGIONS], chans)
+    bias = ops.pad_vec(cu(sd["learnable_bias"].reshape(-1)), cout, DEV)
+    wrow = ops.pack_conv_weight_row(wm, chans) if ops.row_supported(cout, k, chans) else None
+    out, st, cs = ops.conv_learned9(srcs, ops.pack_conv_weight(wm, chans), wrow, wedge, bias, cout, k,
+                                    epi_act=L.ACT_GELU if epi_gelu else L.ACT_NONE, want_stats=True, want_chan_sum=csum)
+    got = ops.unpack_nchw(out, cout).cpu().numpy()
+    assert got.shape == ref.shape and relerr(got, ref) < 6e-6, relerr(got, ref)
+    p = (k - 1) // 2
+    ring = np.ones((H, W), bool)
+    ring[p:H - p, p:W - p] = False
+    assert relerr(got[..., ring], ref[..., ring]) < 3e-6  # the FFMA ring by itself
+    cob = (cout + 3) // 4
+    refp = np.concatenate([ref, np.zeros((B, cob * 4 - cout, H, W))], 1).reshape(B, cob, 4 * H * W)
+    ref_st = np.stack([refp.sum(-1), (refp ** 2).sum(-1)], -1)
+    assert np.allclose(st.cpu().numpy(), ref_st, rtol=3e-5, atol=2e-5 * H * W)
+    if csum:
+        assert np.allclose(cs.cpu().numpy()[:, :cout], ref.sum((2, 3)), rtol=3e-5, atol=2e-5 * H * W)

@@ -29,34 +29,40 @@ def test_unet_forward_host_logic(monkeypatch, tag):
 
 @pytest.mark.parametrize("tag,k,co,symm", [("blc3", 3, 8, False), ("blc5", 5, 8, False), ("blc3s", 3, 16, True)])
 def test_learned_boundary_conv_host_logic(monkeypatch, tag, k, co, symm):
-    """Nine regions, the reference's row swap (:1060), bc_x = bc_y = 2 enlargement, and which kernel each region goes to."""
+    """bc_x = bc_y = 1 goes to the two-launch kernel path (interior conv + ring kernel: ONE conv_learned9 call with the
+    interior filters, the eight boundary filter sets in the reference's region order and the learnable bias); the
+    bc_x = bc_y = 2 enlargement (FluidNet's head) keeps the nine-region composite with the reference's row swap (:1060)."""
     emu.install(monkeypatch)
     calls = []
-    inner = ops.conv_fwd
+    inner, inner9 = ops.conv_fwd, ops.conv_learned9
     monkeypatch.setattr(ops, "conv_fwd", lambda srcs, *a, impl="auto", wpk_row=None, **kw: (
-        calls.append((impl, wpk_row is not None, tuple(srcs[0].t.shape[-2:]))), inner(srcs, *a, impl=impl, wpk_row=wpk_row, **kw))[1])
+        calls.append(("conv_fwd", impl)), inner(srcs, *a, impl=impl, wpk_row=wpk_row, **kw))[1])
+    monkeypatch.setattr(ops, "conv_learned9", lambda *a, **kw: (calls.append(("learned9", len(a[3]))), inner9(*a, **kw))[1])
     g = load("ops")
     ci = g[tag + "_x"].shape[1]
     m = P.BoundaryLearnedConvolution2D(ci, co, k, use_symm=symm).double()
     m.load_state_dict({kk: torch.tensor(v) for kk, v in split_weights(g, tag + "_w::").items()})
     y = m(torch.tensor(g[tag + "_x"]))
     assert tuple(y.shape) == g[tag + "_y"].shape and relerr(y.numpy(), g[tag + "_y"]) < 1e-13
-    assert all(impl == "ffma" and not row for impl, row, _ in calls)  # 20 x 28: below the tensor-core threshold
+    assert calls == [("learned9", 8)]
     if tag == "blc3":
+        calls.clear()
         y2 = m(torch.tensor(g[tag + "_x"]), bc_x=2, bc_y=2)
         assert tuple(y2.shape) == g["blc3_y_bc2"].shape and relerr(y2.numpy(), g["blc3_y_bc2"]) < 1e-13
-    # a grid-sized input: interior region on the tensor-core kernels (row image packed), strips on the FFMA kernel
-    calls.clear()
+        assert len(calls) == 9 and all(c[0] == "conv_fwd" for c in calls)
+    # cached filter images follow in-place updates of ANY of the nine filter sets and of the bias
     x = torch.randn(1, ci, 40, 48, dtype=torch.float64)
-    sd = {kk: t.detach().numpy() for kk, t in m.state_dict().items()}
-    assert relerr(m(x).numpy(), RN.boundary_learned_conv(x.numpy(), sd, "", k, co, use_symm=symm)) < 1e-13
-    big = [(impl, row) for impl, row, hw in calls if min(hw) >= 32]
-    assert big == [("auto", True)] and all(impl == "ffma" for impl, row, hw in calls if min(hw) < 32)
-    # cached filter images follow in-place updates
+    for name in ("conv", "conv_top_right", "conv_left"):
+        with torch.no_grad():
+            getattr(m, name).weight.mul_(0.5)
+        sd = {kk: t.detach().numpy() for kk, t in m.state_dict().items()}
+        assert relerr(m(x).numpy(), RN.boundary_learned_conv(x.numpy(), sd, "", k, co, use_symm=symm)) < 1e-13
     with torch.no_grad():
-        m.conv.weight.mul_(0.5)
+        m.learnable_bias.add_(1.0)
     sd = {kk: t.detach().numpy() for kk, t in m.state_dict().items()}
     assert relerr(m(x).numpy(), RN.boundary_learned_conv(x.numpy(), sd, "", k, co, use_symm=symm)) < 1e-13
+    # a strip-sized input (fewer rows than the reference's boundary strips need) is refused by the kernel path
+    assert not m.kernel_path_ok(k if k == 5 else 2, 40, [ci])
 
 
 @pytest.mark.parametrize("tag", LEARNED_CASES)
