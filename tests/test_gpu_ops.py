@@ -655,7 +655,8 @@ def test_trunk_persistent_kernel(B, H, W, R, pad, xform0, max_ctas):
     s = src
     for i in range(R):
         yb, sti, _ = ops.conv_fwd([s], lays[i].wpk, lays[i].bias, 16, 3, pad, want_stats=True, impl="mux_f16x2", wpk_row=lays[i].wpk_row)
-        assert np.allclose(st_all[i].cpu().numpy(), sti.cpu().numpy(), rtol=1e-9, atol=1e-7)
+        # (per-thread partial sums are float32 and the rows per CTA differ between the two kernels: ~1e-7 relative)
+        assert np.allclose(st_all[i].cpu().numpy(), sti.cpu().numpy(), rtol=3e-6, atol=3e-6 * H * W)
         s = ops.Source(yb, L.XFORM_GN_GELU, sti, lays[i].gamma, lays[i].beta)
     assert (yb - out).abs().max().item() <= 2e-6 * max(1.0, float(yb.abs().max()))
     # twice in a row: scratch is re-zeroed by the call, same result bit for bit up to the statistics' atomic order
