@@ -237,13 +237,15 @@ int pbmc_advect_diffuse_slab(const float* T, const float* u, const float* v, con
  * boundary rows into the neighbours' ghost rows; the CTA that finishes last publishes (s + 1, local max) into every
  * rank's slot of parity (s + 1) & 1 with st.release.sys and sets steps_done = s.  pbmc_slab_sync_publish makes the
  * first publication of a run (tag steps_done + 1) from u, v; call it again -- after a host-side barrier and with the
- * blocks re-zeroed -- whenever the velocity field changes.  The kernel traps if a peer stays silent for 30 s.
+ * blocks re-zeroed -- whenever the velocity field changes.  If a peer stays silent for 10 s the kernel records it in
+ * `failed` and goes on; the host must check `failed` when it synchronises.
  * Ranks must run on DIFFERENT devices (or be launched strictly one after the other on one stream, as the
  * single-GPU tests do): a kernel that waits for a peer's kernel must never share a GPU with it. */
 #define PBMC_MAX_RANKS 16
 typedef struct {
   unsigned long long slot[2][PBMC_MAX_RANKS];
-  unsigned int steps_done, ctas_done, local_max, reserved;
+  unsigned int steps_done, ctas_done, local_max;
+  unsigned int failed; /* 0, or 0x80000000 | (bit r: rank r's publication did not arrive within 10 s); checked by the host */
 } pbmc_slab_sync;
 int pbmc_slab_sync_publish(const float* u, const float* v, int H, int W, pbmc_slab_sync* self,
                            pbmc_slab_sync* const* peers_h, int rank, int world, void* stream);

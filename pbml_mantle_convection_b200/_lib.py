@@ -61,7 +61,7 @@ MAX_RANKS = 16
 
 class SlabSync(C.Structure):
     _fields_ = [("slot", (C.c_uint64 * MAX_RANKS) * 2), ("steps_done", C.c_uint), ("ctas_done", C.c_uint),
-                ("local_max", C.c_uint), ("reserved", C.c_uint)]
+                ("local_max", C.c_uint), ("failed", C.c_uint)]
 
 
 class Edge9Desc(C.Structure):

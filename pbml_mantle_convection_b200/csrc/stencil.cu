@@ -53,7 +53,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // Wait until every rank has published its max|u|,|v| for step `s` (tag == s) in THIS rank's slots and return the
 // global maximum (float bits).  Lane r polls rank r's slot; the acquire also orders the neighbours' ghost-row stores
 // of step s - 1 (issued before their release) before this step's reads.  Whole warp calls it.
-__device__ __forceinline__ uint32_t slab_wait_global_max(const pbmc_slab_sync* self, uint32_t s, int world) {
+__device__ __forceinline__ uint32_t slab_wait_global_max(pbmc_slab_sync* self, uint32_t s, int world) {
   const int lane = threadIdx.x & 31;
   uint32_t bits = 0u;
   if (lane < world) {
@@ -64,7 +64,13 @@ __device__ __forceinline__ uint32_t slab_wait_global_max(const pbmc_slab_sync* s
       do {
         __nanosleep(64);
         v = ld_acquire_sys_u64(slot);
-        if ((uint32_t)(v >> 32) != s && globaltimer_ns() - t0 > 30000000000ull) __trap();  // 30 s: a peer died; fail loudly
+        if ((uint32_t)(v >> 32) != s && globaltimer_ns() - t0 > 10000000000ull) {
+          // 10 s without the peer's publication: record WHO is missing (bit r = rank r, bit 31 = failed) and go on
+          // with what is there -- the host checks `failed` at its next synchronisation point and raises; the context
+          // stays usable, so the sync blocks can be read for the post-mortem
+          atomicOr(&self->failed, 0x80000000u | (1u << lane));
+          break;
+        }
       } while ((uint32_t)(v >> 32) != s);
     }
     bits = (uint32_t)v;

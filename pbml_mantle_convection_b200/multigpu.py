@@ -157,7 +157,9 @@ class SlabStencil:
         self._buf.zero_()
         grp = self.group if self.group is not None else dist.group.WORLD
         hdl = symm_mem.rendezvous(self._buf, group=grp)
-        base = [int(p) for p in hdl.buffer_ptrs]
+        # peers' addresses of THIS tensor: the handle lists the base of the allocation the tensor lives in on every rank
+        off = self._buf.data_ptr() - int(hdl.buffer_ptrs[s.rank])
+        base = [int(p) + off for p in hdl.buffer_ptrs]
         row_bytes, slot_bytes = W * 4, rows_max * W * 4
         # neighbour ghost rows, per output slot k: up neighbour's LAST local row, down neighbour's local row 0
         self._peer_up = [base[s.rank - 1] + k * slot_bytes + (sizes[s.rank - 1].rows - 1) * row_bytes if s.up else 0 for k in (0, 1)]
@@ -169,7 +171,8 @@ class SlabStencil:
             self._sync = symm_mem.empty((ops.SLAB_SYNC_BYTES // 8,), dtype=torch.int64, device=dev)
             self._sync.zero_()
             self._sync_handle = symm_mem.rendezvous(self._sync, group=grp)
-            self._sync_ptrs = [int(p) for p in self._sync_handle.buffer_ptrs]
+            off_s = self._sync.data_ptr() - int(self._sync_handle.buffer_ptrs[s.rank])
+            self._sync_ptrs = [int(p) + off_s for p in self._sync_handle.buffer_ptrs]
 
             def step_flags(T, u, v, _uvmax_unused):
                 k = self._slot
@@ -334,12 +337,24 @@ class SlabStencil:
         self.last_dt = dt
         return dt
 
+    def check_sync(self):
+        """Flag mode: raise if a step kernel gave up waiting for a peer's publication (pbmc_slab_sync.failed)."""
+        if getattr(self, "_sync", None) is None:
+            return
+        words = self._sync.view(torch.int32)
+        failed = int(words[2 * 2 * 16 + 3].item()) & 0xFFFFFFFF
+        if failed:
+            missing = [r for r in range(self.slab.world) if failed >> r & 1]
+            raise RuntimeError(f"slab step on rank {self.slab.rank}: no publication from rank(s) {missing} within 10 s "
+                               f"(steps done {int(words[2 * 2 * 16].item())})")
+
     def close(self):
         """Drop the captured graph and the peer mappings (collective: every rank calls it) so that the process group can
         be destroyed cleanly afterwards."""
         self._graph = None
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
+            self.check_sync()
         if self.slab.world > 1 and dist.is_initialized():
             dist.barrier(group=self.group)
         for name in ("_sync_handle", "_symm_handle", "_sync", "_buf"):
@@ -350,6 +365,7 @@ class SlabStencil:
     # ------------------------------------------------------------------ outputs
     def gather(self):
         """Whole-grid T [H, W] on every rank (all_gather of the owned rows; diagnostics / tests)."""
+        self.check_sync()
         own = self.slab.owned(self.T)[0].contiguous()
         if self.slab.world == 1:
             return own

@@ -141,6 +141,7 @@ def test_flag_synchronised_slab_step_emulated(H, W, world):
     st_view = sync.cpu().numpy().view(np.uint32).reshape(world, -1)
     base = 2 * 16 * 2  # uint32 index of steps_done
     assert (st_view[:, base] == steps).all() and (st_view[:, base + 1] == 0).all() and (st_view[:, base + 2] == 0).all()
+    assert (st_view[:, base + 3] == 0).all()  # nobody gave up waiting
     # new velocity field: blocks re-zeroed, tags restart, dt follows the new maximum
     for st in sts:
         st.u, st.v = st.u * 0.5, st.v * 0.25
