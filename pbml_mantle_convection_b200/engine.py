@@ -38,6 +38,41 @@ class _PackedLayer:
         return s
 
 
+class PackedNetwork:
+    """Repacked filters / bias / GroupNorm affine of every layer of a (non-learned) NewFluidNet: conv0, trunk[l][r],
+    conv1, conv2, conv3 as `_PackedLayer`s.  Needs no library context: the fused engine and the slab-decomposed
+    surrogate both start from it."""
+
+
+def pack_network(m, dev) -> PackedNetwork:
+    if m.r_p == "learned":
+        raise NotImplementedError("fused engine covers zeros/replicate/reflect padding; r_p='learned' "
+                                  "runs through BoundaryLearnedConvolution2D.forward")
+    from .symmetric_layers_torch import _check_conv_supported
+
+    f32 = lambda t: None if t is None else t.detach().to(dev, torch.float32)
+
+    def fluid(fl, cin):
+        conv, gn = fl.layers[0], fl.layers[1]
+        _check_conv_supported(conv)  # dilation / stride / groups != 1 would silently compute another operator
+        w = f32(conv.weight)
+        if getattr(conv, "symmetry", None) is not None:
+            w = ops.expand_symmetric(w, conv.out_channels)
+        return _PackedLayer(w, f32(conv.bias), f32(gn.weight), f32(gn.bias), [cin], dev)
+
+    pk = PackedNetwork()
+    pk.conv0 = fluid(m.conv[0], m.c_i)
+    pk.trunk = [[fluid(m.convs[l][r], m.c_h) for r in range(m.repeats)] for l in range(m.levels)]
+    c1, c2, c3 = m.conv[1], m.conv[2], m.conv[3]
+    for c in (c1, c2, c3):
+        _check_conv_supported(c)
+    pk.conv1 = _PackedLayer(f32(c1.weight), f32(c1.bias), f32(m.gn[0].weight), f32(m.gn[0].bias),
+                            [m.c_h] * m.levels + [m.c_i], dev)
+    pk.conv2 = _PackedLayer(f32(c2.weight), f32(c2.bias), None, None, [m.c_h], dev)
+    pk.conv3 = _PackedLayer(f32(c3.weight), f32(c3.bias), None, None, [m.c_h], dev)
+    return pk
+
+
 class SurrogateEngine:
     """Owns everything device-side that belongs to ONE network instance on ONE device."""
 
@@ -82,31 +117,8 @@ class SurrogateEngine:
         key = self._weights_key()
         if not force and key == self._key:
             return
-        m, dev = self.net_module, self.device
-        if m.r_p == "learned":
-            raise NotImplementedError("fused engine covers zeros/replicate/reflect padding; r_p='learned' "
-                                      "runs through BoundaryLearnedConvolution2D.forward")
-        f32 = lambda t: None if t is None else t.detach().to(dev, torch.float32)
-
-        from .symmetric_layers_torch import _check_conv_supported
-
-        def fluid(fl, cin):
-            conv, gn = fl.layers[0], fl.layers[1]
-            _check_conv_supported(conv)  # dilation / stride / groups != 1 would silently compute another operator
-            w = f32(conv.weight)
-            if getattr(conv, "symmetry", None) is not None:
-                w = ops.expand_symmetric(w, conv.out_channels)
-            return _PackedLayer(w, f32(conv.bias), f32(gn.weight), f32(gn.bias), [cin], dev)
-
-        self.conv0 = fluid(m.conv[0], m.c_i)
-        self.trunk = [[fluid(m.convs[l][r], m.c_h) for r in range(m.repeats)] for l in range(m.levels)]
-        c1, c2, c3 = m.conv[1], m.conv[2], m.conv[3]
-        for c in (c1, c2, c3):
-            _check_conv_supported(c)
-        self.conv1 = _PackedLayer(f32(c1.weight), f32(c1.bias), f32(m.gn[0].weight), f32(m.gn[0].bias),
-                                  [m.c_h] * m.levels + [m.c_i], dev)
-        self.conv2 = _PackedLayer(f32(c2.weight), f32(c2.bias), None, None, [m.c_h], dev)
-        self.conv3 = _PackedLayer(f32(c3.weight), f32(c3.bias), None, None, [m.c_h], dev)
+        pk = pack_network(self.net_module, self.device)
+        self.conv0, self.trunk, self.conv1, self.conv2, self.conv3 = pk.conv0, pk.trunk, pk.conv1, pk.conv2, pk.conv3
         self._key = key
         self._build_desc()
 

@@ -283,6 +283,19 @@ def conv_learned9(sources, wpk, wrow, wedge, bias, cout, ksize, epi_act=L.ACT_NO
     return out, stats, csum
 
 
+def block_stats(yb):
+    """(sum, sum^2) per (sample, 4-channel block) of a blocked tensor [B, CB, h, W, 4], float64 [B, CB, 2]: the quantity the
+    conv epilogues accumulate, here for a FEW rows (ghost-row corrections of the slab-decomposed surrogate) with torch
+    reductions."""
+    g = yb.double()
+    return torch.stack([g.sum(dim=(2, 3, 4)), (g * g).sum(dim=(2, 3, 4))], -1)
+
+
+def chan_sums(yb):
+    """Per-channel sums of a blocked tensor [B, CB, h, W, 4] -> float64 [B, CB * 4]."""
+    return yb.double().sum(dim=(2, 3)).reshape(yb.shape[0], -1)
+
+
 def trunk_fwd(src: Source, layers, pad_mode, impl="auto", max_ctas=0, ping=None, stats=None, sync=None):
     """The R FluidLayers of one pyramid level in ONE persistent launch (pbmc_trunk_fwd, csrc/conv_trunk.cu).
     `layers`: objects with .wpk_row, .bias, .gamma, .beta, .cout, .ksize, .cin_blks (engine._PackedLayer) -- each layer's

@@ -1,0 +1,67 @@
+"""Slab-decomposed surrogate time step on the GPU.  One GPU is available to the test
+box, so the ranks are threads of one process (`slab_surrogate.ThreadComm`: every rank drives the REAL kernels on the same
+device and stream; halo rows and the GroupNorm / zero-mean / max|u| reductions go through a shared mailbox).  The gathered
+fields after two full time steps must equal the single-GPU rollout.  Real NCCL: tools/slab_surrogate_check.py under torchrun."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+import pbml_mantle_convection_b200 as P
+from oracle import ref_numpy as RN
+from pbml_mantle_convection_b200 import slab_surrogate as SS
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+PARAMS = (6.79733173, 475523342.0, 2.58574662)
+
+
+def _net(levels, repeats):
+    torch.manual_seed(7)
+    net = P.NewFluidNet(levels, 7, 16, 2, DEV, act_fn="gelu", r_p="replicate", loss_type="curl", use_symm=True, a_bound=10,
+                        repeats=repeats, f=3, p_pred=True).to(DEV).eval()
+    with torch.no_grad():
+        for n, p_ in net.named_parameters():
+            if "layers.1" in n or n.startswith("gn."):
+                p_.add_(0.1 * torch.randn_like(p_))
+    return net
+
+
+@pytest.mark.parametrize("levels,repeats,H,W,world", [(4, 2, 96, 128, 2), (4, 2, 96, 200, 4), (6, 4, 384, 256, 2), (3, 1, 48, 64, 3)])
+def test_slab_surrogate_two_steps_equal_single_gpu(levels, repeats, H, W, world):
+    net = _net(levels, repeats)
+    xc, yc = RN.synthetic_grid(H, W)
+    T0 = RN.synthetic_T0(H, W, seed=3).astype(np.float32)
+    ens = P.EnsembleRollout(net, H, W, [PARAMS], DEV, xc=xc, yc=yc, cn_max=0.99, per_member_dt=False)
+    ens.set_T(T0[None])
+    ens.step(2)
+    u_r, v_r, p_r, _ = ens.fields()
+    T_r, dt_r = ens.T[0].clone(), ens.state.dt_seq[:2, 0].clone()
+    shared = SS.ThreadComm.Shared(world)
+    out, err = [None] * world, []
+
+    def run(r):
+        try:
+            torch.cuda.set_device(DEV)
+            s = SS.SlabSurrogate(net, H, W, xc[0], yc[:, 0], PARAMS, SS.ThreadComm(shared, r), DEV)
+            s.set_T(T0)
+            dts = [s.step().clone(), s.step().clone()]
+            out[r] = (s.gather(s.T)[0], s.gather(s.u)[0], s.gather(s.v)[0], s.gather(s.p)[0], torch.cat(dts))
+        except Exception as e:
+            err.append(e)
+            shared.barrier.abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not err, err
+    torch.cuda.synchronize()
+    for r in range(world):
+        T, u, v, p, dts = out[r]
+        assert tuple(T.shape) == (H, W)
+        # same kernels, same per-pixel arithmetic; only the order of the double-precision statistics sums differs
+        for name, a, b in (("u", u, u_r[0]), ("v", v, v_r[0]), ("p", p, p_r[0])):
+            assert (a - b).abs().max().item() <= 2e-5 * float(b.abs().max()), (name, r)
+        assert (T - T_r).abs().max().item() <= 2e-6, r
+        assert torch.allclose(dts, dt_r, rtol=2e-6, atol=0.0), r
