@@ -212,6 +212,7 @@ class SlabStencil:
             self.T = self._buf[0, :self.slab.rows].unsqueeze(0)
             torch.cuda.synchronize(self.device)
             dist.barrier(group=self.group)
+            self._republish()  # flag mode: tags restart at 1 with this velocity field's maximum
 
     def _republish(self):
         """Flag mode: (re)start the tag sequence for the current velocity field.  Host-side barrier on both sides of the

@@ -16,11 +16,11 @@ import bench  # noqa: E402
 def dump(st, tag):
     torch.cuda.synchronize()
     w = st._sync.cpu().numpy().view(np.uint32)
-    slots = w[:128].reshape(2, 16, 2)  # [par][rank][lo = float bits, hi = tag]
+    slots = w[:64].reshape(2, 16, 2)  # [par][rank][lo = float bits, hi = tag]
     world = st.slab.world
     txt = " ".join(f"p{p}r{r}:(tag {int(slots[p, r, 1])}, {struct.unpack('f', struct.pack('I', int(slots[p, r, 0])))[0]:.4g})"
                    for p in range(2) for r in range(world))
-    print(f"[rank {st.slab.rank}] {tag}: {txt} | steps_done {w[128]} ctas_done {w[129]} local_max {w[130]:#x} failed {w[131]:#x}",
+    print(f"[rank {st.slab.rank}] {tag}: {txt} | steps_done {w[64]} ctas_done {w[65]} local_max {w[66]:#x} failed {w[67]:#x}",
           flush=True)
 
 
