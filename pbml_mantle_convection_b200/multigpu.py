@@ -201,7 +201,14 @@ class SlabStencil:
     # ------------------------------------------------------------------ state
     def set_local(self, T, u, v):
         f = lambda a: torch.as_tensor(a).to(self.device, torch.float32).reshape(1, self.slab.rows, self.W).contiguous().clone()
-        self.T, self.u, self.v = f(T), f(u), f(v)
+        self.T = f(T)
+        if self.u is not None and self.halo == "p2p" and tuple(self.u.shape) == (1, self.slab.rows, self.W):
+            # same buffers: a captured graph (it holds their addresses) stays valid
+            self.u.copy_(torch.as_tensor(u).reshape(self.u.shape))
+            self.v.copy_(torch.as_tensor(v).reshape(self.v.shape))
+        else:
+            self.u, self.v = f(u), f(v)
+            self._graph = None
         self._uv_valid = False
         if self.halo == "p2p":
             # neighbours may still be pushing rows of an earlier run into this rank's buffers
@@ -221,8 +228,7 @@ class SlabStencil:
             return
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)
-        self._sync.zero_()
-        self._graph = None  # the ping-pong phase restarts with the tags
+        self._sync.zero_()  # (a captured graph stays valid: the kernels read tags and step counters from memory)
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)
         self._ops.slab_sync_publish(self.u, self.v, self._sync_ptrs[self.slab.rank], self._sync_ptrs, self.slab.rank)
@@ -236,6 +242,7 @@ class SlabStencil:
         self.u = torch.as_tensor(u).to(self.device, torch.float32).reshape(1, self.slab.rows, self.W).contiguous()
         self.v = torch.as_tensor(v).to(self.device, torch.float32).reshape(1, self.slab.rows, self.W).contiguous()
         self._uv_valid = False
+        self._graph = None  # new velocity buffers: a captured graph holds the old addresses
         if self.halo == "p2p" and self.dt_sync == "flags":
             if self._slot != 0:
                 raise RuntimeError("set_velocity in flag mode needs an even number of steps since set_local (ping-pong phase)")
@@ -318,16 +325,17 @@ class SlabStencil:
                 self._step_once()
                 done += 2
                 self._warm = True
-            if getattr(self, "_graph", None) is None:
+            gs = max(2, int(getattr(self, "graph_steps", 2)) // 2 * 2)  # whole ping-pong periods per captured graph
+            if getattr(self, "_graph", None) is None or getattr(self, "_graph_len", 0) != gs:
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._step_once()
-                    dt = self._step_once()
-                self._graph = g
-            while n - done >= 2:
+                    for _ in range(gs):
+                        dt = self._step_once()
+                self._graph, self._graph_len = g, gs
+            while n - done >= gs:
                 self._graph.replay()
-                done += 2
+                done += gs
             dt = self._dt
             self.T = self._buf[0, :self.slab.rows].unsqueeze(0)
             self.n_steps += done

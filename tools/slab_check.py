@@ -20,6 +20,7 @@ def main():
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     halo = sys.argv[4] if len(sys.argv) > 4 else "nccl"
     dt_sync = sys.argv[5] if len(sys.argv) > 5 else "flags"  # p2p only: "flags" = reduction inside the kernel, "nccl" = all_reduce
+    graph_steps = int(sys.argv[6]) if len(sys.argv) > 6 else 2  # time steps per captured CUDA graph (0: no graph, eager launches)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -30,14 +31,17 @@ def main():
     ut, vt = bench.slab_velocity(torch.tensor(xc[0], dtype=torch.float32), torch.tensor(yc[:, 0], dtype=torch.float32), H, W)
     u, v = ut.numpy(), vt.numpy()
     st = MG.SlabStencil(H, W, xc[0], yc[:, 0], rank, world, dev, raq=2.0, halo=halo, dt_sync=dt_sync)
+    st.graph_steps = graph_steps
     st.scatter(T, u, v)
     st.step(3)  # warm-up (NCCL communicators, module load)
+    st.scatter(T, u, v)
+    st.step(max(4, 2 * graph_steps), use_graph=graph_steps > 0)  # untimed: capture
     st.scatter(T, u, v)
     torch.cuda.synchronize()
     dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    st.step(steps)
+    st.step(steps, use_graph=graph_steps > 0)
     b.record()
     torch.cuda.synchronize()
     ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
@@ -49,7 +53,7 @@ def main():
         ref.scatter(T, u, v)
         ref.step(steps)
         ok = bool(torch.equal(ref.gather(), full)) and bool(torch.isfinite(full).all())
-        print(f"slab_check H={H} W={W} world={world} steps={steps} halo={halo} dt_sync={st.dt_sync}: identical_to_single_gpu={ok} "
+        print(f"slab_check H={H} W={W} world={world} steps={steps} halo={halo} dt_sync={st.dt_sync} graph_steps={graph_steps}: identical_to_single_gpu={ok} "
               f"{H * W * steps / (ms.item() * 1e-3):.4g} cell-updates/s ({ms.item() / steps:.3f} ms/step)", flush=True)
     st.close()
     dist.barrier()
