@@ -20,6 +20,14 @@ Two ways to advance:
   * `attempt_resident(ens, ...)` -- an `EnsembleRollout` advances `check_every` steps per CUDA-graph replay with T, u, v
     and dt on the device; host work (time bookkeeping, cadence checks, snapshots) happens once per block.
 
+External energy solver (the `ML_STOKES` / `ML_PRE` modes and the `intervene_TS` interventions of mode "ML", `:486-505`,
+`:618-630`): the reference calls GAIA's `sim.doTimestep()` with the surrogate's velocities already written into the state
+and takes T and dt from it.  `attempt(..., energy_step=f)` is that hook: `f(state) -> dt` advances `state["T"]` in place
+(it sees `state["v"]`, `state["P"]`, `state["V"]` of this step) every step for modes other than "ML", and on every
+`intervene_TS`-th step in mode "ML"; the driver then applies the reference's wall rows / side columns / clip(0, 2)
+(`:624-629`) and feeds the result to the next surrogate call.  With `TS(stokes, None, ...)` (no ADNet, `:488-500`) the
+surrogate only supplies (u, v, p, V): `dts` is empty and the time step is the callback's.
+
 One deliberate difference: the reference never feeds `T_new` back into `Tp` between GAIA steps (`Tp` is only
 refreshed from GAIA's state, `:618-630`; in pure-ML mode the network would see the initial field forever).  Without
 GAIA the state's T *is* the surrogate's T, so `Tp <- T_new[1]` here -- the semantics of `TS(ts=N)`'s own loop (:377).
@@ -52,9 +60,13 @@ def write_logs(out_dir, mode, snapshots, TS_vec, t_vec, T_vec):
 
 
 def attempt(ts_net, T0, xcc, ycc, raq, fkt, fkp, raq_nd, fkt_nd, fkp_nd, t_end, out_dir, save_every=0.0, write_every=0.0,
-            mode="ML", t=0.0, n_step=0, p_pred=True, max_steps=None, sdf=None, sdf2=None):
-    """Pure-ML `attempt`: returns (t, n_step, logs) with logs = (snapshots, TS_vec, t_vec, T_vec) dicts keyed by mode.
-    T0, xcc, ycc: [1,1,H,W] float64 host tensors (what `:560-581` builds from GAIA's state)."""
+            mode="ML", t=0.0, n_step=0, p_pred=True, max_steps=None, sdf=None, sdf2=None, energy_step=None, intervene_TS=0,
+            core_cool=False):
+    """`attempt(t, n_step)` of advect_wi_gaia.py:538-679 without GAIA: returns (t, n_step, logs) with logs = (snapshots,
+    TS_vec, t_vec, T_vec) dicts keyed by mode.  T0, xcc, ycc: [1,1,H,W] float64 host tensors (what `:560-581` builds
+    from GAIA's state).  energy_step / intervene_TS / core_cool: the external-energy-solver hook, see the module docstring."""
+    if mode != "ML" and energy_step is None and getattr(ts_net, "ad", True) is None:
+        raise ValueError(f"mode {mode!r} with a TS that has no ADNet needs energy_step (nothing would advance T)")
     snapshots, TS_vec, t_vec, T_vec = _new_logs(mode)
     H, W = T0.shape[-2:]
     n = H * W
@@ -77,9 +89,21 @@ def attempt(ts_net, T0, xcc, ycc, raq, fkt, fkp, raq_nd, fkt_nd, fkp_nd, t_end, 
         if p_pred and p is not None:
             state["P"][:] = p.detach().cpu().numpy().flatten()
         state["V"][:] = V.flatten()
-        state["T"][:] = T_new[1].clone().detach().cpu().numpy().flatten()  # :633-635
-        dt = float(dts[1].clone().detach().cpu().numpy())
-        Tp = T_new[1].detach().cpu().reshape(T0.shape)  # see the module docstring
+        external = energy_step is not None and (mode != "ML" or (intervene_TS and n_step % intervene_TS == 0))
+        if external:
+            dt = float(energy_step(state))  # sim.doTimestep(): the external solver advances state["T"] with these velocities, :618-620
+            Tp = torch.tensor(state["T"], dtype=T0.dtype).view(T0.shape).clone()
+            if not core_cool:
+                Tp[:, :, 0, :] = 1.0
+            Tp[:, :, -1, :] = 0.0
+            Tp[:, :, :, 0] = Tp[:, :, :, 1]
+            Tp[:, :, :, -1] = Tp[:, :, :, -2]
+            Tp = torch.clip(Tp, 0.0, 2.0)  # :621-629
+            state["T"][:] = Tp.numpy().flatten()
+        else:
+            state["T"][:] = T_new[1].clone().detach().cpu().numpy().flatten()  # :633-635
+            dt = float(dts[1].clone().detach().cpu().numpy())
+            Tp = T_new[1].detach().cpu().reshape(T0.shape)  # see the module docstring
         t += dt
         T_vec[mode].append(np.copy(state["T"].mean()))
         t_vec[mode].append(np.copy(t))

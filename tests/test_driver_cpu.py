@@ -56,3 +56,40 @@ def test_attempt_respects_max_steps_and_restart_arguments(tmp_path):
                                 t=5.0, n_step=40, max_steps=43, p_pred=False)
     assert n_step == 43 and abs(t - 5.75) < 1e-12
     assert (tmp_path / "snapshots_ML_STOKES.pkl").exists() and np.all(logs[0]["ML_STOKES"]["P"][-1] == 0.0)
+
+
+def test_attempt_external_energy_solver_hook(tmp_path):
+    """ML_STOKES (advect_wi_gaia.py:486-505, :618-630): the surrogate supplies the velocities, an external solver advances T
+    and returns dt every step; in mode "ML" it intervenes every `intervene_TS`-th step.  The driver applies the reference's
+    wall rows / side columns / clip(0, 2) to what the solver returns."""
+    xcc, ycc = _grid()
+    T0 = torch.full((1, 1, H, W), 0.5, dtype=torch.float64)
+    s = torch.tensor(1.0, dtype=torch.float64)
+    seen = []
+
+    def no_ad_ts(Tp, *a):  # TS(stokes, None, ...): no ADNet -> x has no entry 1, dts is empty
+        f = lambda c: torch.full_like(Tp, c)
+        return {0: Tp}, {}, f(1.0), f(2.0), f(3.0), f(4.0)
+
+    def solver(state):
+        seen.append((state["v"][0, 0], state["v"][0, 1], state["V"][0]))
+        state["T"][:] = state["T"] + 1.0  # far above 2: must be clipped; walls must be re-imposed
+        return 0.5
+
+    t, n_step, (snaps, TS_vec, t_vec, T_vec) = D.attempt(no_ad_ts, T0, xcc, ycc, s, s, s, s, s, s, t_end=1.4, out_dir=str(tmp_path),
+                                                       mode="ML_STOKES", energy_step=solver)
+    assert n_step == 3 and abs(t - 1.5) < 1e-12 and seen == [(1.0, 2.0, 4.0)] * 3
+    last = snaps["ML_STOKES"]["T"][-1].reshape(H, W)
+    assert np.all(last[0] == 1.0) and np.all(last[-1] == 0.0) and np.all(last[1:-1] == 2.0) and (tmp_path / "T_vec_ML_STOKES.pkl").exists()
+    # mode "ML": the surrogate's own T / dt except on every 2nd step
+    seen.clear()
+    t, n_step, (snaps, _, t_vec, _) = D.attempt(fake_ts, T0, xcc, ycc, s, s, s, s, s, s, t_end=100.0, out_dir=str(tmp_path), max_steps=4,
+                                                energy_step=solver, intervene_TS=2)
+    assert len(seen) == 2 and np.allclose(t_vec["ML"], [0.0, 0.25, 0.75, 1.0, 1.5])
+    # without a solver a TS that has no ADNet cannot advance T in a non-ML mode
+    class _NoAd:
+        ad = None
+        __call__ = staticmethod(no_ad_ts)
+    import pytest
+    with pytest.raises(ValueError):
+        D.attempt(_NoAd(), T0, xcc, ycc, s, s, s, s, s, s, t_end=1.0, out_dir=str(tmp_path), mode="ML_STOKES")

@@ -430,3 +430,17 @@ def test_forward_with_tma_staged_levels_is_bit_identical():
     per = net(x)
     for a, b in zip(ref, per):
         assert (a - b).abs().max().item() <= 1e-5 * float(a.abs().max())
+
+
+def test_TS_without_adnet_is_the_ML_STOKES_mode():
+    """advect_wi_gaia.py:486-500: `TS(model_uvp, None, ...)` -- the surrogate only supplies (u, v, p, V) to an external
+    energy solver; no T is advanced, `dts` stays empty (reference :453: the ADNet branch is skipped)."""
+    g, nz = load("roll64x96"), noise("roll64x96")["step1"]
+    net = make_net(RN.NetSpec(levels=4), load_weights("roll64x96"), impl="auto")
+    ts = P.TS(net, None, DEV, ts=1, scale=True, p_pred=True, net="newfluidnet")
+    x, dts, u, v, p, V = _ts_call(ts, g["T0"], g["xc"], g["yc"])
+    H, W = g["T0"].shape
+    assert sorted(x.keys()) == [0] and dts == {} and tuple(u.shape) == (1, 1, H, W) and u.dtype == torch.float64
+    for name, a, ref in (("u", u, g["u1"]), ("v", v, g["v1"]), ("p", p, g["p1"])):
+        assert relerr(a[0, 0].cpu().numpy(), ref) <= field_bound(nz[name]), name
+    assert np.abs(V[0, 0].cpu().numpy() - g["V1"]).max() <= max(2e-6, 3 * nz["V_maxabs"])
