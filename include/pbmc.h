@@ -160,7 +160,7 @@ int pbmc_conv_fwd(const pbmc_conv_desc* desc_h, void* stream);
  * Same sources (concat order, fused producer transforms), same `out` / statistics buffers in both calls.
  *   wedge  float [8][cin_blks][k*k][16][4]: region (top_left, top_right, bottom_left, bottom_right, top, bottom, left,
  *          right -- the reference's names), input-channel block of the concatenation, tap dy*k+dx, c_out, c_in % 4;
- *          zero padded (ops.pack_edge9_weights).  c_out <= 16, every source <= 64 channels. */
+ *          zero padded (ops.pack_edge9_weights).  c_out <= 16, every source <= 128 channels. */
 typedef struct {
   pbmc_src src[PBMC_MAX_SRC];
   int nsrc;

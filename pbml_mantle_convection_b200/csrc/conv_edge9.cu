@@ -27,7 +27,7 @@ namespace pbmc {
 
 constexpr int E9_PX = 8;          // ring pixels per CTA
 constexpr int E9_THREADS = E9_PX * 16;
-constexpr int E9_MAXC = 64;       // channels per source (16 blocks); wider sources are split by the caller
+constexpr int E9_MAXC = 128;      // channels per source (32 blocks); wider sources are split by the caller
 
 struct Edge9Params {
   pbmc_src src[PBMC_MAX_SRC];

@@ -15,6 +15,11 @@
 //     layer r: a grid-wide arrive/poll counter (one per sample: samples are independent) in global memory.  The
 //     barrier also publishes the neighbours' boundary rows; everything read after it comes from L2 (ld.global.cg:
 //     L1 may still hold the lines of two layers ago, the ping-pong buffer's previous content).
+// Tried and withdrawn (round 2, profiles/r2_ncu_trunk_512_remap.txt): a staging map in which warp q owns channel block q of
+// the whole row (GroupNorm coefficients in registers, no ld.shared while staging).  It cut the LSU shared-memory
+// wavefronts by 20 % (5.1 M -> 4.1 M per launch) but needed 21 % more instructions (8-byte stores, four positions per
+// lane) and was SLOWER: 72.7 vs 66.6 us per 4-layer launch at 512^2.  The kernel is bound by issued instructions and the
+// hand-off latencies between its phases, not by the shared-memory pipe.
 // Every CTA of the launch must be resident at once (the dispatcher only takes the kernel when the grid fits the
 // caller's CTA budget; the rollout's per-level budgets sum to <= 148).  A CTA that waits longer than 2 s traps.
 #include <stdlib.h>
@@ -134,48 +139,31 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
 
   if (warp < CT_WORKERS) {
     // ================================================================ workers: stage rows, drain accumulators
-    // Staging map: warp wq of a group owns CHANNEL BLOCK wq (4 channels = one GroupNorm group) of the whole row -- lane i
-    // takes positions i, i + 32, i + 64, i + 96 (and lanes 0, 1 the two halo positions 128, 129).  Its 4 scale and 4
-    // shift values live in registers for the whole layer: no shared-memory load in the staging path (the broadcast
-    // ld.shared.v4 of all 32 coefficients per row were 60 % of the kernel's LSU shared-memory wavefronts and shared the
-    // pipe with the tensor core's operand fetch, profiles/r2_ncu_trunk_512.txt).
     const int g = warp >> 2, wq = warp & 3;
-    // source column / validity of position lane + 32 j (j = 0..3; j = 4: the halo positions 128, 129 on lanes 0, 1),
-    // recomputed where needed: a few integer instructions per row instead of ten live registers
-    auto src_col = [&](int j, bool& ok) {
-      const int gxp = x0 - P + lane + 32 * j;
-      const int sx = pad_index(gxp, W, p.pad_mode);
-      ok = gxp < W + P && sx >= 0 && (j < 4 || lane < 2);  // columns past the image feed masked outputs only
-      return sx < 0 ? 0 : sx;
-    };
-    const size_t blk_off = ((size_t)b * 4 + wq) * plane_px * 4;
-    const size_t rstride = (size_t)W * 4;
+    const int i = wq * 32 + lane;  // position in the staged row = input column x0 - 1 + i
+    const int gxp = x0 - P + i;
+    const int sx = pad_index(gxp, W, p.pad_mode);
+    const bool col_ok = gxp < W + P && sx >= 0;  // columns past the image feed masked outputs only
+    const int hch = lane & 15, he = lane >> 4;   // halo positions 128, 129: warp 0 of a group, lane = (position, channel)
+    const int gxh = x0 - P + 128 + he;
+    const int hsx = pad_index(gxh, W, p.pad_mode);
+    const bool h_on = wq == 0 && gxh < W + P && hsx >= 0;
+    const size_t in_boff = (size_t)b * 4 * plane_px * 4;
+    const size_t c_off = in_boff + (size_t)(sx < 0 ? 0 : sx) * 4;
+    const size_t h_off_g = in_boff + (size_t)(hch >> 2) * plane_px * 4 + (size_t)(hsx < 0 ? 0 : hsx) * 4 + (hch & 3);
+    const size_t pstride = plane_px * 4, rstride = (size_t)W * 4;
     struct Row {
-      float4 v[4];
-      float4 h;
+      float4 v0, v1, v2, v3;
+      float h;
       bool ok;
     };
-    // operand image of one staged row: [part hi|lo][chunk = channels 0-7, 8-15][position][8 channels] 16-bit
-    const uint32_t st_off = (uint32_t)((wq >> 1) * PLANE * 16 + (wq & 1) * 8);
-    const uint32_t as_addr = smem_u32(As) + st_off + (uint32_t)lane * 16u;
-    auto sts2 = [](uint32_t addr, uint32_t q0, uint32_t q1) {
-      asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(q0), "r"(q1) : "memory");
+    const uint32_t as_addr = smem_u32(As) + (uint32_t)i * 16u;
+    const uint32_t h_off = (uint32_t)(((hch >> 3) * PLANE + 128 + he) * 16 + (hch & 7) * 2);
+    auto sts = [](uint32_t addr, uint4 q) {
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
     };
-    // 4 floats -> 8 B of the hi plane and 8 B of the lo plane (fp16 hi + fp16 remainder), or 8 B of bf16
-    auto store4 = [&](uint32_t addr, float c0, float c1, float c2, float c3) {
-      if (PARTS == 2) {
-        const __half a0 = __float2half_rn(c0), a1 = __float2half_rn(c1), a2 = __float2half_rn(c2), a3 = __float2half_rn(c3);
-        const __half2 h01 = __halves2half2(a0, a1), h23 = __halves2half2(a2, a3);
-        const __half2 l01 = __floats2half2_rn(c0 - __half2float(a0), c1 - __half2float(a1));
-        const __half2 l23 = __floats2half2_rn(c2 - __half2float(a2), c3 - __half2float(a3));
-        sts2(addr, *reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-        sts2(addr + (uint32_t)PART_BYTES, *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-      } else {
-        const __nv_bfloat162 b01 = __floats2bfloat162_rn(c0, c1), b23 = __floats2bfloat162_rn(c2, c3);
-        sts2(addr, *reinterpret_cast<const uint32_t*>(&b01), *reinterpret_cast<const uint32_t*>(&b23));
-      }
-    };
-    const int col = wq * 32 + lane, gx = x0 + col;  // epilogue map: TMEM lane quarter wq, lane = output column
+    const uint32_t xfa_addr = smem_u32(xf_a), xfb_addr = smem_u32(xf_b);
+    const int col = wq * 32 + lane, gx = x0 + col;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
     const uint32_t bias_addr = smem_u32(bias_s);
     const size_t blk_stride = plane_px * 4;
@@ -186,66 +174,86 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
     for (int l = 0; l < R; ++l) {
       const TrunkLayerDev& Ld = p.L[l];
       const bool do_x = Ld.stats != nullptr;
-      const float* in_blk = Ld.in + blk_off;
+      const float* in_c = Ld.in + c_off;
+      const float* in_h = Ld.in + h_off_g;
+      const uint32_t apar = (uint32_t)l & 1u;  // a_full(ri) completes once per layer
       const int gb = l * nin;                  // running row index of this layer's input row 0 (TMEM ring position)
-      const float a0 = xf_a[wq * 4 + 0], a1 = xf_a[wq * 4 + 1], a2 = xf_a[wq * 4 + 2], a3 = xf_a[wq * 4 + 3];
-      const float b0 = xf_b[wq * 4 + 0], b1 = xf_b[wq * 4 + 1], b2 = xf_b[wq * 4 + 2], b3 = xf_b[wq * 4 + 3];
       auto load_row = [&](int ri, Row& Rw) {
         const int sy = pad_index(y0 - P + ri, H, p.pad_mode);
         Rw.ok = sy >= 0;
-        const float* rp = in_blk + (size_t)(sy < 0 ? 0 : sy) * rstride;
+        const size_t ro = (size_t)(sy < 0 ? 0 : sy) * rstride;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          bool okj;
-          const int sx = src_col(j, okj);
-          Rw.v[j] = (okj && sy >= 0) ? ldcg4(rp + (size_t)sx * 4) : z;
+        Rw.v0 = Rw.v1 = Rw.v2 = Rw.v3 = z;
+        Rw.h = 0.f;
+        if (col_ok && sy >= 0) {
+          const float* c = in_c + ro;
+          Rw.v0 = ldcg4(c);
+          Rw.v1 = ldcg4(c + pstride);
+          Rw.v2 = ldcg4(c + 2 * pstride);
+          Rw.v3 = ldcg4(c + 3 * pstride);
         }
-        bool okh;
-        const int hsx = src_col(4, okh);
-        Rw.h = (okh && sy >= 0) ? ldcg4(rp + (size_t)hsx * 4) : z;
+        if (h_on && sy >= 0) Rw.h = __ldcg(in_h + ro);
       };
+      const float h_a = xf_a[hch], h_b = xf_b[hch];
       auto stage_row = [&](int ri, const Row& Rw) {
-        float v[16] = {Rw.v[0].x, Rw.v[0].y, Rw.v[0].z, Rw.v[0].w, Rw.v[1].x, Rw.v[1].y, Rw.v[1].z, Rw.v[1].w,
-                       Rw.v[2].x, Rw.v[2].y, Rw.v[2].z, Rw.v[2].w, Rw.v[3].x, Rw.v[3].y, Rw.v[3].z, Rw.v[3].w};
-        float hv[4] = {Rw.h.x, Rw.h.y, Rw.h.z, Rw.h.w};
+        float v[16] = {Rw.v0.x, Rw.v0.y, Rw.v0.z, Rw.v0.w, Rw.v1.x, Rw.v1.y, Rw.v1.z, Rw.v1.w,
+                       Rw.v2.x, Rw.v2.y, Rw.v2.z, Rw.v2.w, Rw.v3.x, Rw.v3.y, Rw.v3.z, Rw.v3.w};
+        float hv = Rw.h;
         if (do_x) {
           // GroupNorm + GELU, branch-free: out-of-image taps are masked back to zero afterwards
-          bool keep[4];
-          bool every = true;
+          const bool keep = Rw.ok && col_ok;
+          const bool all_keep = __all_sync(0xffffffffu, keep);  // interior warp: nothing to mask (warp-uniform)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            bool okj;
-            (void)src_col(j, okj);
-            keep[j] = Rw.ok && okj;
-            every = every && keep[j];
-            v[4 * j + 0] = fmaf(v[4 * j + 0], a0, b0);
-            v[4 * j + 1] = fmaf(v[4 * j + 1], a1, b1);
-            v[4 * j + 2] = fmaf(v[4 * j + 2], a2, b2);
-            v[4 * j + 3] = fmaf(v[4 * j + 3], a3, b3);
+          for (int j = 0; j < 4; j += 2) {
+            float4 a0, b0, a1, b1;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a0.x), "=f"(a0.y), "=f"(a0.z), "=f"(a0.w) : "r"(xfa_addr + j * 16));
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(xfb_addr + j * 16));
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a1.x), "=f"(a1.y), "=f"(a1.z), "=f"(a1.w) : "r"(xfa_addr + j * 16 + 16));
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(xfb_addr + j * 16 + 16));
+            float x8[8];
+            x8[0] = fmaf(v[4 * j + 0], a0.x, b0.x); x8[1] = fmaf(v[4 * j + 1], a0.y, b0.y);
+            x8[2] = fmaf(v[4 * j + 2], a0.z, b0.z); x8[3] = fmaf(v[4 * j + 3], a0.w, b0.w);
+            x8[4] = fmaf(v[4 * j + 4], a1.x, b1.x); x8[5] = fmaf(v[4 * j + 5], a1.y, b1.y);
+            x8[6] = fmaf(v[4 * j + 6], a1.z, b1.z); x8[7] = fmaf(v[4 * j + 7], a1.w, b1.w);
+            gelu_erf2n<4>(x8);
+            if (all_keep) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[4 * j + e] = x8[e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[4 * j + e] = keep ? x8[e] : 0.f;
+            }
           }
-          gelu_erf2n<4>(v);
-          gelu_erf2n<4>(v + 8);
-          if (!__all_sync(0xffffffffu, every)) {  // interior warp: nothing to mask (warp-uniform)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[4 * j + e] = keep[j] ? v[4 * j + e] : 0.f;
-          }
-          if (lane < 2) {
-            hv[0] = fmaf(hv[0], a0, b0); hv[1] = fmaf(hv[1], a1, b1); hv[2] = fmaf(hv[2], a2, b2); hv[3] = fmaf(hv[3], a3, b3);
-            gelu_erf2n<2>(hv);
-            bool okh;
-            (void)src_col(4, okh);
-            const bool hk = okh && Rw.ok;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) hv[e] = hk ? hv[e] : 0.f;
+          if (h_on) {
+            float hx[2] = {fmaf(hv, h_a, h_b), 0.f};
+            gelu_erf2n<1>(hx);
+            hv = Rw.ok ? hx[0] : 0.f;
           }
         }
         const uint32_t sa = as_addr + (uint32_t)ri * (uint32_t)STAGE_BYTES;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) store4(sa + (uint32_t)(32 * j) * 16u, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        if (lane < 2) store4(sa + 128u * 16u, hv[0], hv[1], hv[2], hv[3]);  // position 128 + lane
+        if (PARTS == 2) {
+          uint4 h0, l0, h1, l1;
+          split_f16(v, h0, l0);
+          split_f16(v + 8, h1, l1);
+          sts(sa, h0);
+          sts(sa + PLANE * 16, h1);
+          sts(sa + 2 * PLANE * 16, l0);
+          sts(sa + 3 * PLANE * 16, l1);
+        } else {
+          sts(sa, pack_bf16(v));
+          sts(sa + PLANE * 16, pack_bf16(v + 8));
+        }
+        if (wq == 0) {
+          const uint32_t ha = smem_u32(As) + (uint32_t)ri * (uint32_t)STAGE_BYTES + h_off;
+          if (PARTS == 2) {
+            const __half hh = __float2half_rn(hv);
+            const __half hl = __float2half_rn(hv - __half2float(hh));
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha), "h"(__half_as_ushort(hh)) : "memory");
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha + (uint32_t)PART_BYTES), "h"(__half_as_ushort(hl)) : "memory");
+          } else {
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha), "h"(__bfloat16_as_ushort(__float2bfloat16_rn(hv))) : "memory");
+          }
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full((uint32_t)ri));

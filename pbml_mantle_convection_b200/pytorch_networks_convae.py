@@ -93,7 +93,7 @@ class BoundaryLearnedConvolution2D(nn.Module):
     def kernel_path_ok(self, H, W, src_channels, bc_x=1, bc_y=1):
         pad = self.k + 1 if self.k == 5 else self.k
         return (bc_x == 1 and bc_y == 1 and self.c_o <= 16 and self.k in (3, 5) and H >= pad and W >= pad
-                and all(c <= 64 for c in src_channels) and len(src_channels) <= L.MAX_SRC)
+                and all(c <= 128 for c in src_channels) and len(src_channels) <= L.MAX_SRC)
 
     def forward_blocked(self, sources, src_channels, epi_act=L.ACT_NONE, want_stats=True, want_chan_sum=False):
         """sources: ops.Source list (concat order, producer transforms fused) -> (out blocked, stats, chan_sum)."""
