@@ -280,31 +280,46 @@ def unet_channels(levels, c_h):
 
 
 def unet_forward(sd, spec: NetSpec, inp):
-    """Unet.forward (pytorch_networks_convae.py:1985-2068), r_p != 'learned' (SURVEY.md section 8f N4).
-    The time-stepper variant of the surrogate: the input is padded by 3 columns each side, goes down `levels`-1
+    """Unet.forward (pytorch_networks_convae.py:1985-2068).
+    The time-stepper variant of the surrogate: the input is padded by 3 columns each side -- or, with r_p='learned', the
+    first 9-region conv enlarges it by the same 3 columns itself (`bc_x=4, bc_y=1`, :1994-1996) --, goes down `levels`-1
     poolings with the width doubling from level 2 on, comes back up with skip concatenations, and the head removes
     the per-channel mean BEFORE the 3 columns are cropped again.  Returns (u, v, p, T) like the reference."""
-    x = {0: np.pad(inp, ((0, 0), (0, 0), (0, 0), (3, 3)), mode=_PAD[spec.r_p])}  # :1990-1991
+    learned = spec.r_p == "learned"
+    k, sym = spec.f, spec.use_symm
+
+    def layer(x, prefix, c_out, bc_x=1, bc_y=1):
+        if not learned:
+            return fluid_layer(x, sd, prefix, c_out, spec)
+        y = boundary_learned_conv(x, sd, prefix + "layers.0.", k, c_out, use_symm=sym, bc_x=bc_x, bc_y=bc_y)
+        return gelu(group_norm(y, sd[prefix + "layers.1.weight"], sd[prefix + "layers.1.bias"], int(c_out / min(4, c_out))))
+
+    def head_conv(x, idx, c_out):
+        if learned:
+            return boundary_learned_conv(x, sd, f"conv.{idx}.", k, c_out, use_symm=sym)
+        return conv2d_same(x, sd[f"conv.{idx}.weight"], sd[f"conv.{idx}.bias"], spec.r_p)
+
+    x = {0: inp if learned else np.pad(inp, ((0, 0), (0, 0), (0, 0), (3, 3)), mode=_PAD[spec.r_p])}  # :1990-1991
     down, up, top = unet_channels(spec.levels, spec.c_h)
     for r in range(spec.repeats):
-        x[0] = fluid_layer(x[0], sd, f"conv.{r}.", spec.c_h, spec)
+        x[0] = layer(x[0], f"conv.{r}.", spec.c_h, bc_x=4 if (learned and r == 0) else 1)
     sizes = {0: x[0].shape[-2:]}
     for l in range(1, spec.levels):
         x[l] = avg_pool2(x[l - 1])
         sizes[l] = x[l].shape[-2:]
         for r in range(spec.repeats):
-            x[l] = fluid_layer(x[l], sd, f"convs.{l - 1}.{r}.", down[l], spec)
+            x[l] = layer(x[l], f"convs.{l - 1}.{r}.", down[l])
     xu = x[spec.levels - 1]
     for l_i, l in enumerate(range(spec.levels - 2, 0, -1)):
         xu = np.concatenate([x[l], bicubic_upsample(xu, sizes[l])], axis=1)
         for r in range(spec.repeats):
-            xu = fluid_layer(xu, sd, f"upconvs.{l_i}.{r}.", up[l_i], spec)
+            xu = layer(xu, f"upconvs.{l_i}.{r}.", up[l_i])
     y = np.concatenate([bicubic_upsample(xu, sizes[0]), x[0]], axis=1)
     R = spec.repeats
-    y = conv2d_same(y, sd[f"conv.{R}.weight"], sd[f"conv.{R}.bias"], spec.r_p)
+    y = head_conv(y, R, top)
     y = gelu(group_norm(y, sd["gn.0.weight"], sd["gn.0.bias"], int(top / 4)))
-    y = gelu(conv2d_same(y, sd[f"conv.{R + 1}.weight"], sd[f"conv.{R + 1}.bias"], spec.r_p))
-    y = conv2d_same(y, sd[f"conv.{R + 2}.weight"], sd[f"conv.{R + 2}.bias"], spec.r_p)
+    y = gelu(head_conv(y, R + 1, top))
+    y = head_conv(y, R + 2, spec.c_o)
     y = (y - y.mean(axis=(2, 3), keepdims=True))[..., 3:-3]  # :2025
     if spec.loss_type in ("mae", "mass"):  # :2027-2037
         return y[:, 0:1], y[:, 1:2], (y[:, 3:4] if spec.p_pred else None), y[:, 2:3]

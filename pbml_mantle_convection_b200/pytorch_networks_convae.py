@@ -432,7 +432,8 @@ class Unet(nn.Module):
     (u, v, p, T_next) (reference :1700-2068).  Same constructor, module tree and `state_dict`
     keys/shapes as the reference.  `forward` runs on the module-level kernels (FluidLayer = conv + GroupNorm + GELU
     through libpbmc, incremental 2x2 pooling, bicubic up-sampling, curl head); it is not yet one fused DAG like
-    NewFluidNet's, and the learned-boundary variant (which enlarges the input through `bc_x=4`) is not built."""
+    NewFluidNet's.  The learned-boundary variant (r_p="learned": every conv is the 9-region conv, the first one enlarging the
+    width through `bc_x=4`) runs on the same path: two launches per 9-region conv, the bc_x=4 layer as the 9-call composite."""
 
     def __init__(self, levels: int, c_i: int, c_h: int, c_o: int, device=torch.device("cpu"), act_fn: str = "gelu",
                  r_p="replicate", loss_type="curl", use_symm=False, dilation=1, a_bound=10.0, use_cosine=False, repeats=2,
@@ -481,15 +482,16 @@ class Unet(nn.Module):
             raise L.PbmcError("Unet runs on CUDA only: there is no CPU implementation of this path")
         if inputs.dim() != 4 or inputs.shape[1] != self.c_i:
             raise ValueError(f"expected inputs [B,{self.c_i},H,W], got {tuple(inputs.shape)}")
-        if self.r_p == "learned":
-            raise NotImplementedError("the learned-boundary U-Net (bc_x=4 enlargement, :1996) is not built")
+        learned = self.r_p == "learned"
         dev, dtype, R = inputs.device, inputs.dtype, self.repeats
         blocked = lambda t: ops.Source(ops.pack_nchw(t))
         pool = lambda t: ops.unpack_nchw(ops.avgpool2(blocked(t)), t.shape[1])
         up = lambda t, size: ops.unpack_nchw(ops.bicubic_up(blocked(t), int(size[0]), int(size[1])), t.shape[1])
-        x = [torch.nn.functional.pad(inputs.float(), (3, 3, 0, 0), mode=self.r_p)]  # :1990-1991
+        # non-learned: 3 padded columns each side (:1990-1991); learned: the first 9-region conv enlarges the width by the
+        # same 3 columns itself (bc_x=4, bc_y=1, :1994-1996)
+        x = [inputs.float() if learned else torch.nn.functional.pad(inputs.float(), (3, 3, 0, 0), mode=self.r_p)]
         for r in range(R):
-            x[0] = self.conv[r](x[0])
+            x[0] = self.conv[r](x[0], bc_x=4, bc_y=1) if (learned and r == 0) else self.conv[r](x[0])
         for l in range(1, self.levels):
             t = pool(x[l - 1])
             for r in range(R):
@@ -502,11 +504,12 @@ class Unet(nn.Module):
                 xu = self.upconvs[l_i][r](xu)
         y = torch.cat((up(xu, x[0].shape[-2:]), x[0]), 1)
         c = self.c_head
-        yb = ops.pack_nchw(conv_module_forward(self.conv[R], y))
+        head = (lambda m, t: m(t)) if learned else conv_module_forward  # 9-region conv modules / plain conv modules
+        yb = ops.pack_nchw(head(self.conv[R], y))
         y = ops.finalize_nchw(ops.Source(yb, L.XFORM_GN_GELU, _stats_of_blocked(yb, c), ops.pad_vec(self.gn[0].weight, c, dev, 1.0),
                                          ops.pad_vec(self.gn[0].bias, c, dev)), c)
-        y = ops.finalize_nchw(ops.Source(ops.pack_nchw(conv_module_forward(self.conv[R + 1], y)), L.XFORM_GELU), c)
-        y = conv_module_forward(self.conv[R + 2], y)
+        y = ops.finalize_nchw(ops.Source(ops.pack_nchw(head(self.conv[R + 1], y)), L.XFORM_GELU), c)
+        y = head(self.conv[R + 2], y)
         y = (y - y.mean(dim=(2, 3), keepdim=True))[..., 3:-3].contiguous()  # mean over the PADDED width, then crop (:2025)
         if self.loss_type in ("mae", "mass"):
             p = y[:, 3:4].to(dtype) if self.p_pred else None

@@ -50,7 +50,7 @@ def spec_from_variant(d):
 VARIANTS = ["var_zeros_nosym", "var_reflect_sym", "var_replicate_odd", "var_mae_p", "var_k5"]
 
 
-UNET_CASES = ["unet_curl_p", "unet_curl_k5", "unet_mae"]
+UNET_CASES = ["unet_curl_p", "unet_curl_k5", "unet_mae", "unet_learned_k3", "unet_learned_k5"]
 
 
 LEARNED_CASES = ["learned_k5", "learned_k3_p", "learned_fluidnet"]

@@ -287,6 +287,9 @@ def golden_unet():
         "unet_curl_p": (RN.NetSpec(levels=4, c_i=10, c_h=8, c_o=3, r_p="replicate", use_symm=False, repeats=2, f=3), 36, 50),
         "unet_curl_k5": (RN.NetSpec(levels=3, c_i=10, c_h=16, c_o=2, r_p="reflect", use_symm=False, repeats=2, f=5, p_pred=False), 40, 53),
         "unet_mae": (RN.NetSpec(levels=3, c_i=10, c_h=8, c_o=4, r_p="zeros", use_symm=False, repeats=1, f=3, loss_type="mae"), 24, 30),
+        # learned-boundary U-Net: the first conv enlarges the width by 3 columns each side itself (bc_x=4, :1994-1996)
+        "unet_learned_k3": (RN.NetSpec(levels=3, c_i=10, c_h=8, c_o=3, r_p="learned", use_symm=False, repeats=2, f=3), 36, 50),
+        "unet_learned_k5": (RN.NetSpec(levels=3, c_i=10, c_h=8, c_o=2, r_p="learned", use_symm=False, repeats=1, f=5, p_pred=False), 48, 58),
     }
     out = {}
     for tag, (spec, H, W) in cases.items():
@@ -425,7 +428,7 @@ def golden_noise():
         res = net(torch.tensor(g["inp"], dtype=torch.float32))
         noise[tag] = {n: relerr(r.double().numpy(), g[n]) for n, r in zip("uvp", res) if r is not None}
     for file, cases, seed in (("learned", {"learned_k5": P.NewFluidNet, "learned_k3_p": P.NewFluidNet, "learned_fluidnet": P.FluidNet}, 6),
-                              ("unet", {"unet_curl_p": None, "unet_curl_k5": None, "unet_mae": None}, 5)):
+                              ("unet", {"unet_curl_p": None, "unet_curl_k5": None, "unet_mae": None, "unet_learned_k3": None, "unet_learned_k5": None}, 5)):
         g = dict(np.load(os.path.join(HERE, file + ".npz")))
         for tag, cls in cases.items():
             d = {k[len(tag) + 2:]: v for k, v in g.items() if k.startswith(tag + "::")}
