@@ -519,9 +519,9 @@ def run_ours(args, wl):
                     "frac": r["frac"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)",
                     "traffic_source": traffic_src, "algorithmic_bytes_per_launch": B * H * W * {"conv16x16_l0": 128, "trunk_l0": 128 * 4, "conv1_103x16": 480}.get(dom, 16),
                     "peak_source": r["peak_source"], "ms_per_launch": r["ms"], "share_of_step": share[dom] / step_ms}
-        if traffic is not None and rec.get("tensor_subpipe_hmma_active_cycles"):
+        if traffic is not None and rec.get("tensor_pipe_active_pct_of_active_cycles") is not None:
             # second view of the same kernel: how busy the tensor pipe was in the recorded ncu capture
-            roofline["tensor_pipe_active_frac_ncu"] = rec["tensor_subpipe_hmma_active_cycles"] / rec["elapsed_cycles"]
+            roofline["tensor_pipe_active_frac_ncu"] = rec["tensor_pipe_active_pct_of_active_cycles"] / 100.0
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = max(2, min(60, int(15.0 / (1.45e-6 * H * W))))  # ~10-30 s of CPU work (0.38 s per 512^2 step on 16 cores)
