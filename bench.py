@@ -393,6 +393,24 @@ def ensemble_record(net, rank, world, local, dev, K, Wm, flush):
             "surrogate_steps_per_s": world * B * K / (ms * 1e-3), "finite": bool(fin.item()), "clocks": clk.summary()}
 
 
+def teardown(code=0):
+    """Leave a multi-rank run: barrier, destroy the process group -- under a watchdog.  Round 1's 8-rank slab run printed its
+    line and then never exited (process-group teardown with captured NCCL work alive); nothing captures NCCL any more and
+    the normal path is taken, but a hung teardown must not turn a finished measurement into a killed run: after 60 s the
+    process leaves without running destructors."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    dog = threading.Timer(60.0, lambda: (sys.stderr.write("bench.py: teardown watchdog fired\n"), sys.stderr.flush(), os._exit(code)))
+    dog.daemon = True
+    dog.start()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    dog.cancel()
+
+
 def run_ours(args, wl):
     import torch.distributed as dist
 
@@ -571,11 +589,14 @@ def run_ours(args, wl):
         if line is not None:
             line["sub_records"] = subs
             line["gpu_launches"] += launches_per_step(6, 4) * subs["ensemble256"]["steps"] + subs["slab8192"]["steps"]
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if line is not None:
         emit(line)
+    bad = False
+    if subs is not None:
+        sl = subs["slab8192"]
+        bad = not (sl["finite"] and sl["bounded"] and sl["identical_to_single_gpu"] and subs["ensemble256"]["finite"])
+    if world > 1:
+        teardown(1 if bad else 0)
     if subs is not None:
         sl = subs["slab8192"]
         if not (sl["finite"] and sl["bounded"] and sl["identical_to_single_gpu"] and subs["ensemble256"]["finite"]):
@@ -715,11 +736,10 @@ def run_slab(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     rec = slab_record(rank, world, local, dev, wl["H"], wl["W"], args.steps, max(args.warmup, 3), args.halo, args.dt_sync, wl["desc"])
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if rank == 0:
         emit(rec)
+    if world > 1:
+        teardown(0 if (rec["finite"] and rec["bounded"] and rec["identical_to_single_gpu"]) else 1)
     if not (rec["finite"] and rec["bounded"] and rec["identical_to_single_gpu"]):
         raise SystemExit("slab workload: non-finite / unbounded field or the decomposed run differs from the single-domain run")
 
