@@ -393,6 +393,24 @@ def ensemble_record(net, rank, world, local, dev, K, Wm, flush):
             "surrogate_steps_per_s": world * B * K / (ms * 1e-3), "finite": bool(fin.item()), "clocks": clk.summary()}
 
 
+def teardown(code=0):
+    """Leave a multi-rank run: barrier, destroy the process group -- under a watchdog.  Round 1's 8-rank slab run printed its
+    line and then never exited (process-group teardown with captured NCCL work alive); nothing captures NCCL any more and
+    the normal path is taken, but a hung teardown must not turn a finished measurement into a killed run: after 60 s the
+    process leaves without running destructors."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    dog = threading.Timer(60.0, lambda: (sys.stderr.write("bench.py: teardown watchdog fired\n"), sys.stderr.flush(), os._exit(code)))
+    dog.daemon = True
+    dog.start()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    dog.cancel()
+
+
 def run_ours(args, wl):
     import torch.distributed as dist
 
@@ -519,9 +537,9 @@ def run_ours(args, wl):
                     "frac": r["frac"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)",
                     "traffic_source": traffic_src, "algorithmic_bytes_per_launch": B * H * W * {"conv16x16_l0": 128, "trunk_l0": 128 * 4, "conv1_103x16": 480}.get(dom, 16),
                     "peak_source": r["peak_source"], "ms_per_launch": r["ms"], "share_of_step": share[dom] / step_ms}
-        if traffic is not None and rec.get("tensor_subpipe_hmma_active_cycles"):
+        if traffic is not None and rec.get("tensor_pipe_active_pct_of_active_cycles") is not None:
             # second view of the same kernel: how busy the tensor pipe was in the recorded ncu capture
-            roofline["tensor_pipe_active_frac_ncu"] = rec["tensor_subpipe_hmma_active_cycles"] / rec["elapsed_cycles"]
+            roofline["tensor_pipe_active_frac_ncu"] = rec["tensor_pipe_active_pct_of_active_cycles"] / 100.0
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = max(2, min(60, int(15.0 / (1.45e-6 * H * W))))  # ~10-30 s of CPU work (0.38 s per 512^2 step on 16 cores)
@@ -571,11 +589,14 @@ def run_ours(args, wl):
         if line is not None:
             line["sub_records"] = subs
             line["gpu_launches"] += launches_per_step(6, 4) * subs["ensemble256"]["steps"] + subs["slab8192"]["steps"]
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if line is not None:
         emit(line)
+    bad = False
+    if subs is not None:
+        sl = subs["slab8192"]
+        bad = not (sl["finite"] and sl["bounded"] and sl["identical_to_single_gpu"] and subs["ensemble256"]["finite"])
+    if world > 1:
+        teardown(1 if bad else 0)
     if subs is not None:
         sl = subs["slab8192"]
         if not (sl["finite"] and sl["bounded"] and sl["identical_to_single_gpu"] and subs["ensemble256"]["finite"]):
@@ -715,11 +736,10 @@ def run_slab(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     rec = slab_record(rank, world, local, dev, wl["H"], wl["W"], args.steps, max(args.warmup, 3), args.halo, args.dt_sync, wl["desc"])
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if rank == 0:
         emit(rec)
+    if world > 1:
+        teardown(0 if (rec["finite"] and rec["bounded"] and rec["identical_to_single_gpu"]) else 1)
     if not (rec["finite"] and rec["bounded"] and rec["identical_to_single_gpu"]):
         raise SystemExit("slab workload: non-finite / unbounded field or the decomposed run differs from the single-domain run")
 

@@ -58,7 +58,7 @@ def main():
         ms1 = (time.perf_counter() - t0) * 1e3 / steps
         eT = (T - ens.T[0]).abs().max().item()
         eu = ((u - ens.fields()[0][0]).abs().max() / ens.fields()[0][0].abs().max()).item()
-        ok = eT <= 2e-6 and eu <= 2e-5 and bool(torch.isfinite(T).all())
+        ok = eT <= 5e-6 and eu <= 2e-4 and bool(torch.isfinite(T).all())  # see tests/test_gpu_slab_surrogate.py for the bounds
         print(f"slab_surrogate_check H={H} W={W} world={world} steps={steps} levels={levels}: matches_single_gpu={ok} "
               f"(max|dT| {eT:.2e}, rel max|du| {eu:.2e}); {ms:.2f} ms/step decomposed (host-driven, wall clock) vs {ms1:.2f} ms/step "
               f"fused single GPU", flush=True)
