@@ -171,10 +171,12 @@ class SurrogateEngine:
     def release_workspaces(self):
         self._ws = {}
 
-    def graph_key(self, B, H, W):
+    def graph_key(self, B, H, W, refresh=True):
         """Everything a captured graph of this engine bakes in besides its own buffers: packed-weight identity, conv
-        implementation, workspace address.  A change in any of them must force a re-capture."""
-        self.refresh()
+        implementation, workspace address.  A change in any of them must force a re-capture.  refresh=False: the caller
+        has just called refresh() (the parameter walk costs ~30 us for the primary network's 108 tensors)."""
+        if refresh:
+            self.refresh()
         return (self._key, self.conv_impl, self.trunk_mode, self.up_staged, self.workspace(B, H, W).data_ptr())
 
     # -------------------------------------------------------------- forward

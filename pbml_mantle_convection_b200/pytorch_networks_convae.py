@@ -610,7 +610,7 @@ class TS(nn.Module):
         if stokes.training and any(m.dropout.p != 0.0 for m in stokes.modules() if isinstance(m, FluidLayer)):
             raise NotImplementedError("dropout>0 in training mode is outside the inference path")
         eng.refresh()
-        key = (B, H, W, n, dtype, id(grid), id(eng), eng.graph_key(B, H, W), float(cn_max), bool(stokes.p_pred))
+        key = (B, H, W, n, dtype, id(grid), id(eng), eng.graph_key(B, H, W, refresh=False), float(cn_max), bool(stokes.p_pred))
         pl = self._plan if key == self._plan_key else None
         if pl is None:
             pl = _FusedPlan()
