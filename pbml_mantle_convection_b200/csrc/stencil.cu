@@ -373,10 +373,16 @@ __global__ void __launch_bounds__(128, 6) stencil_march_kernel(const StencilPara
   __shared__ uint32_t s_last, s_bits;
   m = warp_max(m);
   if (lane == 0 && m > 0.f) atomic_max_nonneg(&sa.self->local_max, m);
-  __threadfence_system();  // this thread's ghost-row stores into the neighbours (and the atomic) before the CTA is counted
+  // Only a warp that stored rows into a NEIGHBOUR's memory needs the system-scope fence (its stores must be performed
+  // over NVLink before the CTA is counted); everything else this CTA wrote is local and ordered by the fence + atomic of
+  // thread 0 below.  (MEMBAR.SC.SYS in every thread of every CTA cost microseconds per step.)
+  const bool pushed = warp_on && ((p.push_up != nullptr && p.push_up_row >= y0 && p.push_up_row < y1) ||
+                                  (p.push_down != nullptr && p.push_down_row >= y0 && p.push_down_row < y1));
+  if (pushed) __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t total = gridDim.x * gridDim.y * gridDim.z;
+    __threadfence();  // the CTA's atomicMax / stores (observed through the barrier) before its count
     const uint32_t prev = atomicAdd(&sa.self->ctas_done, 1u);
     s_last = prev == total - 1u;
     if (s_last) {

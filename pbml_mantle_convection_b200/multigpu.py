@@ -173,13 +173,14 @@ class SlabStencil:
             self._sync_handle = symm_mem.rendezvous(self._sync, group=grp)
             off_s = self._sync.data_ptr() - int(self._sync_handle.buffer_ptrs[s.rank])
             self._sync_ptrs = [int(p) + off_s for p in self._sync_handle.buffer_ptrs]
+            self._sync_arr = ops.peer_array(self._sync_ptrs)  # marshalled once: the step is one C call
 
             def step_flags(T, u, v, _uvmax_unused):
                 k = self._slot
                 out = self._buf[1 - k, :s.rows].unsqueeze(0)
                 ops.advect_diffuse_slab_sync(T, u, v, self.xcoef, self.ycoef, self.members, self.dx_min, self.cn_max, out,
                                              self._dt, s.up, s.down, self._peer_up[1 - k], self._peer_down[1 - k],
-                                             self._sync_ptrs[s.rank], self._sync_ptrs, s.rank)
+                                             self._sync_ptrs[s.rank], self._sync_arr, s.rank)
                 self._slot = 1 - k
                 return out, self._dt
 

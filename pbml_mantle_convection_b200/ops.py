@@ -454,7 +454,14 @@ SLAB_SYNC_BYTES = C.sizeof(L.SlabSync)
 
 
 def _peer_array(peer_ptrs):
+    if isinstance(peer_ptrs, C.Array):  # already marshalled (per-step callers build it once)
+        return peer_ptrs
     return (C.c_void_p * len(peer_ptrs))(*[int(q) for q in peer_ptrs])
+
+
+def peer_array(peer_ptrs):
+    """ctypes array of the ranks' pbmc_slab_sync addresses, to be built once and passed to the per-step calls."""
+    return _peer_array(peer_ptrs)
 
 
 def slab_sync_publish(u, v, self_ptr, peer_ptrs, rank):
