@@ -59,6 +59,8 @@ def main():
         eT = (T - ens.T[0]).abs().max().item()
         eu = ((u - ens.fields()[0][0]).abs().max() / ens.fields()[0][0].abs().max()).item()
         ok = eT <= 5e-6 and eu <= 2e-4 and bool(torch.isfinite(T).all())  # see tests/test_gpu_slab_surrogate.py for the bounds
+        rows_bad = ((u - ens.fields()[0][0]).abs().max(dim=1).values > 1e-3 * float(ens.fields()[0][0].abs().max())).nonzero().flatten().tolist()
+        print(f"  rows with |du| > 1e-3 max|u|: {len(rows_bad)} {rows_bad[:16]}{' ...' if len(rows_bad) > 16 else ''}", flush=True)
         print(f"slab_surrogate_check H={H} W={W} world={world} steps={steps} levels={levels}: matches_single_gpu={ok} "
               f"(max|dT| {eT:.2e}, rel max|du| {eu:.2e}); {ms:.2f} ms/step decomposed (host-driven, wall clock) vs {ms1:.2f} ms/step "
               f"fused single GPU", flush=True)
