@@ -50,8 +50,8 @@ def main():
         ens.set_T(T0[None])
         ens.step(steps)
         torch.cuda.synchronize()
+        ens.n_done = 0  # BEFORE set_T: it writes the slot of the current step parity
         ens.set_T(T0[None])
-        ens.n_done = 0
         t0 = time.perf_counter()
         ens.step(steps)
         torch.cuda.synchronize()
