@@ -57,7 +57,10 @@ enum { PBMC_HEAD_CURL = 0, PBMC_HEAD_MAE = 1 };
 /* pbmc_net.flags: PER_LAYER = never use the persistent trunk kernel; UP_STAGED = the bicubic kernel writes the up-sampled
  * levels as conv[1]'s fp16 hi|lo operand image (PBMC_LAYOUT_STAGED16) and conv[1] stages them with TMA bulk copies
  * (bit-identical results; measured neutral-to-slower, so off by default) */
-enum { PBMC_NET_TRUNK_PER_LAYER = 1, PBMC_NET_UP_STAGED = 2 };
+enum { PBMC_NET_TRUNK_PER_LAYER = 1, PBMC_NET_UP_STAGED = 2, PBMC_NET_TRUNK_THREAD_LOADER = 4 };
+/* pbmc_trunk_desc.loader: BULK (default) = TMA bulk copies (cp.async.bulk + mbarrier transaction bytes), all rows of a layer
+ * requested up front by one warp; THREADS = every worker loads its own pixels with ld.global (round 2's first version) */
+enum { PBMC_TRUNK_LOADER_BULK = 0, PBMC_TRUNK_LOADER_THREADS = 1 };
 /* conv implementation selector: FFMA = fp32 CUDA cores; UMMA_* = tcgen05 tensor cores:
  * 3XTF32 / F16X2 split every operand into hi + lo (tf32 resp. fp16) and issue 3 passes --
  * fp32-grade accuracy; BF16 = single pass with bf16 operands (looser, stated bound).
@@ -316,6 +319,8 @@ typedef struct {
   double* stats;
   unsigned int* sync;
   int R, B, H, W, pad_mode, impl, max_ctas, pre_zeroed;
+  int loader;   /* PBMC_TRUNK_LOADER_*: how the raw input rows reach shared memory (fp16 hi+lo kernel; bf16 always THREADS) */
+  int reserved;
 } pbmc_trunk_desc;
 int pbmc_trunk_fwd(const pbmc_trunk_desc* desc_h, void* stream);
 /* 1 if pbmc_trunk_fwd would take this configuration (shape, budget), else 0 */

@@ -20,7 +20,7 @@ XFORM_NONE, XFORM_GN_GELU, XFORM_GN, XFORM_GELU = 0, 1, 2, 3
 LAYOUT_BLOCKED, LAYOUT_STAGED16 = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
 HEAD_CURL, HEAD_MAE = 0, 1
-TRUNK_MODE = {"auto": 0, "per_layer": 1}
+TRUNK_MODE = {"auto": 0, "per_layer": 1, "auto_thread_loader": 4}  # pbmc_net.flags bits (PBMC_NET_TRUNK_*)
 NET_UP_STAGED = 2
 CONV_IMPL = {"auto": 0, "ffma": 1, "umma_3xtf32": 2, "umma_bf16": 3, "umma_f16x2": 4,
              "row_f16x2": 5, "row_bf16": 6, "mux_f16x2": 7, "mux_bf16": 8}
@@ -73,7 +73,7 @@ class Edge9Desc(C.Structure):
 class TrunkDesc(C.Structure):
     _fields_ = [("src0", Src), ("layers", C.POINTER(Layer)), ("ping", C.c_void_p * 2), ("stats", C.c_void_p),
                 ("sync", C.c_void_p), ("R", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("pad_mode", C.c_int),
-                ("impl", C.c_int), ("max_ctas", C.c_int), ("pre_zeroed", C.c_int)]
+                ("impl", C.c_int), ("max_ctas", C.c_int), ("pre_zeroed", C.c_int), ("loader", C.c_int), ("reserved", C.c_int)]
 
 
 _STRUCTS = {"pbmc_edge9_desc": Edge9Desc, "pbmc_trunk_desc": TrunkDesc, "pbmc_slab_sync": SlabSync, "pbmc_member": Member, "pbmc_src": Src, "pbmc_conv_desc": ConvDesc, "pbmc_layer": Layer, "pbmc_net": Net}

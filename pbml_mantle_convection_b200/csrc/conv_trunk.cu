@@ -38,7 +38,7 @@ constexpr int CT_MAXR = 24;                      // input rows per CTA (all resi
 constexpr int CT_ND = 10;                        // TMEM accumulator ring
 constexpr int CT_N = 48;                         // (dy, c_out)
 constexpr int CT_PLANE = 136;                    // positions per K-chunk plane (128 + 2 halo, rounded up to 8)
-constexpr int CT_HDR = 2048;
+constexpr int CT_HDR = 2304;                     // barriers, TMEM slot, reduction scratch, coefficients, raw-row barriers
 
 struct TrunkLayerDev {
   const float* in;       // [B][4][H][W][4] raw producer output (or the level's input for layer 0)
@@ -58,6 +58,26 @@ struct ConvTrunkParams {
   int R, B, H, W, pad_mode, rpc;
 };
 
+// BULK loader: the raw input rows of a layer are copied into shared memory by the TMA engine (cp.async.bulk, one copy
+// per 4-channel plane and row, all rows of the layer requested up front by ONE thread right after the grid barrier) --
+// each row lands in the very stage slot its operand image will occupy (4 planes x 130 positions x 16 B of fp32 = the
+// size of the fp16 hi|lo image), the group that owns the row waits for its mbarrier, reads its pixels from shared memory,
+// and writes the GroupNorm+GELU'd, split operand image over them.  No global load, no address arithmetic and no
+// prefetch registers in the workers; the copies run ahead of the staging by as many rows as the layer has.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void ct_worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CT_WORKERS * 32) : "memory"); }
 __device__ __forceinline__ void ct_mma_bar() { asm volatile("bar.sync 2, %0;" ::"n"(CT_NMMA * 32) : "memory"); }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -67,7 +87,7 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
   return v;
 }
 
-template <int PARTS>
+template <int PARTS, bool BULK>
 __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTrunkParams p) {
   constexpr int KS = 3, P = 1, N = CT_N, ND = CT_ND, PLANE = CT_PLANE;
   constexpr int PART_BYTES = 2 * PLANE * 16, STAGE_BYTES = PARTS * PART_BYTES;
@@ -75,6 +95,8 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
   constexpr uint32_t FMT = PARTS == 2 ? 0u : 1u;  // fp16 hi|lo split, or one bf16 pass
   constexpr uint32_t IDESC = row_idesc(FMT, N);
   static_assert(8 * (CT_MAXR + 2 * ND) <= 448, "barrier area");
+  static_assert(!BULK || PARTS == 2, "the raw fp32 row fills exactly the fp16 hi|lo stage slot");
+  static_assert(2048 + 8 * CT_MAXR <= CT_HDR, "raw-row barriers");
   static_assert(ND * N <= 512, "TMEM has 512 columns");
   static_assert(B_GROUP % 128 == 0, "operand buffers stay 128-byte aligned");
   extern __shared__ __align__(128) unsigned char smem[];
@@ -98,10 +120,14 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
   auto a_full = [&](uint32_t r) { return bar0 + r * 8u; };
   auto d_full = [&](uint32_t d) { return bar0 + (uint32_t)(CT_MAXR + d) * 8u; };
   auto d_empty = [&](uint32_t d) { return bar0 + (uint32_t)(CT_MAXR + ND + d) * 8u; };
+  auto raw_full = [&](uint32_t r) { return bar0 + 2048u + r * 8u; };  // BULK: the raw row r of this layer has landed
 
   // ---- one-time set-up: barriers, TMEM, layer 0's filters / bias / GroupNorm coefficients
   if (tid == 0) {
-    for (int r = 0; r < CT_MAXR; ++r) mbar_init(a_full(r), 4);  // the 4 warps of the group that stages the row
+    for (int r = 0; r < CT_MAXR; ++r) {
+      mbar_init(a_full(r), 4);  // the 4 warps of the group that stages the row
+      if (BULK) mbar_init(raw_full(r), 1);  // one arrive.expect_tx (+ the bytes of the row's four bulk copies)
+    }
     for (int d = 0; d < ND; ++d) {
       mbar_init(d_full(d), 1);        // tcgen05.commit
       mbar_init(d_empty(d), 4 * KS);  // 4 warps x the KS output rows that read D_d
@@ -170,6 +196,27 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
     const bool col_in = gx < W;
     const size_t o_off = (((size_t)b * 4) * plane_px + (size_t)y0 * W + gx) * 4;
     const unsigned int nctas = gridDim.x * gridDim.y;
+    // BULK loader geometry: the in-image part of positions 0..129 (input columns x0-1 .. x0+128) is copied, a padded
+    // position reads the position its padding rule points at
+    constexpr uint32_t RAWP = PLANE * 16;  // plane stride of a raw row inside its stage slot
+    const int i_lo = x0 == 0 ? 1 : 0, i_hi = min(129, W - x0), ncols = i_hi - i_lo + 1;
+    const uint32_t raw_pos = (uint32_t)((sx < 0 ? 0 : sx) - (x0 - P)) * 16u;
+    const uint32_t raw_hpos = (uint32_t)(hch >> 2) * RAWP + (uint32_t)((hsx < 0 ? 0 : hsx) - (x0 - P)) * 16u + (uint32_t)(hch & 3) * 4u;
+    auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory"); };
+    // all raw rows of layer l, requested by lanes 0..3 of warp 0 (one 4-channel plane each) right after the grid barrier
+    auto request_rows = [&](int l) {
+      if (warp != 0 || lane >= 4) return;
+      asm volatile("fence.proxy.async;" ::: "memory");  // other CTAs' (generic-proxy) stores, acquired at the barrier, before the async-proxy reads
+      const float* src_pl = p.L[l].in + (((size_t)b * 4 + lane) * plane_px + (size_t)(x0 - P + i_lo)) * 4;
+      const uint32_t dst_pl = smem_u32(As) + (uint32_t)lane * RAWP + (uint32_t)i_lo * 16u;
+      for (int ri = 0; ri < nin; ++ri) {
+        const int sy = pad_index(y0 - P + ri, H, p.pad_mode);
+        if (sy < 0) continue;  // a zero-padded row: nothing to copy, the workers stage zeros
+        if (lane == 0) mbar_expect_tx(raw_full((uint32_t)ri), (uint32_t)(4 * ncols * 16));
+        bulk_g2s(dst_pl + (uint32_t)ri * (uint32_t)STAGE_BYTES, src_pl + (size_t)sy * W * 4, (uint32_t)(ncols * 16), raw_full((uint32_t)ri));
+      }
+    };
+    if (BULK) request_rows(0);
 
     for (int l = 0; l < R; ++l) {
       const TrunkLayerDev& Ld = p.L[l];
@@ -185,6 +232,20 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         Rw.v0 = Rw.v1 = Rw.v2 = Rw.v3 = z;
         Rw.h = 0.f;
+        if (BULK) {
+          if (sy >= 0) {
+            mbar_wait_parked(raw_full((uint32_t)ri), apar);  // the row's four planes have landed in its stage slot
+            const uint32_t base = smem_u32(As) + (uint32_t)ri * (uint32_t)STAGE_BYTES;
+            if (col_ok) {
+              Rw.v0 = lds4(base + raw_pos);
+              Rw.v1 = lds4(base + RAWP + raw_pos);
+              Rw.v2 = lds4(base + 2 * RAWP + raw_pos);
+              Rw.v3 = lds4(base + 3 * RAWP + raw_pos);
+            }
+            if (h_on) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(Rw.h) : "r"(base + raw_hpos) : "memory");
+          }
+          return;
+        }
         if (col_ok && sy >= 0) {
           const float* c = in_c + ro;
           Rw.v0 = ldcg4(c);
@@ -231,6 +292,7 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
           }
         }
         const uint32_t sa = as_addr + (uint32_t)ri * (uint32_t)STAGE_BYTES;
+        if (BULK) group_bar();  // every thread of the group has read its pixels of the raw row: now it may be overwritten
         if (PARTS == 2) {
           uint4 h0, l0, h1, l1;
           split_f16(v, h0, l0);
@@ -374,6 +436,7 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
           __threadfence();
         }
         ct_worker_bar();
+        if (BULK) request_rows(l + 1);
         if (tid < 16) load_coeffs(l + 1);
         ct_worker_bar();
       }
@@ -463,18 +526,18 @@ bool conv_trunk_supported(const pbmc_trunk_desc& t) {
   return choose_rpc_trunk(cdiv(t.W, 128) * t.B, t.H, avail) > 0;
 }
 
-template <int PARTS>
+template <int PARTS, bool BULK>
 static int launch_trunk(ConvTrunkParams& p, cudaStream_t st) {
   constexpr int STAGE_BYTES = PARTS * 2 * CT_PLANE * 16, B_GROUP = 3 * PARTS * (2 * CT_N * 16);
   static bool attr_set = false;
   if (!attr_set) {
-    PBMC_CUDA(cudaFuncSetAttribute(conv_trunk_kernel<PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PBMC_CUDA(cudaFuncSetAttribute(conv_trunk_kernel<PARTS, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const size_t smem = CT_HDR + (size_t)2 * B_GROUP + (size_t)(p.rpc + 2) * STAGE_BYTES;
   if (smem > 227 * 1024) return PBMC_ERR_UNSUPPORTED;
   dim3 grid(cdiv(p.H, p.rpc), cdiv(p.W, 128), p.B);
-  conv_trunk_kernel<PARTS><<<grid, CT_THREADS, smem, st>>>(p);
+  conv_trunk_kernel<PARTS, BULK><<<grid, CT_THREADS, smem, st>>>(p);
   PBMC_CHECK_LAUNCH("conv_trunk_kernel");
   return PBMC_OK;
 }
@@ -514,7 +577,8 @@ int conv_trunk_dispatch(const pbmc_trunk_desc& t, cudaStream_t st) {
     PBMC_CUDA(cudaMemsetAsync(t.sync, 0, (size_t)t.B * sizeof(unsigned int), st));
     PBMC_CUDA(cudaMemsetAsync(t.stats, 0, (size_t)t.R * t.B * 8 * sizeof(double), st));
   }
-  return bf16 ? launch_trunk<1>(p, st) : launch_trunk<2>(p, st);
+  if (bf16) return launch_trunk<1, false>(p, st);
+  return t.loader == PBMC_TRUNK_LOADER_THREADS ? launch_trunk<2, false>(p, st) : launch_trunk<2, true>(p, st);
 }
 
 }  // namespace pbmc

@@ -618,7 +618,8 @@ class _Lay:
     (1, 40, 130, 4, "replicate", True, 0), (2, 33, 256, 3, "zeros", False, 0), (1, 70, 300, 4, "reflect", True, 0),
     (1, 64, 64, 4, "replicate", True, 3), (1, 7, 9, 2, "replicate", True, 2), (3, 50, 77, 1, "replicate", False, 0),
     (1, 128, 128, 6, "replicate", True, 0)])
-def test_trunk_persistent_kernel(B, H, W, R, pad, xform0, max_ctas):
+@pytest.mark.parametrize("loader", ["bulk", "threads"])
+def test_trunk_persistent_kernel(B, H, W, R, pad, xform0, max_ctas, loader):
     """pbmc_trunk_fwd: R FluidLayers (conv -> GroupNorm -> GELU, pytorch_networks_convae.py:790-799, :1323-1324) in one
     persistent launch with a grid-wide barrier per layer, against (a) the float64 numpy oracle and (b) the same layers
     launched one by one through pbmc_conv_fwd (same arithmetic per output; only the order of the double-precision
@@ -644,7 +645,7 @@ def test_trunk_persistent_kernel(B, H, W, R, pad, xform0, max_ctas):
         src = ops.Source(xb, L.XFORM_GN_GELU, st0, cu(g0).float(), cu(be0).float())
     else:
         src = ops.Source(xb)
-    out, st_last, st_all = ops.trunk_fwd(src, lays, pad, impl="mux_f16x2", max_ctas=max_ctas)
+    out, st_last, st_all = ops.trunk_fwd(src, lays, pad, impl="mux_f16x2", max_ctas=max_ctas, loader=loader)
     got = ops.unpack_nchw(out, 16).cpu().numpy()
     assert relerr(got, raws[-1]) < 6e-6, relerr(got, raws[-1])
     ref_st = np.stack([raws[-1].reshape(B, 4, -1).sum(-1), (raws[-1] ** 2).reshape(B, 4, -1).sum(-1)], -1)
@@ -660,7 +661,10 @@ def test_trunk_persistent_kernel(B, H, W, R, pad, xform0, max_ctas):
         s = ops.Source(yb, L.XFORM_GN_GELU, sti, lays[i].gamma, lays[i].beta)
     assert (yb - out).abs().max().item() <= 2e-6 * max(1.0, float(yb.abs().max()))
     # twice in a row: scratch is re-zeroed by the call, same result bit for bit up to the statistics' atomic order
-    out2, _, _ = ops.trunk_fwd(src, lays, pad, impl="mux_f16x2", max_ctas=max_ctas)
+    out2, _, _ = ops.trunk_fwd(src, lays, pad, impl="mux_f16x2", max_ctas=max_ctas, loader=loader)
+    if loader == "bulk":  # the two loaders feed the same arithmetic
+        out3, _, _ = ops.trunk_fwd(src, lays, pad, impl="mux_f16x2", max_ctas=max_ctas, loader="threads")
+        assert (out3 - out).abs().max().item() <= 2e-6 * max(1.0, float(out.abs().max()))
     assert (out2 - out).abs().max().item() <= 2e-6 * max(1.0, float(out.abs().max()))
 
 

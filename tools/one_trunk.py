@@ -1,5 +1,5 @@
 """Developer tool: launch the persistent trunk kernel (pbmc_trunk_fwd, R layers of one level) a few times -- the target
-for ncu.  usage: one_trunk.py H W [R] [B] [max_ctas] [impl]"""
+for ncu.  usage: one_trunk.py H W [R] [B] [max_ctas] [impl] [loader = bulk | threads]"""
 import os
 import sys
 
@@ -15,6 +15,7 @@ R = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 B = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 max_ctas = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 impl = sys.argv[6] if len(sys.argv) > 6 else "mux_f16x2"
+loader = sys.argv[7] if len(sys.argv) > 7 else "bulk"
 g = torch.Generator(device=dev).manual_seed(5)
 x = torch.randn(B, 4, H, W, 4, device=dev, generator=g)
 stats = torch.stack([x.double().sum((2, 3, 4)), (x.double() ** 2).sum((2, 3, 4))], -1).contiguous()
@@ -39,9 +40,9 @@ for _ in range(6):
     flush.zero_()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    ops.trunk_fwd(src, lays, "replicate", impl=impl, max_ctas=max_ctas, ping=ping, stats=st, sync=sync)
+    ops.trunk_fwd(src, lays, "replicate", impl=impl, max_ctas=max_ctas, ping=ping, stats=st, sync=sync, loader=loader)
     b.record()
     ev.append((a, b))
 torch.cuda.synchronize()
 ms = sorted(a.elapsed_time(b) for a, b in ev[2:])
-print(f"trunk {H}x{W} R={R} B={B} max_ctas={max_ctas} {impl}: {ms[len(ms) // 2] * 1e3:.1f} us per launch, {ms[len(ms) // 2] * 1e3 / R:.1f} us per layer")
+print(f"trunk {H}x{W} R={R} B={B} max_ctas={max_ctas} {impl} loader={loader}: {ms[len(ms) // 2] * 1e3:.1f} us per launch, {ms[len(ms) // 2] * 1e3 / R:.1f} us per layer")
