@@ -773,7 +773,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rollout512", choices=sorted(WORKLOADS))
     ap.add_argument("--conv", default="auto", choices=["auto", "ffma", "umma_3xtf32", "umma_bf16", "umma_f16x2", "row_f16x2", "row_bf16", "mux_f16x2", "mux_bf16"])
-    ap.add_argument("--trunk", default="auto", choices=["auto", "per_layer", "auto_thread_loader"],
+    ap.add_argument("--trunk", default="auto", choices=["auto", "per_layer", "auto_bulk_loader"],
                     help="auto: the R trunk layers of a pyramid level as one persistent launch where it fits; per_layer: one launch per layer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p"], help="slab workloads: how the one-row T halo moves")

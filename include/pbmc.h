@@ -57,10 +57,13 @@ enum { PBMC_HEAD_CURL = 0, PBMC_HEAD_MAE = 1 };
 /* pbmc_net.flags: PER_LAYER = never use the persistent trunk kernel; UP_STAGED = the bicubic kernel writes the up-sampled
  * levels as conv[1]'s fp16 hi|lo operand image (PBMC_LAYOUT_STAGED16) and conv[1] stages them with TMA bulk copies
  * (bit-identical results; measured neutral-to-slower, so off by default) */
-enum { PBMC_NET_TRUNK_PER_LAYER = 1, PBMC_NET_UP_STAGED = 2, PBMC_NET_TRUNK_THREAD_LOADER = 4 };
-/* pbmc_trunk_desc.loader: BULK (default) = TMA bulk copies (cp.async.bulk + mbarrier transaction bytes), all rows of a layer
- * requested up front by one warp; THREADS = every worker loads its own pixels with ld.global (round 2's first version) */
-enum { PBMC_TRUNK_LOADER_BULK = 0, PBMC_TRUNK_LOADER_THREADS = 1 };
+enum { PBMC_NET_TRUNK_PER_LAYER = 1, PBMC_NET_UP_STAGED = 2, PBMC_NET_TRUNK_BULK_LOADER = 4 };
+/* pbmc_trunk_desc.loader: THREADS (default) = every worker loads its own pixels with ld.global.cg; BULK = TMA bulk copies
+ * (cp.async.bulk + mbarrier transaction bytes): all raw rows of a layer are requested up front by one warp, land in the
+ * stage slot their operand image will occupy and are converted in place.  Same results; measured SLOWER on B200 (77.9 vs
+ * 67.6 us per 4-layer launch at 512^2: the extra shared-memory loads and the per-row group barrier cost more than the
+ * hidden global-load latency gains), so it is opt-in. */
+enum { PBMC_TRUNK_LOADER_THREADS = 0, PBMC_TRUNK_LOADER_BULK = 1 };
 /* conv implementation selector: FFMA = fp32 CUDA cores; UMMA_* = tcgen05 tensor cores:
  * 3XTF32 / F16X2 split every operand into hi + lo (tf32 resp. fp16) and issue 3 passes --
  * fp32-grade accuracy; BF16 = single pass with bf16 operands (looser, stated bound).

@@ -20,7 +20,7 @@ XFORM_NONE, XFORM_GN_GELU, XFORM_GN, XFORM_GELU = 0, 1, 2, 3
 LAYOUT_BLOCKED, LAYOUT_STAGED16 = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
 HEAD_CURL, HEAD_MAE = 0, 1
-TRUNK_MODE = {"auto": 0, "per_layer": 1, "auto_thread_loader": 4}  # pbmc_net.flags bits (PBMC_NET_TRUNK_*)
+TRUNK_MODE = {"auto": 0, "per_layer": 1, "auto_bulk_loader": 4}  # pbmc_net.flags bits (PBMC_NET_TRUNK_*)
 NET_UP_STAGED = 2
 CONV_IMPL = {"auto": 0, "ffma": 1, "umma_3xtf32": 2, "umma_bf16": 3, "umma_f16x2": 4,
              "row_f16x2": 5, "row_bf16": 6, "mux_f16x2": 7, "mux_bf16": 8}

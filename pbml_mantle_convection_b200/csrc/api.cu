@@ -413,7 +413,7 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
       t.R = R; t.B = B; t.H = Hl; t.W = Wl; t.pad_mode = n.pad_mode; t.impl = n.conv_impl;
       t.max_ctas = L > 1 ? cta_budget[l] : 148;
       t.pre_zeroed = 1;  // the statistics / counter region was zeroed by the memset at the top of the forward
-      t.loader = (n.flags & PBMC_NET_TRUNK_THREAD_LOADER) ? PBMC_TRUNK_LOADER_THREADS : PBMC_TRUNK_LOADER_BULK;
+      t.loader = (n.flags & PBMC_NET_TRUNK_BULK_LOADER) ? PBMC_TRUNK_LOADER_BULK : PBMC_TRUNK_LOADER_THREADS;
       RC(conv_trunk_dispatch(t, sl));
     }
     for (int r = 0; r < R && !trunk_persistent; ++r) {

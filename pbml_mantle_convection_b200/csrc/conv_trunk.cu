@@ -58,7 +58,8 @@ struct ConvTrunkParams {
   int R, B, H, W, pad_mode, rpc;
 };
 
-// BULK loader: the raw input rows of a layer are copied into shared memory by the TMA engine (cp.async.bulk, one copy
+// BULK loader (opt-in, pbmc_trunk_desc.loader; correct, measured 15 % slower than the thread loader, see include/pbmc.h):
+// the raw input rows of a layer are copied into shared memory by the TMA engine (cp.async.bulk, one copy
 // per 4-channel plane and row, all rows of the layer requested up front by ONE thread right after the grid barrier) --
 // each row lands in the very stage slot its operand image will occupy (4 planes x 130 positions x 16 B of fp32 = the
 // size of the fp16 hi|lo image), the group that owns the row waits for its mbarrier, reads its pixels from shared memory,
@@ -578,7 +579,7 @@ int conv_trunk_dispatch(const pbmc_trunk_desc& t, cudaStream_t st) {
     PBMC_CUDA(cudaMemsetAsync(t.stats, 0, (size_t)t.R * t.B * 8 * sizeof(double), st));
   }
   if (bf16) return launch_trunk<1, false>(p, st);
-  return t.loader == PBMC_TRUNK_LOADER_THREADS ? launch_trunk<2, false>(p, st) : launch_trunk<2, true>(p, st);
+  return t.loader == PBMC_TRUNK_LOADER_BULK ? launch_trunk<2, true>(p, st) : launch_trunk<2, false>(p, st);
 }
 
 }  // namespace pbmc

@@ -131,7 +131,7 @@ class SurrogateEngine:
         n.head_kind = L.HEAD_CURL if m.loss_type == "curl" else L.HEAD_MAE
         n.p_pred = int(bool(m.p_pred))
         n.conv_impl = L.CONV_IMPL[self.conv_impl]
-        n.flags = L.TRUNK_MODE[self.trunk_mode] | (L.NET_UP_STAGED if self.up_staged else 0)  # "thread_loader": bits 4 | 0
+        n.flags = L.TRUNK_MODE[self.trunk_mode] | (L.NET_UP_STAGED if self.up_staged else 0)  
         n.a_bound = float(m.a_bound)
         n.conv0 = self.conv0.c()
         for l in range(m.levels):

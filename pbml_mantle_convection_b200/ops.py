@@ -296,7 +296,7 @@ def chan_sums(yb):
     return yb.double().sum(dim=(2, 3)).reshape(yb.shape[0], -1)
 
 
-def trunk_fwd(src: Source, layers, pad_mode, impl="auto", max_ctas=0, ping=None, stats=None, sync=None, loader="bulk"):
+def trunk_fwd(src: Source, layers, pad_mode, impl="auto", max_ctas=0, ping=None, stats=None, sync=None, loader="threads"):
     """The R FluidLayers of one pyramid level in ONE persistent launch (pbmc_trunk_fwd, csrc/conv_trunk.cu).
     `layers`: objects with .wpk_row, .bias, .gamma, .beta, .cout, .ksize, .cin_blks (engine._PackedLayer) -- each layer's
     GroupNorm affine is applied by ITS consumer.  Returns (raw output of the last layer [B,4,H,W,4], its GroupNorm sums
@@ -323,7 +323,7 @@ def trunk_fwd(src: Source, layers, pad_mode, impl="auto", max_ctas=0, ping=None,
     t.R, t.B, t.H, t.W = R, B, H, W
     t.pad_mode = L.PAD[pad_mode] if isinstance(pad_mode, str) else int(pad_mode)
     t.impl, t.max_ctas, t.pre_zeroed = L.CONV_IMPL[impl], int(max_ctas), 0
-    t.loader = {"bulk": 0, "threads": 1}[loader]
+    t.loader = {"threads": 0, "bulk": 1}[loader]
     L.check(L.load().pbmc_trunk_fwd(C.byref(t), L.stream_ptr(dev)), "pbmc_trunk_fwd")
     return ping[(R - 1) & 1], stats[R - 1], stats
 

@@ -618,7 +618,7 @@ class _Lay:
     (1, 40, 130, 4, "replicate", True, 0), (2, 33, 256, 3, "zeros", False, 0), (1, 70, 300, 4, "reflect", True, 0),
     (1, 64, 64, 4, "replicate", True, 3), (1, 7, 9, 2, "replicate", True, 2), (3, 50, 77, 1, "replicate", False, 0),
     (1, 128, 128, 6, "replicate", True, 0)])
-@pytest.mark.parametrize("loader", ["bulk", "threads"])
+@pytest.mark.parametrize("loader", ["threads", "bulk"])
 def test_trunk_persistent_kernel(B, H, W, R, pad, xform0, max_ctas, loader):
     """pbmc_trunk_fwd: R FluidLayers (conv -> GroupNorm -> GELU, pytorch_networks_convae.py:790-799, :1323-1324) in one
     persistent launch with a grid-wide barrier per layer, against (a) the float64 numpy oracle and (b) the same layers

@@ -15,7 +15,7 @@ R = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 B = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 max_ctas = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 impl = sys.argv[6] if len(sys.argv) > 6 else "mux_f16x2"
-loader = sys.argv[7] if len(sys.argv) > 7 else "bulk"
+loader = sys.argv[7] if len(sys.argv) > 7 else "threads"
 g = torch.Generator(device=dev).manual_seed(5)
 x = torch.randn(B, 4, H, W, 4, device=dev, generator=g)
 stats = torch.stack([x.double().sum((2, 3, 4)), (x.double() ** 2).sum((2, 3, 4))], -1).contiguous()
