@@ -629,12 +629,17 @@ class TS(nn.Module):
             pl.T_out, pl.dt_out, pl.f_out = pl.split(pl.out)
             pl.graph, pl.calls = None, 0
             self._plan, self._plan_key = pl, key
+        # `forward` may already have copied T into the cached plan and REPLAYED its graph speculatively, so that all of the
+        # bookkeeping above overlapped the device work; the replay counts only if this call resolved to that very plan
+        # with unchanged parameters (otherwise its results are discarded: it only wrote the plan's own buffers)
+        spec_ok = getattr(self, "_spec_plan", None) is pl and early_copied and pl is self._early_plan
         if (prm, prm_nd) != pl.members_key:
             pl.members.copy_(ops.make_members([prm] * B, "cpu", nd_override=[prm_nd] * B))
             pl.members_key = (prm, prm_nd)
+            spec_ok = False
         if not early_copied or pl is not self._early_plan:
             pl.T_in.copy_(T_prev.reshape(B, H, W), non_blocking=True)
-        self._early_plan = None
+        self._early_plan = self._spec_plan = None
 
         def body():
             st = pl.state
@@ -658,7 +663,9 @@ class TS(nn.Module):
                 with torch.cuda.graph(g):
                     body()
                 pl.graph = g
-            pl.graph.replay()
+                spec_ok = False
+            if not spec_ok:
+                pl.graph.replay()
         T_all, dt_all, f_all = pl.split(pl.out.clone())  # callers own what they get
         x = {0: T_prev if T_prev.is_cuda else pl.T_in.clone().view(T_prev.shape)}
         dts = {}
@@ -722,9 +729,15 @@ class TS(nn.Module):
         # The host->device copy of T is the first thing the device needs: if the cached plan fits this call's shape and
         # dtype it is enqueued before the (tens of microseconds of) host-side bookkeeping below, which then overlaps it.
         early, pl0 = False, self._plan
+        self._spec_plan = None
         if pl0 is not None and pl0.T_in.dtype == dtype and tuple(pl0.T_in.shape) == (B, H, W) and T_prev.numel() == B * H * W:
             pl0.T_in.copy_(T_prev.reshape(B, H, W), non_blocking=True)
             early = True
+            if self.use_cuda_graph and pl0.graph is not None and self.ad is not None and not torch.cuda.is_current_stream_capturing():
+                # speculative replay: the device starts on this call's T at once; _forward_fused verifies below that the
+                # call really resolves to this plan (same grid, weights, parameters) and otherwise redoes it
+                pl0.graph.replay()
+                self._spec_plan = pl0
         self._early_plan = pl0 if early else None
         grid = self._get_grid(xc, yc, ycc, dev)
         fl = lambda t: float(t)
