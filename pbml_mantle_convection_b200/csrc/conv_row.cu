@@ -647,6 +647,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
           if (h_on && sy >= 0 && (hch >> 2) < gi.nb) B.h = __ldg(gi.base + hoff + ro);
         };
         auto gproc = [&](int st, GBuf& B) {
+          if (tr_lane && st / CR_NPG < 37) CR_TR(100 + pg * 300 + 8 * (st / CR_NPG));
           float v[16] = {B.v0.x, B.v0.y, B.v0.z, B.v0.w, B.v1.x, B.v1.y, B.v1.z, B.v1.w,
                          B.v2.x, B.v2.y, B.v2.z, B.v2.w, B.v3.x, B.v3.y, B.v3.z, B.v3.w};
           float hv = B.h;
@@ -669,7 +670,9 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
           }
           const uint32_t slot = (uint32_t)st & (NSTAGE - 1);
           const uint32_t sa = as_addr + slot * (uint32_t)G::STAGE_BYTES;
+          if (tr_lane && st / CR_NPG < 37) CR_TR(101 + pg * 300 + 8 * (st / CR_NPG));
           if (st >= NSTAGE) mbar_wait_parked(a_empty(slot), (((uint32_t)st / NSTAGE) & 1u) ^ 1u);  // first pass: ring is free
+          if (tr_lane && st / CR_NPG < 37) CR_TR(102 + pg * 300 + 8 * (st / CR_NPG));
           auto sts = [](uint32_t addr, uint4 q) {
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
           };
@@ -696,9 +699,12 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
               asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha), "h"(__bfloat16_as_ushort(__float2bfloat16_rn(hv))) : "memory");
             }
           }
+          if (tr_lane && st / CR_NPG < 37) CR_TR(104 + pg * 300 + 8 * (st / CR_NPG));
           fence_proxy_async_smem();
+          if (tr_lane && st / CR_NPG < 37) CR_TR(105 + pg * 300 + 8 * (st / CR_NPG));
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full(slot));
+          if (tr_lane && st / CR_NPG < 37) CR_TR(103 + pg * 300 + 8 * (st / CR_NPG));
         };
         // The producer warps stage the groups that are not operand images (nslist), in (row, group) order, the k-th
         // such stage in slot k % NSTAGE of their own ring; group pg takes k = pg, pg + NPG, ...
@@ -714,6 +720,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         for (int k = pg; k < total_ns; k += 2 * CR_NPG) {
           gproc(k, g0);
           if (k + 2 * CR_NPG < total_ns) kload(k + 2 * CR_NPG, g0);
+          if (tr_lane && k / CR_NPG < 37) CR_TR(106 + pg * 300 + 8 * (k / CR_NPG));
           if (k + CR_NPG < total_ns) {
             gproc(k + CR_NPG, g1);
             if (k + 3 * CR_NPG < total_ns) kload(k + 3 * CR_NPG, g1);
