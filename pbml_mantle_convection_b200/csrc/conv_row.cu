@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
           B.v0 = B.v1 = B.v2 = B.v3 = z;
           B.h = 0.f;
           const float* cb = gi.base + coff + ro;
-          if (col_ok && sy >= 0) {
+          if (col_ok && sy >= 0 && !CR_DBG(2)) {
             B.v0 = ldg4(cb);
             if (gi.nb > 1) B.v1 = ldg4(cb + pstride);
             if (gi.nb > 2) B.v2 = ldg4(cb + 2 * pstride);
@@ -676,7 +676,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
           auto sts = [](uint32_t addr, uint4 q) {
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
           };
-          if (PARTS == 2) {
+          if (CR_DBG(4)) {
+          } else if (PARTS == 2) {
             uint4 h0, l0, h1, l1;
             split_f16(v, h0, l0);
             split_f16(v + 8, h1, l1);
@@ -700,7 +701,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
             }
           }
           if (tr_lane && st / CR_NPG < 37) CR_TR(104 + pg * 300 + 8 * (st / CR_NPG));
-          fence_proxy_async_smem();
+          if (!CR_DBG(32)) fence_proxy_async_smem();
           if (tr_lane && st / CR_NPG < 37) CR_TR(105 + pg * 300 + 8 * (st / CR_NPG));
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full(slot));
