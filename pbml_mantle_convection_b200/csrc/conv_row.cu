@@ -19,8 +19,8 @@
 // i.e. k TMEM loads from the SAME lane -- no shuffles, no junk lanes, no halo columns in M.
 // D_r live in a TMEM ring of ND accumulators (N columns each).
 //
-// Warp roles:  0-7 epilogue (two sets of 4 warps on alternate output rows; TMEM lane quarter = warp & 3),
-// 8 .. 8+4*NPG-1 producers (NPG groups of 128 threads, one thread per position plus the k-1 halo positions,
+// Warp roles:  epilogue sets of 4 warps (output rows dealt round-robin; TMEM lane quarter = warp & 3),
+// then the producers (NPG groups of 128 threads, one thread per position plus the k-1 halo positions,
 // round-robin over stages, loads two stages ahead), last warp = MMA issuer (one elected lane) + TMEM allocator.
 // Pipelines: a_full/a_empty (producers <-> MMA, NSTAGE smem stages; one stage = one input row of one
 // 16-channel group), d_full/d_empty (MMA <-> epilogue, ND accumulators; D_r is released by the k output
@@ -36,10 +36,14 @@ namespace pbmc {
 
 extern thread_local int g_conv_pdl_next;  // conv_mux.cu: set by api.cu right before the launch it applies to
 
-constexpr int CR_EPI_WARPS = 8;                        // two sets of 4 (alternate output rows)
-constexpr int CR_NPG = 3;                              // producer groups (4 warps = 128 positions each)
-constexpr int CR_MMA_WARP = CR_EPI_WARPS + 4 * CR_NPG;  // warps 0-7 epilogue, 8 .. 8+4*NPG-1 producers, then the MMA issuer
-constexpr int CR_TMA_WARP = CR_MMA_WARP + 1;            // one lane bulk-copies the stages of operand-image (STAGED16) sources
+// Role split (template parameter NPG of the kernel): 5 sets of 4 warps are divided between epilogue and producers.
+//   NPG = 3: two epilogue sets (alternate output rows) + three producer groups -- one 16-channel group per row, where an
+//            output row is due after every stage;
+//   NPG = 4: one epilogue set + four producer groups -- several groups per row (conv[1]: 7 stages per output row), where
+//            the epilogue idles and the producers' serial per-stage chain sets the pace (tools/exp_conv1.sh).
+constexpr int CR_SETS = 5;
+constexpr int CR_MMA_WARP = 4 * CR_SETS;      // warps 0 .. 4*EPI_SETS-1 epilogue, then 4*NPG producer warps, then the MMA issuer
+constexpr int CR_TMA_WARP = CR_MMA_WARP + 1;  // one lane bulk-copies the stages of operand-image (STAGED16) sources
 constexpr int CR_THREADS = (CR_TMA_WARP + 1) * 32;
 constexpr int CR_NT = 8;                                // stages of the bulk-copy ring (power of two)
 constexpr int CR_MAXG = 24;
@@ -113,7 +117,8 @@ struct RowGeom {
   } while (0)
 #endif
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CR_EPI_WARPS * 32) : "memory"); }
+template <int NWARPS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NWARPS * 32) : "memory"); }
 
 __device__ __forceinline__ float xform1(float v, float a, float b, int xform) {
   if (xform == PBMC_XFORM_NONE) return v;
@@ -122,9 +127,11 @@ __device__ __forceinline__ float xform1(float v, float a, float b, int xform) {
   return v;
 }
 
-template <int KS, int PARTS>
+template <int KS, int PARTS, int NPG>
 __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_constant__ ConvRowParams p) {
   using G = RowGeom<KS, PARTS>;
+  constexpr int CR_NPG = NPG, EPI_SETS = CR_SETS - NPG, CR_EPI_WARPS = 4 * EPI_SETS;
+  static_assert(NPG >= 1 && EPI_SETS >= 1, "role split");
   constexpr int P = G::P, N = G::N, NSTAGE = G::NSTAGE, ND = G::ND, PLANE = G::PLANE;
   static_assert(8 * (2 * NSTAGE + 2 * ND + 2 * CR_NT) <= 448, "barrier area");
   static_assert((NSTAGE & (NSTAGE - 1)) == 0, "NSTAGE must be a power of two");
@@ -238,8 +245,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
   if (tid == 0) CR_TR(1);
 
   if (warp < CR_EPI_WARPS) {
-    // ================================================================ epilogue: two sets of 4 warps,
-    // set e takes output rows yo = e, e+2, ...; thread = output column (TMEM lane quarter = warp & 3)
+    // ================================================================ epilogue: EPI_SETS sets of 4 warps,
+    // set e takes output rows yo = e, e + EPI_SETS, ...; thread = output column (TMEM lane quarter = warp & 3)
     const int eset = warp >> 2, q = warp & 3;
     const int col = q * 32 + lane, gx = x0 + col;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -250,15 +257,15 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     const bool epi_gelu = p.epi_act == PBMC_ACT_GELU;
     const uint32_t bias_addr = smem_u32(bias_s);
     float* orow = p.out + (((size_t)b * cout_blks) * plane_px + (size_t)(y0 + eset) * W + gx) * 4;
-    const size_t blk_stride = plane_px * 4, row_stride = (size_t)2 * W * 4;
+    const size_t blk_stride = plane_px * 4, row_stride = (size_t)EPI_SETS * W * 4;
     const bool col_in = gx < W;
     // The epilogue's instruction stream is the busiest in the CTA (ncu: half of all issued instructions), so
     // the common shape -- 16 outputs, no activation, no channel sums -- gets a loop with nothing else in it.
     auto row_loop = [&](auto lean_tag) {
       constexpr bool LEAN = decltype(lean_tag)::value;
-      // ring positions advance by 2 rows per iteration (ND is even: a set always sees the same slot parity class)
+      // ring positions advance by EPI_SETS rows per iteration
       uint32_t s_lo = (uint32_t)eset % ND, s_hi = (uint32_t)(eset + KS - 1) % ND, par_hi = ((uint32_t)(eset + KS - 1) / ND) & 1u;
-      for (int yo = eset; yo < nrows; yo += 2) {
+      for (int yo = eset; yo < nrows; yo += EPI_SETS) {
         mbar_wait_parked(d_full(s_hi), par_hi);  // the last input row this output row needs (commits are in order)
         tc_fence_after();
         if ((tid & 127) == 0) CR_TR(1200 + 3 * yo);
@@ -308,8 +315,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
           }
         }
         orow += row_stride;
-        s_lo += 2; if (s_lo >= (uint32_t)ND) s_lo -= ND;
-        s_hi += 2; if (s_hi >= (uint32_t)ND) { s_hi -= ND; par_hi ^= 1u; }
+        s_lo += EPI_SETS; if (s_lo >= (uint32_t)ND) s_lo -= ND;
+        s_hi += EPI_SETS; if (s_hi >= (uint32_t)ND) { s_hi -= ND; par_hi ^= 1u; }
         if ((tid & 127) == 0) CR_TR(1202 + 3 * yo);
       }
     };
@@ -325,13 +332,13 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         const double c2 = warp_sum((double)s2[qb]);
         if (lane == 0) { red[(warp * 4 + qb) * 2] = a; red[(warp * 4 + qb) * 2 + 1] = c2; }
       }
-      epi_bar_sync();
+      epi_bar_sync<CR_EPI_WARPS>();
       if (tid < 8 && (tid >> 1) < p.cout_blks) {
         double t = 0.0;
         for (int w = 0; w < CR_EPI_WARPS; ++w) t += red[(w * 4 + (tid >> 1)) * 2 + (tid & 1)];
         atomicAdd(p.out_stats + ((size_t)b * p.cout_blks + (tid >> 1)) * 2 + (tid & 1), t);
       }
-      epi_bar_sync();
+      epi_bar_sync<CR_EPI_WARPS>();
     }
     if (want_cs) {
 #pragma unroll
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         const double a = warp_sum((double)cs[c]);
         if (lane == 0) red[warp * 4 + c] = a;
       }
-      epi_bar_sync();
+      epi_bar_sync<CR_EPI_WARPS>();
       if (tid < 4) {
         double t = 0.0;
         for (int w = 0; w < CR_EPI_WARPS; ++w) t += red[w * 4 + tid];
@@ -927,15 +934,15 @@ static int choose_rpc(int units, int H, int ks, int max_ctas) {
   return best;
 }
 
-template <int KS, int PARTS>
-static int launch_row(ConvRowParams& p, cudaStream_t st) {
+template <int KS, int PARTS, int NPG>
+static int launch_row_npg(ConvRowParams& p, cudaStream_t st) {
   using G = RowGeom<KS, PARTS>;
   const size_t smem = CR_SMEM_HDR + (size_t)p.ngroups * G::B_GROUP + (size_t)(G::NSTAGE + (p.has_staged ? CR_NT : 0)) * G::STAGE_BYTES +
                       (size_t)p.cin_ch * 8;
   if (smem > 227 * 1024) return PBMC_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
-    PBMC_CUDA(cudaFuncSetAttribute(conv_row_kernel<KS, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PBMC_CUDA(cudaFuncSetAttribute(conv_row_kernel<KS, PARTS, NPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int nstrips = cdiv(p.W, 128);
@@ -957,9 +964,17 @@ static int launch_row(ConvRowParams& p, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = (pdl || g_conv_pdl_next) ? 1 : 0;
   g_conv_pdl_next = 0;
-  PBMC_CUDA(cudaLaunchKernelEx(&cfg, conv_row_kernel<KS, PARTS>, p));
+  PBMC_CUDA(cudaLaunchKernelEx(&cfg, conv_row_kernel<KS, PARTS, NPG>, p));
   PBMC_CHECK_LAUNCH("conv_row_kernel");
   return PBMC_OK;
+}
+
+template <int KS, int PARTS>
+static int launch_row(ConvRowParams& p, cudaStream_t st) {
+  // several K groups per input row (conv[1]): four producer groups, one epilogue set; else three and two
+  static const int forced = PBMC_DEV_KNOB("PBMC_ROW_NPG", 0);  // developer knob
+  const bool heavy = forced ? forced == 4 : p.ngroups >= 3;
+  return heavy ? launch_row_npg<KS, PARTS, 4>(p, st) : launch_row_npg<KS, PARTS, 3>(p, st);
 }
 
 static int row_groups(const pbmc_conv_desc& d) {
