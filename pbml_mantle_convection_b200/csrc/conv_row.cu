@@ -76,10 +76,17 @@ struct RowGroup {
   int staged;         // PBMC_LAYOUT_STAGED16: base = this sample's fp16 hi|lo operand image, rows are bulk-copied
 };
 
-template <int KS, int PARTS>
+// MERGE (k = 3, fp16 hi|lo): the hi*hi and hi*lo products share ONE N = 96 MMA -- B = [W_hi ; W_lo] stacked along N, so A_hi is
+// fetched from shared memory once for both (the MMA is operand-fetch bound: 4 KB of A + 1.5 KB of B per N = 48 MMA at
+// 128 B/clk) -- followed by the N = 48 MMA A_lo * W_hi on the first half: 6 MMAs and 37.5 KB of operand reads per stage
+// instead of 9 and 49.5 KB.  An accumulator is then 96 columns, [0,48) = hi*hi + lo*hi and [48,96) = hi*lo, summed by the
+// epilogue; the ring shrinks to 5 accumulators.
+template <int KS, int PARTS, bool MERGE = false>
 struct RowGeom {
+  static_assert(!MERGE || (KS == 3 && PARTS == 2), "merged passes: 3x3, fp16 hi|lo only");
   static constexpr int P = KS / 2;
   static constexpr int N = KS * 16;
+  static constexpr int DN = MERGE ? 2 * N : N;      // TMEM columns of one accumulator
   static constexpr int PWS = 128 + KS - 1;
   static constexpr int PLANE = (PWS + 7) / 8 * 8;   // positions per K-chunk plane (16 B each)
   static constexpr int PART_BYTES = 2 * PLANE * 16;  // two K chunks (8 channels each)
@@ -87,11 +94,11 @@ struct RowGeom {
   static constexpr int NSTAGE = 8;
   // accumulator ring: the MMA warp may run ND - KS rows ahead of the epilogue (measured with tools/probe:
   // dependent accumulation into the same TMEM columns costs nothing, one N = 48 MMA is ~44 clk)
-  static constexpr int ND = KS == 3 ? 10 : 6;
-  static constexpr uint32_t TMEM_COLS = ND * N <= 256 ? 256 : 512;
+  static constexpr int ND = MERGE ? 5 : (KS == 3 ? 10 : 6);
+  static constexpr uint32_t TMEM_COLS = ND * DN <= 256 ? 256 : 512;
   static constexpr int B_TILE = 2 * N * 16;  // one (group, dx, part) operand: [2 chunks][N rows][16 B]
   static constexpr int B_GROUP = KS * PARTS * B_TILE;
-  static_assert(ND * N <= 512, "TMEM has 512 columns");
+  static_assert(ND * DN <= 512, "TMEM has 512 columns");
   static_assert(ND >= KS + 1, "the MMA must be able to run ahead of the epilogue");
 };
 
@@ -129,14 +136,16 @@ __device__ __forceinline__ float xform1(float v, float a, float b, int xform) {
 
 template <int KS, int PARTS, int NPG>
 __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_constant__ ConvRowParams p) {
-  using G = RowGeom<KS, PARTS>;
+  constexpr bool MERGE = NPG == 4 && KS == 3 && PARTS == 2;  // the several-groups-per-row variant (conv[1]) merges two passes
+  using G = RowGeom<KS, PARTS, MERGE>;
   constexpr int CR_NPG = NPG, EPI_SETS = CR_SETS - NPG, CR_EPI_WARPS = 4 * EPI_SETS;
   static_assert(NPG >= 1 && EPI_SETS >= 1, "role split");
-  constexpr int P = G::P, N = G::N, NSTAGE = G::NSTAGE, ND = G::ND, PLANE = G::PLANE;
+  constexpr int P = G::P, N = G::N, DN = G::DN, NSTAGE = G::NSTAGE, ND = G::ND, PLANE = G::PLANE;
   static_assert(8 * (2 * NSTAGE + 2 * ND + 2 * CR_NT) <= 448, "barrier area");
   static_assert((NSTAGE & (NSTAGE - 1)) == 0, "NSTAGE must be a power of two");
   constexpr uint32_t FMT = PARTS == 2 ? 0u : 1u;  // fp16 hi|lo split, or one bf16 pass
   constexpr uint32_t IDESC = row_idesc(FMT, N);
+  constexpr uint32_t IDESC2 = row_idesc(FMT, 2 * N);  // MERGE: A_hi x [W_hi ; W_lo]
   extern __shared__ __align__(128) unsigned char smem[];
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 448);  // barriers occupy [0, 8 * (2 NSTAGE + 2 ND))
   RowGroup* gtab = reinterpret_cast<RowGroup*>(smem + 512);
@@ -217,7 +226,16 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     if (tid < 16) bias_s[tid] = tid < p.cout_blks * 4 ? __ldg(p.bias + tid) : 0.f;
     const uint4* wsrc = reinterpret_cast<const uint4*>(p.wpk);
     uint4* wdst = reinterpret_cast<uint4*>(Bs);
-    for (int e = tid; e < NG * (G::B_GROUP / 16); e += CR_THREADS) wdst[e] = __ldg(wsrc + e);
+    if (MERGE) {
+      // [group][dx][part][chunk][48 rows] -> [group][dx][chunk][96 rows: hi 0..47 | lo 48..95]: one N = 96 operand per (group, dx)
+      for (int e = tid; e < NG * (G::B_GROUP / 16); e += CR_THREADS) {
+        const int q = e / (2 * N), row = e - q * (2 * N);  // q = (group, dx, part), row = chunk * N + r
+        const int part = q & 1, chunk = row >= N;
+        wdst[(q >> 1) * (4 * N) + chunk * (2 * N) + part * N + (row - chunk * N)] = __ldg(wsrc + e);
+      }
+    } else {
+      for (int e = tid; e < NG * (G::B_GROUP / 16); e += CR_THREADS) wdst[e] = __ldg(wsrc + e);
+    }
   }
   // Everything above overlaps the tail of the previous kernel in the stream when this kernel was launched with
   // programmatic stream serialization; the producer's outputs (activations, GroupNorm sums) are read only below.
@@ -273,7 +291,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         uint32_t sl = s_lo;
 #pragma unroll
         for (int dy = 0; dy < KS; ++dy) {
-          if (!CR_DBG(8)) tmem_ld16_issue(lane_addr + sl * (uint32_t)N + (uint32_t)(dy * 16), r[dy]);
+          if (!CR_DBG(8)) tmem_ld16_issue(lane_addr + sl * (uint32_t)DN + (uint32_t)(dy * 16), r[dy]);
           if (++sl == (uint32_t)ND) sl = 0;
         }
 #pragma unroll
@@ -320,7 +338,73 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         if ((tid & 127) == 0) CR_TR(1202 + 3 * yo);
       }
     };
-    if (cout_blks == 4 && !epi_gelu && !want_cs)
+    // MERGE: an accumulator is [0,48) = hi*hi + lo*hi | [48,96) = hi*lo; two halves of 8 output channels keep 48 values live
+    auto row_loop_merged = [&]() {
+      uint32_t s_lo = (uint32_t)eset % ND, s_hi = (uint32_t)(eset + KS - 1) % ND, par_hi = ((uint32_t)(eset + KS - 1) / ND) & 1u;
+      for (int yo = eset; yo < nrows; yo += EPI_SETS) {
+        mbar_wait_parked(d_full(s_hi), par_hi);
+        tc_fence_after();
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          uint32_t ra[KS][8], rb[KS][8];
+          uint32_t sl = s_lo;
+#pragma unroll
+          for (int dy = 0; dy < KS; ++dy) {
+            tmem_ld8_issue(lane_addr + sl * (uint32_t)DN + (uint32_t)(dy * 16 + hq * 8), ra[dy]);
+            tmem_ld8_issue(lane_addr + sl * (uint32_t)DN + (uint32_t)(N + dy * 16 + hq * 8), rb[dy]);
+            if (++sl == (uint32_t)ND) sl = 0;
+          }
+#pragma unroll
+          for (int dy = 0; dy < KS; ++dy) { tmem_ld_wait8(ra[dy]); tmem_ld_wait8(rb[dy]); }
+          if (hq == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              sl = s_lo;
+#pragma unroll
+              for (int dy = 0; dy < KS; ++dy) {
+                mbar_arrive_n(d_empty(sl), yo == 0 ? (uint32_t)(KS - dy) : 1u);
+                if (++sl == (uint32_t)ND) sl = 0;
+              }
+            }
+          }
+          if (col_in) {
+#pragma unroll
+            for (int qh = 0; qh < 2; ++qh) {
+              const int qb = 2 * hq + qh;
+              if (qb < cout_blks) {
+                float4 bq;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bq.x), "=f"(bq.y), "=f"(bq.z), "=f"(bq.w) : "r"(bias_addr + qb * 16));
+                const float bias4[4] = {bq.x, bq.y, bq.z, bq.w};
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float a = __uint_as_float(ra[0][qh * 4 + e]), c = __uint_as_float(rb[0][qh * 4 + e]);
+#pragma unroll
+                  for (int dy = 1; dy < KS; ++dy) {
+                    a += __uint_as_float(ra[dy][qh * 4 + e]);
+                    c += __uint_as_float(rb[dy][qh * 4 + e]);
+                  }
+                  a = (a + c) + bias4[e];
+                  if (epi_gelu) a = gelu_erf(a);
+                  o[e] = a;
+                }
+                *reinterpret_cast<float4*>(orow + qb * blk_stride) = make_float4(o[0], o[1], o[2], o[3]);
+                s1[qb] += (o[0] + o[1]) + (o[2] + o[3]);
+                s2[qb] = fmaf(o[0], o[0], fmaf(o[1], o[1], fmaf(o[2], o[2], fmaf(o[3], o[3], s2[qb]))));
+                if (qb == 0 && want_cs) { cs[0] += o[0]; cs[1] += o[1]; cs[2] += o[2]; cs[3] += o[3]; }
+              }
+            }
+          }
+        }
+        orow += row_stride;
+        s_lo += EPI_SETS; if (s_lo >= (uint32_t)ND) s_lo -= ND;
+        s_hi += EPI_SETS; if (s_hi >= (uint32_t)ND) { s_hi -= ND; par_hi ^= 1u; }
+      }
+    };
+    if (MERGE)
+      row_loop_merged();
+    else if (cout_blks == 4 && !epi_gelu && !want_cs)
       row_loop(std::true_type{});
     else
       row_loop(std::false_type{});
@@ -770,7 +854,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     // Stage (ri, g) lives in the producers' ring (its pk-th stage) or, for an operand-image group, in the bulk-copy
     // ring (its tk-th stage); with no such group pk is simply the stage number.
     const bool leader = elect_one();
-    constexpr uint32_t A_LBO = PLANE * 16, B_LBO = N * 16, SBO = 128;
+    constexpr uint32_t A_LBO = PLANE * 16, B_LBO = (MERGE ? 2 * N : N) * 16, SBO = 128;
     const uint64_t a_desc0 = umma_desc(smem_u32(As), A_LBO, SBO), b_desc0 = umma_desc(smem_u32(Bs), B_LBO, SBO);
 #ifdef PBMC_ROW_TRACE
     const uint32_t dx_step = (uint32_t)p.dbg_dx >> 4;
@@ -795,7 +879,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
       bool ready = total > 0 && mbar_test(a_full(0), 0u);
       for (int ri = 0; ri < nin; ++ri) {
         if (ri >= ND) mbar_wait(d_empty(ds), d_par ^ 1u);  // first ND rows: the ring is free
-        const uint32_t dcol = tmem_base + ds * (uint32_t)N;
+        const uint32_t dcol = tmem_base + ds * (uint32_t)DN;
         for (int g = 0; g < NG; ++g, ++st) {
           const uint32_t slot = (uint32_t)st & (NSTAGE - 1);
           if (!ready) mbar_wait(a_full(slot), ((uint32_t)st / NSTAGE) & 1u);
@@ -810,10 +894,15 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
               const uint64_t a_hi = a_s + (uint64_t)(dx * dx_step);
               const uint64_t b_hi = b_s + (uint64_t)(dx * PARTS * (G::B_TILE >> 4));
               if (CR_DBG(1)) continue;
-              umma_ss<1>(dcol, a_hi, b_hi, IDESC, (uint32_t)(g | dx));
-              if (PARTS == 2) {
-                umma_ss<1>(dcol, a_hi + (uint64_t)(G::PART_BYTES >> 4), b_hi, IDESC, 1u);
-                umma_ss<1>(dcol, a_hi, b_hi + (uint64_t)(G::B_TILE >> 4), IDESC, 1u);
+              if (MERGE) {
+                umma_ss<1>(dcol, a_hi, b_hi, IDESC2, (uint32_t)(g | dx));                          // A_hi x [W_hi ; W_lo] -> 96 columns
+                umma_ss<1>(dcol, a_hi + (uint64_t)(G::PART_BYTES >> 4), b_hi, IDESC, 1u);          // A_lo x W_hi -> the first 48
+              } else {
+                umma_ss<1>(dcol, a_hi, b_hi, IDESC, (uint32_t)(g | dx));
+                if (PARTS == 2) {
+                  umma_ss<1>(dcol, a_hi + (uint64_t)(G::PART_BYTES >> 4), b_hi, IDESC, 1u);
+                  umma_ss<1>(dcol, a_hi, b_hi + (uint64_t)(G::B_TILE >> 4), IDESC, 1u);
+                }
               }
             }
             umma_commit(a_empty(slot));                // frees the smem stage once these MMAs have read it
@@ -831,7 +920,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
       bool ready = total > 0 && mbar_test(full, par);
       for (int ri = 0; ri < nin; ++ri) {
         if (ri >= ND) mbar_wait(d_empty(ds), d_par ^ 1u);  // first ND rows: the ring is free
-        const uint32_t dcol = tmem_base + ds * (uint32_t)N;
+        const uint32_t dcol = tmem_base + ds * (uint32_t)DN;
         for (int g = 0; g < NG; ++g, ++st) {
           if (!ready) mbar_wait(full, par);
           tc_fence_after();
@@ -850,10 +939,15 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
               const uint64_t a_hi = a_s + (uint64_t)(dx * dx_step);
               const uint64_t b_hi = b_s + (uint64_t)(dx * PARTS * (G::B_TILE >> 4));
               if (CR_DBG(1)) continue;
-              umma_ss<1>(dcol, a_hi, b_hi, IDESC, (uint32_t)(g | dx));
-              if (PARTS == 2) {
-                umma_ss<1>(dcol, a_hi + (uint64_t)(G::PART_BYTES >> 4), b_hi, IDESC, 1u);
-                umma_ss<1>(dcol, a_hi, b_hi + (uint64_t)(G::B_TILE >> 4), IDESC, 1u);
+              if (MERGE) {
+                umma_ss<1>(dcol, a_hi, b_hi, IDESC2, (uint32_t)(g | dx));                          // A_hi x [W_hi ; W_lo] -> 96 columns
+                umma_ss<1>(dcol, a_hi + (uint64_t)(G::PART_BYTES >> 4), b_hi, IDESC, 1u);          // A_lo x W_hi -> the first 48
+              } else {
+                umma_ss<1>(dcol, a_hi, b_hi, IDESC, (uint32_t)(g | dx));
+                if (PARTS == 2) {
+                  umma_ss<1>(dcol, a_hi + (uint64_t)(G::PART_BYTES >> 4), b_hi, IDESC, 1u);
+                  umma_ss<1>(dcol, a_hi, b_hi + (uint64_t)(G::B_TILE >> 4), IDESC, 1u);
+                }
               }
             }
             umma_commit(c_empty);                      // frees the smem stage once these MMAs have read it
