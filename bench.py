@@ -431,6 +431,7 @@ def run_ours(args, wl):
     net = primary_net(dev)
     net.conv_impl = args.conv
     net.trunk_mode = args.trunk
+    net.up_staged = bool(args.up_staged)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
     T0 = np.stack([P.synthetic_T0(H, W, seed=1 + rank * B + m) for m in range(B)])
     dev_ms, wall, finite, clk = timed_rollout(net, H, W, B, rank, world, local, dev, K, Wm, flush, T0)
@@ -552,7 +553,7 @@ def run_ours(args, wl):
             "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "desc": wl["desc"], "grid": [H, W], "batch_per_gpu": B,
-                       "net": "NewFluidNet(levels=6,c_i=7,c_h=16,c_o=2,k=3,replicate,symm,curl,repeats=4)", "conv_impl": args.conv, "trunk": args.trunk,
+                       "net": "NewFluidNet(levels=6,c_i=7,c_h=16,c_o=2,k=3,replicate,symm,curl,repeats=4)", "conv_impl": args.conv, "trunk": args.trunk, "up_staged": bool(args.up_staged),
                        "l2": "flushed (256 MiB write, untimed) between timed steps; per-step CUDA-event intervals summed",
                        "parallelism": f"{world} independent rollouts (no collective)" if world > 1 else "single GPU",
                        "host_affinity": f"each rank bound to its own {numa_cpus} CPUs out of its GPU's NUMA-local set (NVML)" if numa_cpus else "unbound",
@@ -775,6 +776,8 @@ def main():
     ap.add_argument("--conv", default="auto", choices=["auto", "ffma", "umma_3xtf32", "umma_bf16", "umma_f16x2", "row_f16x2", "row_bf16", "mux_f16x2", "mux_bf16"])
     ap.add_argument("--trunk", default="auto", choices=["auto", "per_layer", "auto_bulk_loader"],
                     help="auto: the R trunk layers of a pyramid level as one persistent launch where it fits; per_layer: one launch per layer")
+    ap.add_argument("--up-staged", dest="up_staged", action="store_true",
+                    help="up-sampled pyramid levels written as conv[1]'s fp16 hi|lo operand image and staged by TMA bulk copies")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p"], help="slab workloads: how the one-row T halo moves")
     ap.add_argument("--dt-sync", dest="dt_sync", default="flags", choices=["flags", "nccl"],
