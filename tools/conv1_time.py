@@ -14,6 +14,7 @@ dev = torch.device("cuda:0")
 H, W = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (512, 512)
 impl = sys.argv[3] if len(sys.argv) > 3 else "row_f16x2"
 g = torch.Generator(device=dev).manual_seed(5)
+torch.manual_seed(0)
 x = torch.randn(1, 4, H, W, 4, device=dev, generator=g)
 stats = torch.stack([x.double().sum((2, 3, 4)), (x.double() ** 2).sum((2, 3, 4))], -1).contiguous()
 gam, bet, bias = torch.ones(16, device=dev), torch.zeros(16, device=dev), torch.zeros(16, device=dev)

@@ -19,6 +19,7 @@ lib = C.CDLL(L.LIB_PATH)
 buf = torch.zeros(4096, dtype=torch.int64, device=dev)
 lib.pbmc_debug_set_row_trace(C.c_void_p(buf.data_ptr()))
 g = torch.Generator(device=dev).manual_seed(5)
+torch.manual_seed(0)
 x = torch.randn(1, 4, H, W, 4, device=dev, generator=g)
 stats = torch.stack([x.double().sum((2, 3, 4)), (x.double() ** 2).sum((2, 3, 4))], -1).contiguous()
 gam, bet, bias = torch.ones(16, device=dev), torch.zeros(16, device=dev), torch.zeros(16, device=dev)
@@ -35,7 +36,7 @@ t = buf.cpu().numpy()
 t0 = t[0]
 rel = lambda i: int(t[i] - t0) if t[i] else None
 print("setup done", rel(1), " epilogue loop done", rel(3), " end", rel(2))
-NPG = 3
+NPG = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 for pg in range(NPG):
     print(f"P{pg}: role start {rel(4+pg)}  prologue done {rel(8+pg)}")
     k = 0
