@@ -28,6 +28,8 @@ bool conv_mux_one_wave(const pbmc_conv_desc& d);
 int conv_trunk_dispatch(const pbmc_trunk_desc& t, cudaStream_t st);  // conv_trunk.cu
 bool conv_trunk_supported(const pbmc_trunk_desc& t);
 extern thread_local int g_conv_pdl_next;  // conv_mux.cu: the next mux launch uses programmatic dependent launch
+int build_input_enqueue(const float* T, const float* xc, const float* yc, const float* ycc, const pbmc_member* members, float* inp,
+                        float* V, int B, int H, int W, void* zero, size_t zero_bytes, cudaStream_t st);  // pyramid.cu
 
 }  // namespace pbmc
 
@@ -276,7 +278,7 @@ extern "C" size_t pbmc_workspace_bytes(const pbmc_net* n, int B, int H, int W) {
 // Enqueue one surrogate forward.  `uv` points at the 2*B uint32 slots (uvmax of this step).
 static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, char* ws, const float* inp,
                                 const pbmc_member* members, float* u, float* v, float* p, uint32_t* uvmax, int B, int H,
-                                int W, cudaStream_t st);
+                                int W, cudaStream_t st, bool pre_zeroed = false);
 
 // The forward runs on the context's high-priority stream, forked from / joined to the caller's stream.
 static int surrogate_enqueue(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, char* ws, const float* inp,
@@ -291,9 +293,10 @@ static int surrogate_enqueue(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, ch
   return rc;
 }
 
+// pre_zeroed: the caller's previous kernel has already cleared the scratch region [P.stats, P.stats + P.stats_bytes)
 static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, char* ws, const float* inp,
                                 const pbmc_member* members, float* u, float* v, float* p, uint32_t* uvmax, int B, int H,
-                                int W, cudaStream_t st) {
+                                int W, cudaStream_t st, bool pre_zeroed) {
   const int L = P.L, R = P.R, CB = P.CB;
   // Programmatic dependent launch on the critical chain (PBMC_CHAIN_PDL overrides the mask; default 1 | 4):
   //   1  conv[2], conv[3]   on: nothing else runs then; the next conv's set-up overlaps the previous one's drain
@@ -306,8 +309,10 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
   auto S = [&](int slot) { return reinterpret_cast<double*>(ws + P.stat_off(slot, B)); };
   double* chan_sum = reinterpret_cast<double*>(ws + P.chan_sum);
   // zero all statistics accumulators (GroupNorm sums, zero-mean sums) in one memset
-  PBMC_CUDA(cudaMemsetAsync(ws + P.stats, 0, P.stats_bytes - (size_t)2 * B * sizeof(uint32_t), st));
-  if (uvmax) PBMC_CUDA(cudaMemsetAsync(uvmax, 0, (size_t)B * sizeof(uint32_t), st));
+  if (!pre_zeroed) {
+    PBMC_CUDA(cudaMemsetAsync(ws + P.stats, 0, P.stats_bytes - (size_t)2 * B * sizeof(uint32_t), st));
+    if (uvmax) PBMC_CUDA(cudaMemsetAsync(uvmax, 0, (size_t)B * sizeof(uint32_t), st));
+  }
 
   pbmc_conv_desc d;
   // conv[0]: FluidLayer(c_i -> c_h), :1317
@@ -530,22 +535,36 @@ extern "C" int pbmc_rollout(pbmc_ctx* ctx, const pbmc_net* net, const pbmc_membe
   if (!aligned16(workspace)) return PBMC_ERR_MISALIGNED;
   RC(check_device_ptr(workspace));
   RC(check_device_ptr(T_seq));
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t caller = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   uint32_t* uvmax = reinterpret_cast<uint32_t*>(ws + P.uvmax);
   const size_t field = (size_t)B * H * W;
-  for (int i = first_step; i < first_step + n_steps; ++i) {
-    const float* Tin = T_seq + (size_t)((i - 1) % nslots) * field;
-    float* Tout = T_seq + (size_t)(i % nslots) * field;
-    const bool last = (i == first_step + n_steps - 1);
-    RC(pbmc_build_input(Tin, xc, yc, ycc, members, reinterpret_cast<float*>(ws + P.inp), last ? V : nullptr, B, H, W, st));
-    RC(surrogate_enqueue(ctx, *net, P, ws, reinterpret_cast<float*>(ws + P.inp), members, u, v, p, uvmax, B, H, W, st));
-    if (!per_member_dt && B > 1) {
-      uvmax_batch_reduce_kernel<<<1, 32, 0, st>>>(uvmax, B);
-      PBMC_CHECK_LAUNCH("uvmax_batch_reduce_kernel");
+  // All steps run on the context's high-priority stream, forked from / joined to the caller's stream ONCE: inside the
+  // loop every link of the critical chain (input build -> conv[0] -> ... -> head -> stencil -> next input build) is a
+  // plain same-stream dependency, and the scratch of each forward is cleared by its input-build kernel.
+  cudaStream_t st = ctx->s[0];
+  PBMC_CUDA(cudaEventRecord(ctx->ev_in, caller));
+  PBMC_CUDA(cudaStreamWaitEvent(st, ctx->ev_in, 0));
+  auto steps = [&]() -> int {
+    for (int i = first_step; i < first_step + n_steps; ++i) {
+      const float* Tin = T_seq + (size_t)((i - 1) % nslots) * field;
+      float* Tout = T_seq + (size_t)(i % nslots) * field;
+      const bool last = (i == first_step + n_steps - 1);
+      RC(build_input_enqueue(Tin, xc, yc, ycc, members, reinterpret_cast<float*>(ws + P.inp), last ? V : nullptr, B, H, W, ws + P.stats,
+                             P.stats_bytes, st));
+      RC(surrogate_enqueue_on(ctx, *net, P, ws, reinterpret_cast<float*>(ws + P.inp), members, u, v, p, uvmax, B, H, W, st, true));
+      if (!per_member_dt && B > 1) {
+        uvmax_batch_reduce_kernel<<<1, 32, 0, st>>>(uvmax, B);
+        PBMC_CHECK_LAUNCH("uvmax_batch_reduce_kernel");
+      }
+      RC(pbmc_advect_diffuse(Tin, u, v, xcoef, ycoef, members, uvmax, per_member_dt ? 1 : 0, dx_min, cn_max, 0.0, Tout, nullptr,
+                             dt_seq ? dt_seq + (size_t)(i - 1) * B : nullptr, B, H, W, st));
     }
-    RC(pbmc_advect_diffuse(Tin, u, v, xcoef, ycoef, members, uvmax, per_member_dt ? 1 : 0, dx_min, cn_max, 0.0, Tout, nullptr,
-                           dt_seq ? dt_seq + (size_t)(i - 1) * B : nullptr, B, H, W, st));
-  }
-  return PBMC_OK;
+    return PBMC_OK;
+  };
+  const int rc = steps();
+  // join even on error so that a capture in progress is not left with a dangling fork
+  cudaEventRecord(ctx->ev_out, st);
+  cudaStreamWaitEvent(caller, ctx->ev_out, 0);
+  return rc;
 }

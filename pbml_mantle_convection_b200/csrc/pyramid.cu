@@ -60,11 +60,18 @@ __global__ void finalize_nchw_kernel(const pbmc_src S, float* __restrict__ dst, 
 // ---------------------------------------------------------------- A1: network input
 // TS.forward, pytorch_networks_convae.py:379-407.  log10(clip(exp(z),1e-8,1)) is evaluated as
 // clamp(z*log10(e), -8, 0): identical in exact arithmetic, and free of the exp->log10 round trip.
+// `zero` / `zero_words`: scratch of the forward that follows (statistics accumulators, grid-barrier counters, the CFL
+// maximum) cleared here, grid-stride, instead of by memset nodes in front of conv[0] -- two links less on the rollout's
+// critical chain.  NULL outside the rollout.
 __global__ void build_input_kernel(const float* __restrict__ T, const float* __restrict__ xc,
                                    const float* __restrict__ yc, const float* __restrict__ ycc,
                                    const pbmc_member* __restrict__ mem, float* __restrict__ inp, float* __restrict__ V,
-                                   size_t plane) {
+                                   size_t plane, uint32_t* __restrict__ zero, size_t zero_words) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (zero != nullptr) {
+    const size_t nthr = (size_t)gridDim.x * gridDim.y * blockDim.x;
+    for (size_t w = (size_t)blockIdx.y * gridDim.x * blockDim.x + i; w < zero_words; w += nthr) zero[w] = 0u;
+  }
   if (i >= plane) return;
   const int b = blockIdx.y;
   const pbmc_member m = mem[b];
@@ -275,16 +282,23 @@ extern "C" int pbmc_finalize_nchw(const pbmc_src* S, float* dst, int B, int C, i
   return PBMC_OK;
 }
 
-extern "C" int pbmc_build_input(const float* T, const float* xc, const float* yc, const float* ycc,
-                                const pbmc_member* members, float* inp, float* V, int B, int H, int W, void* stream) {
+namespace pbmc {
+int build_input_enqueue(const float* T, const float* xc, const float* yc, const float* ycc, const pbmc_member* members, float* inp,
+                        float* V, int B, int H, int W, void* zero, size_t zero_bytes, cudaStream_t st) {
   if (!T || !xc || !yc || !ycc || !members || !inp) return PBMC_ERR_NULL_POINTER;
   if (B <= 0 || H < 3 || W < 3) return PBMC_ERR_BAD_SHAPE;
-  if (!aligned16(inp)) return PBMC_ERR_MISALIGNED;
+  if (!aligned16(inp) || (zero_bytes & 3) != 0) return PBMC_ERR_MISALIGNED;
   const size_t plane = (size_t)H * W;
   dim3 grid((unsigned)((plane + 255) / 256), B);
-  build_input_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, xc, yc, ycc, members, inp, V, plane);
+  build_input_kernel<<<grid, 256, 0, st>>>(T, xc, yc, ycc, members, inp, V, plane, reinterpret_cast<uint32_t*>(zero), zero_bytes / 4);
   PBMC_CHECK_LAUNCH("build_input_kernel");
   return PBMC_OK;
+}
+}  // namespace pbmc
+
+extern "C" int pbmc_build_input(const float* T, const float* xc, const float* yc, const float* ycc,
+                                const pbmc_member* members, float* inp, float* V, int B, int H, int W, void* stream) {
+  return pbmc::build_input_enqueue(T, xc, yc, ycc, members, inp, V, B, H, W, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int pbmc_avgpool2(const pbmc_src* S, float* dst, int B, int H, int W, void* stream) {
