@@ -29,7 +29,8 @@ int conv_trunk_dispatch(const pbmc_trunk_desc& t, cudaStream_t st);  // conv_tru
 bool conv_trunk_supported(const pbmc_trunk_desc& t);
 extern thread_local int g_conv_pdl_next;  // conv_mux.cu: the next mux launch uses programmatic dependent launch
 int build_input_enqueue(const float* T, const float* xc, const float* yc, const float* ycc, const pbmc_member* members, float* inp,
-                        float* V, int B, int H, int W, void* zero, size_t zero_bytes, cudaStream_t st);  // pyramid.cu
+                        float* V, int B, int H, int W, void* zero, size_t zero_bytes, cudaStream_t st, bool pdl);  // pyramid.cu
+extern thread_local int g_stencil_pdl_next;  // stencil.cu: the next plain stencil launch uses programmatic dependent launch
 
 }  // namespace pbmc
 
@@ -301,10 +302,11 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
   // Programmatic dependent launch on the critical chain (PBMC_CHAIN_PDL overrides the mask; default 1 | 4):
   //   1  conv[2], conv[3]   on: nothing else runs then; the next conv's set-up overlaps the previous one's drain
   //   4  conv[1]            on  (0.2348 -> 0.2331 -> 0.2311 ms/step at 512^2 with 1, then 1 | 4)
-  //   8  head kernel        off: no measurable change
+  //   8  head kernel        on
+  //  16  conv[0]            on in a rollout (behind the input-build kernel, no memset node in between)
   //   2  level-0 trunk      off: 0.27 ms -- an early-resident CTA parked in griddepcontrol.wait takes an SM from
   //                              the other levels' streams
-  static const int chain_pdl = PBMC_DEV_KNOB("PBMC_CHAIN_PDL", 5);
+  static const int chain_pdl = PBMC_DEV_KNOB("PBMC_CHAIN_PDL", 5 | 8 | 16);
   auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto S = [&](int slot) { return reinterpret_cast<double*>(ws + P.stat_off(slot, B)); };
   double* chan_sum = reinterpret_cast<double*>(ws + P.chan_sum);
@@ -319,7 +321,12 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
   fill_conv(d, n, n.conv0, B, H, W, F(P.x0), S(0), nullptr, PBMC_ACT_NONE);
   d.nsrc = 1;
   d.src[0] = make_src(inp, P.CIB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
-  RC(conv_enqueue(d, st));
+  g_conv_pdl_next = pre_zeroed ? (chain_pdl & 16) : 0;  // rollout: directly behind the input-build kernel
+  {
+    const int rc0 = conv_enqueue(d, st);
+    g_conv_pdl_next = 0;
+    RC(rc0);
+  }
   PBMC_CUDA(cudaEventRecord(ctx->ev_fork[0], st));
 
   // pyramid levels (:1319-1327): level l runs on stream l (level 0 on the caller's stream)
@@ -545,20 +552,26 @@ extern "C" int pbmc_rollout(pbmc_ctx* ctx, const pbmc_net* net, const pbmc_membe
   cudaStream_t st = ctx->s[0];
   PBMC_CUDA(cudaEventRecord(ctx->ev_in, caller));
   PBMC_CUDA(cudaStreamWaitEvent(st, ctx->ev_in, 0));
+  static const int tail_pdl = PBMC_DEV_KNOB("PBMC_TAIL_PDL", 3);  // 1 stencil behind head, 2 input build behind stencil
   auto steps = [&]() -> int {
     for (int i = first_step; i < first_step + n_steps; ++i) {
       const float* Tin = T_seq + (size_t)((i - 1) % nslots) * field;
       float* Tout = T_seq + (size_t)(i % nslots) * field;
       const bool last = (i == first_step + n_steps - 1);
+      // programmatic dependent launch: behind the previous step's stencil (not for the call's first step: whatever
+      // precedes it in the stream is not ours)
       RC(build_input_enqueue(Tin, xc, yc, ycc, members, reinterpret_cast<float*>(ws + P.inp), last ? V : nullptr, B, H, W, ws + P.stats,
-                             P.stats_bytes, st));
+                             P.stats_bytes, st, (tail_pdl & 2) && i > first_step));
       RC(surrogate_enqueue_on(ctx, *net, P, ws, reinterpret_cast<float*>(ws + P.inp), members, u, v, p, uvmax, B, H, W, st, true));
       if (!per_member_dt && B > 1) {
         uvmax_batch_reduce_kernel<<<1, 32, 0, st>>>(uvmax, B);
         PBMC_CHECK_LAUNCH("uvmax_batch_reduce_kernel");
       }
-      RC(pbmc_advect_diffuse(Tin, u, v, xcoef, ycoef, members, uvmax, per_member_dt ? 1 : 0, dx_min, cn_max, 0.0, Tout, nullptr,
-                             dt_seq ? dt_seq + (size_t)(i - 1) * B : nullptr, B, H, W, st));
+      g_stencil_pdl_next = (tail_pdl & 1) && (per_member_dt || B == 1);  // directly behind the head kernel
+      const int rcs = pbmc_advect_diffuse(Tin, u, v, xcoef, ycoef, members, uvmax, per_member_dt ? 1 : 0, dx_min, cn_max, 0.0, Tout, nullptr,
+                                          dt_seq ? dt_seq + (size_t)(i - 1) * B : nullptr, B, H, W, st);
+      g_stencil_pdl_next = 0;
+      RC(rcs);
     }
     return PBMC_OK;
   };

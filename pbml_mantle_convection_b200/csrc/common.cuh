@@ -42,6 +42,25 @@ void set_last_cuda_error(cudaError_t e, const char* where);
 #define PBMC_DEV_KNOB(name, dflt) (dflt)
 #endif
 
+// Kernel launch with optional programmatic stream serialization: the kernel may become resident while its predecessor in
+// the stream drains and must execute griddepcontrol.wait before it touches anything the predecessor (or, transitively,
+// anything earlier) wrote or still reads.  Without the attribute griddepcontrol.* are no-ops.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                           Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

@@ -67,6 +67,9 @@ __global__ void build_input_kernel(const float* __restrict__ T, const float* __r
                                    const float* __restrict__ yc, const float* __restrict__ ycc,
                                    const pbmc_member* __restrict__ mem, float* __restrict__ inp, float* __restrict__ V,
                                    size_t plane, uint32_t* __restrict__ zero, size_t zero_words) {
+  // no-ops unless launched with programmatic stream serialization (the rollout does, behind the stencil)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (zero != nullptr) {
     const size_t nthr = (size_t)gridDim.x * gridDim.y * blockDim.x;
@@ -284,13 +287,14 @@ extern "C" int pbmc_finalize_nchw(const pbmc_src* S, float* dst, int B, int C, i
 
 namespace pbmc {
 int build_input_enqueue(const float* T, const float* xc, const float* yc, const float* ycc, const pbmc_member* members, float* inp,
-                        float* V, int B, int H, int W, void* zero, size_t zero_bytes, cudaStream_t st) {
+                        float* V, int B, int H, int W, void* zero, size_t zero_bytes, cudaStream_t st, bool pdl) {
   if (!T || !xc || !yc || !ycc || !members || !inp) return PBMC_ERR_NULL_POINTER;
   if (B <= 0 || H < 3 || W < 3) return PBMC_ERR_BAD_SHAPE;
   if (!aligned16(inp) || (zero_bytes & 3) != 0) return PBMC_ERR_MISALIGNED;
   const size_t plane = (size_t)H * W;
   dim3 grid((unsigned)((plane + 255) / 256), B);
-  build_input_kernel<<<grid, 256, 0, st>>>(T, xc, yc, ycc, members, inp, V, plane, reinterpret_cast<uint32_t*>(zero), zero_bytes / 4);
+  PBMC_CUDA(launch_maybe_pdl(build_input_kernel, grid, dim3(256), 0, st, pdl, T, xc, yc, ycc, members, inp, V, plane,
+                             reinterpret_cast<uint32_t*>(zero), zero_bytes / 4));
   PBMC_CHECK_LAUNCH("build_input_kernel");
   return PBMC_OK;
 }
@@ -298,7 +302,7 @@ int build_input_enqueue(const float* T, const float* xc, const float* yc, const 
 
 extern "C" int pbmc_build_input(const float* T, const float* xc, const float* yc, const float* ycc,
                                 const pbmc_member* members, float* inp, float* V, int B, int H, int W, void* stream) {
-  return pbmc::build_input_enqueue(T, xc, yc, ycc, members, inp, V, B, H, W, nullptr, 0, (cudaStream_t)stream);
+  return pbmc::build_input_enqueue(T, xc, yc, ycc, members, inp, V, B, H, W, nullptr, 0, (cudaStream_t)stream, false);
 }
 
 extern "C" int pbmc_avgpool2(const pbmc_src* S, float* dst, int B, int H, int W, void* stream) {

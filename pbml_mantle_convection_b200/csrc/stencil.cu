@@ -262,6 +262,9 @@ __global__ void __launch_bounds__(ST_BX* ST_BY) stencil_kernel(const StencilPara
 //          step s + 1's value, i.e. after every rank has finished step s and consumed the tags of step s.
 template <bool SYNC>
 __global__ void __launch_bounds__(128, 6) stencil_march_kernel(const StencilParams p, int rpw, const SlabSyncArgs sa) {
+  // no-ops unless launched with programmatic stream serialization (the rollout does, behind the head kernel)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int H = p.H, W = p.W, b = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = (blockIdx.x * 32 + lane) * 4;
@@ -553,6 +556,8 @@ extern "C" int pbmc_stencil_coefs(const double* coord, int n, double wall_lo, do
   return PBMC_OK;
 }
 
+thread_local int g_stencil_pdl_next = 0;  // set by api.cu (pbmc_rollout) right before the launch it applies to
+
 static int advect_diffuse_launch(const float* T, const float* u, const float* v, const float* x, const float* y,
                                  const pbmc_member* members, const uint32_t* uvmax_in, int member_stride, double dx_min,
                                  double cn_max, double dt_fixed, float* T_out, uint32_t* uvmax_out, double* dt_out, int B, int H,
@@ -596,10 +601,13 @@ static int advect_diffuse_launch(const float* T, const float* u, const float* v,
     }
     dim3 grid(strips, cdiv(H, 4 * rpw), B);
     if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
-    if (sync != nullptr)
+    if (sync != nullptr) {
       stencil_march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(p, rpw, *sync);
-    else
-      stencil_march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(p, rpw, SlabSyncArgs{});
+    } else {
+      const bool pdl = g_stencil_pdl_next != 0;
+      g_stencil_pdl_next = 0;
+      PBMC_CUDA(launch_maybe_pdl(stencil_march_kernel<false>, grid, dim3(128), 0, (cudaStream_t)stream, pdl, p, rpw, SlabSyncArgs{}));
+    }
     PBMC_CHECK_LAUNCH("stencil_march_kernel");
     return PBMC_OK;
   }
