@@ -556,7 +556,9 @@ extern "C" int pbmc_stencil_coefs(const double* coord, int n, double wall_lo, do
   return PBMC_OK;
 }
 
+namespace pbmc {
 thread_local int g_stencil_pdl_next = 0;  // set by api.cu (pbmc_rollout) right before the launch it applies to
+}
 
 static int advect_diffuse_launch(const float* T, const float* u, const float* v, const float* x, const float* y,
                                  const pbmc_member* members, const uint32_t* uvmax_in, int member_stride, double dx_min,
