@@ -27,6 +27,7 @@ bool conv_mux_supported(const pbmc_conv_desc& d);
 bool conv_mux_one_wave(const pbmc_conv_desc& d);
 int conv_trunk_dispatch(const pbmc_trunk_desc& t, cudaStream_t st);  // conv_trunk.cu
 bool conv_trunk_supported(const pbmc_trunk_desc& t);
+double conv_trunk_layer_cost(int rpc);
 extern thread_local int g_conv_pdl_next;  // conv_mux.cu: the next mux launch uses programmatic dependent launch
 int build_input_enqueue(const float* T, const float* xc, const float* yc, const float* ycc, const pbmc_member* members, float* inp,
                         float* V, int B, int H, int W, void* zero, size_t zero_bytes, cudaStream_t st, bool pdl);  // pyramid.cu
@@ -367,6 +368,69 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
   // 1.445 ms) -- conv[1] is paced by its MMA issue loop, not by its producers, and the operand-image writer of the
   // bicubic kernel stores 2 x 8 B per thread.  pbmc_net.flags & PBMC_NET_UP_STAGED turns it on (results are bit-identical).
   up_staged = up_staged && (n.flags & PBMC_NET_UP_STAGED) != 0;
+  // Persistent trunk kernels (csrc/conv_trunk.cu: the R layers of a level in one launch, grid barrier between layers)
+  // need EVERY CTA of EVERY level resident at once: taken only when all levels have a budget and the budgets fit 148 SMs.
+  bool trunk_persistent = (n.flags & PBMC_NET_TRUNK_PER_LAYER) == 0 && CB == 4 && n.ksize == 3;
+  // Their budgets are balanced on finish times, not on row counts: a level's kernel takes R x (the kernel's own per-layer
+  // cost model, which moves in steps of a staging round of 5 rows), the coarse levels start after their pooling chain and
+  // must still be up-sampled before conv[1] can begin.  Smallest common finish time whose CTA counts fit 148 SMs
+  // (512^2: 100 / 32 / 8 / 4 / 2 / 2 instead of the row-proportional 108 / 26 / 6 / 3 / 2 / 2: 0.2135 -> 0.2065 ms per step,
+  // the level-0 kernel keeps its five rounds and the up-sampling of the others no longer trails it).
+  if (trunk_persistent && L > 1) {
+    struct Opt { int ctas; double t; };
+    Opt opts[PBMC_MAX_LEVELS][32];
+    int nopt[PBMC_MAX_LEVELS];
+    double cand[PBMC_MAX_LEVELS * 32];
+    int ncand = 0;
+    bool ok = true;
+    for (int l = 0; l < L && ok; ++l) {
+      const int units = B * ((P.Wl[l] + 127) / 128), Hl = P.Hl[l];
+      const double start = 6000.0 * l, tail = l ? 2000.0 + 0.06 * (double)B * H * W : 0.0;
+      nopt[l] = 0;
+      double last = 1e30;
+      const int rpc_min = Hl < 8 ? Hl : 8;  // no more than one CTA per 8 rows (2 of 10 staged rows are halo)
+      for (int rpc = Hl < 22 ? Hl : 22; rpc >= rpc_min && nopt[l] < 32; --rpc) {  // fewest CTAs first
+        const double c = conv_trunk_layer_cost(rpc);
+        const long ctas = (long)units * ((Hl + rpc - 1) / rpc);
+        if (c <= 0.0 || ctas > 148) continue;
+        const double t = start + R * c + tail;
+        if (t < last - 1e-9) { opts[l][nopt[l]++] = Opt{(int)ctas, t}; cand[ncand++] = t; last = t; }
+      }
+      ok = nopt[l] > 0;
+    }
+    if (ok) {
+      double best_t = 1e30;
+      int best_b[PBMC_MAX_LEVELS];
+      for (int k = 0; k < ncand; ++k) {
+        if (cand[k] >= best_t) continue;
+        int sum = 0, bb[PBMC_MAX_LEVELS];
+        bool feas = true;
+        for (int l = 0; l < L && feas; ++l) {
+          int pick = -1;
+          for (int o = 0; o < nopt[l]; ++o)
+            if (opts[l][o].t <= cand[k] + 1e-9) { pick = opts[l][o].ctas; break; }  // options are ordered by CTA count
+          feas = pick > 0;
+          bb[l] = pick;
+          sum += pick;
+        }
+        if (feas && sum <= 148) { best_t = cand[k]; for (int l = 0; l < L; ++l) best_b[l] = bb[l]; }
+      }
+      if (best_t < 1e30) {
+        // CTAs left over go to the levels in order (level 0 heads the chain that conv[1] waits on): each takes its fastest
+        // option that still fits
+        int sum = 0;
+        for (int l = 0; l < L; ++l) sum += best_b[l];
+        for (int l = 0; l < L; ++l)
+          for (int o = nopt[l] - 1; o >= 0; --o)
+            if (opts[l][o].ctas > best_b[l] && sum - best_b[l] + opts[l][o].ctas <= 148) {
+              sum += opts[l][o].ctas - best_b[l];
+              best_b[l] = opts[l][o].ctas;
+              break;
+            }
+        for (int l = 0; l < L; ++l) cta_budget[l] = best_b[l];
+      }
+    }
+  }
 #ifdef PBMC_DEV_BUILD
   {
     // developer knob: PBMC_BUDGETS="116,24,6,3,2,1" overrides the per-level CTA budgets
@@ -381,9 +445,6 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
     }
   }
 #endif
-  // Persistent trunk kernels (csrc/conv_trunk.cu: the R layers of a level in one launch, grid barrier between layers)
-  // need EVERY CTA of EVERY level resident at once: taken only when all levels have a budget and the budgets fit 148 SMs.
-  bool trunk_persistent = (n.flags & PBMC_NET_TRUNK_PER_LAYER) == 0 && CB == 4 && n.ksize == 3;
   {
     int total = 0;
     for (int l = 0; l < L && trunk_persistent; ++l) {

@@ -500,14 +500,20 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
 
 // Output rows per CTA: the whole grid must be resident at once (ctas <= avail); among those, minimise
 // fixed cost + staging rounds + epilogue rounds (clocks from tools/muxtrace.py, as conv_mux.cu).
+// clocks of one layer for a CTA that owns `rpc` output rows (0: more rows than shared memory holds)
+double conv_trunk_layer_cost(int rpc) {
+  if (rpc < 1 || rpc > CT_MAXR - 2) return 0.0;
+  const int rounds1 = cdiv(rpc + 2, CT_SETS), rounds2 = cdiv(rpc, CT_SETS);
+  return 1500.0 + rounds1 * 2800.0 + rounds2 * 1000.0;
+}
+
 static int choose_rpc_trunk(int units, int H, int avail) {
   int best = 0;
   double best_cost = 1e30;
   for (int r = 1; r <= CT_MAXR - 2 && r <= H; ++r) {
     const long ctas = (long)units * cdiv(H, r);
     if (ctas > avail) continue;
-    const int rounds1 = cdiv(r + 2, CT_SETS), rounds2 = cdiv(r, CT_SETS);
-    const double cost = 1500.0 + rounds1 * 2800.0 + rounds2 * 1000.0;
+    const double cost = conv_trunk_layer_cost(r);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = r; }
   }
   return best;
