@@ -1047,7 +1047,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     // copies run up to CR_NT stages ahead of the MMAs.  Replicate padding only (checked on the host): the padded
     // columns are part of the image, a padded row is the clamped row.
     const uint32_t smask = *stg_mask;
-    if (lane == 0 && p.raw_loader && PARTS == 2) {
+    if (lane < 4 && p.raw_loader && PARTS == 2) {
       // raw fp32 rows for the producers: stage k = (row ri, group g) lands in slot k % CR_NT of the second ring, one copy per
       // 4-channel plane covering the in-image part of positions 0 .. PWS-1 (input columns x0-P ..): a padded position is read
       // by the producers from the position its padding rule points at, a zero-padded row is not copied at all
@@ -1059,18 +1059,21 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         const uint32_t s = (uint32_t)k & (CR_NT - 1);
         if (k >= CR_NT) mbar_wait_parked(t_empty(s), (((uint32_t)k / CR_NT) & 1u) ^ 1u);
         const uint32_t bar = t_full(s);
+        // lane j copies channel plane j; lane 0 announces the bytes (a complete_tx that overtakes it only drives the
+        // transaction count negative for a moment: the phase cannot complete before lane 0's arrival)
         if (sy < 0) {
-          mbar_arrive(bar);  // nothing to copy: the producers stage zeros
+          if (lane == 0) mbar_arrive(bar);  // nothing to copy: the producers stage zeros
         } else {
           const RowGroup gi = gtab[g];
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(gi.nb * ncols * 16)) : "memory");
-          const float* src = gi.base + ((size_t)sy * W + (size_t)(x0 - P + i_lo)) * 4;
-          const uint32_t dst = smem_u32(As) + (uint32_t)(NSTAGE + s) * (uint32_t)G::STAGE_BYTES + (uint32_t)i_lo * 16u;
-          for (int j = 0; j < gi.nb; ++j)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             dst + (uint32_t)j * RAWP),
-                         "l"(src + (size_t)j * plane_px * 4), "r"((uint32_t)(ncols * 16)), "r"(bar)
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(gi.nb * ncols * 16)) : "memory");
+          if (lane < gi.nb) {
+            const float* src = gi.base + ((size_t)lane * plane_px + (size_t)sy * W + (size_t)(x0 - P + i_lo)) * 4;
+            const uint32_t dst = smem_u32(As) + (uint32_t)(NSTAGE + s) * (uint32_t)G::STAGE_BYTES + (uint32_t)lane * RAWP + (uint32_t)i_lo * 16u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                         "r"((uint32_t)(ncols * 16)), "r"(bar)
                          : "memory");
+          }
         }
         if (++g == NG) {
           g = 0;
