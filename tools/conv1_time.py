@@ -21,7 +21,10 @@ gam, bet, bias = torch.ones(16, device=dev), torch.zeros(16, device=dev), torch.
 ch = [16] * 6 + [7]
 w = torch.randn(16, sum(ch), 3, 3, device=dev, generator=g) / 30
 wpk, wrow = ops.pack_conv_weight(w, ch), ops.pack_conv_weight_row(w, ch)
-srcs = [ops.Source(torch.randn_like(x)) for _ in range(5)] + [ops.Source(x, L.XFORM_GN_GELU, stats, gam, bet)] + \
+alias = os.environ.get("CONV1_ALIAS", "0") == "1"   # all five up-sampled sources are ONE tensor: 42 MB of inputs, L2 resident
+noflush = os.environ.get("CONV1_NOFLUSH", "0") == "1"
+up0 = torch.randn_like(x)
+srcs = [ops.Source(up0 if alias else torch.randn_like(x)) for _ in range(5)] + [ops.Source(x, L.XFORM_GN_GELU, stats, gam, bet)] + \
        [ops.Source(torch.randn(1, 2, H, W, 4, device=dev, generator=g))]
 o, st = torch.empty_like(x), torch.zeros_like(stats)
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -31,7 +34,8 @@ for _ in range(5):
 torch.cuda.synchronize()
 ts = []
 for _ in range(30):
-    flush.zero_()
+    if not noflush:
+        flush.zero_()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     f()
@@ -40,4 +44,4 @@ for _ in range(30):
     ts.append(a.elapsed_time(b) * 1e3)
 ts.sort()
 print(f"conv[1] {H}x{W} {impl} flags={os.environ.get('PBMC_ROW_DBG_FLAGS', '0')}: median {ts[len(ts) // 2]:.1f} us, best {ts[0]:.1f} us "
-      f"(L2 flushed), checksum {float(o.double().sum()):.6e}", flush=True)
+      f"({'no flush' if noflush else 'L2 flushed'}{', aliased sources' if alias else ''}, raw={os.environ.get('PBMC_ROW_RAW', '1')}), checksum {float(o.double().sum()):.6e}", flush=True)
