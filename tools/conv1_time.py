@@ -36,6 +36,8 @@ ts = []
 for _ in range(30):
     if not noflush:
         flush.zero_()
+    else:
+        torch.cuda._sleep(400000)  # keeps the GPU busy while the host enqueues the launch (no host gap between the events)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     f()
