@@ -22,6 +22,12 @@
 // Warp roles:  epilogue sets of 4 warps (output rows dealt round-robin; TMEM lane quarter = warp & 3),
 // then the producers (NPG groups of 128 threads, one thread per position plus the k-1 halo positions,
 // round-robin over stages, loads two stages ahead), last warp = MMA issuer (one elected lane) + TMEM allocator.
+// Tried and withdrawn for the several-groups variant (round 2; tools/conv1_time.py, tools/exp_conv1_mem.sh): raw fp32 rows
+// streamed by cp.async.bulk into a second shared-memory ring so that the producers neither compute addresses nor hold
+// prefetch registers.  Bit-identical, and no faster: 66.6 us with one copying lane, 58.5 us with one lane per channel plane,
+// 59.4 us with a 12-stage ring, against 58.3 us for the register-prefetch producers -- half of the producers' time then
+// went into waiting for their row (ncu source view), with ALL inputs resident in L2 as well (aliased sources, no flush:
+// 60.4 us), so it is the bulk-copy path's rate for 2 KB copies (about four per 800 clk per SM) that paces it, not DRAM.
 // Pipelines: a_full/a_empty (producers <-> MMA, NSTAGE smem stages; one stage = one input row of one
 // 16-channel group), d_full/d_empty (MMA <-> epilogue, ND accumulators; D_r is released by the k output
 // rows that read it).
@@ -47,12 +53,7 @@ constexpr int CR_TMA_WARP = CR_MMA_WARP + 1;  // one lane bulk-copies the stages
 constexpr int CR_THREADS = (CR_TMA_WARP + 1) * 32;
 constexpr int CR_NT = 8;                                // stages of the bulk-copy ring (power of two)
 constexpr int CR_MAXG = 24;
-constexpr int CR_SMEM_HDR = 2176 + 256;                 // ... + the raw-row ring's barriers (2 x CR_RAW_NT)
-// raw-row mode (ConvRowParams::raw_loader): 6 operand stages between producers and MMA, 12 raw stages between the copying
-// lanes and the producers -- the raw ring is what covers the memory latency (8.3 KB per stage, ~3 k clk: with 8 raw
-// stages half of the producers' time was spent waiting for their row to land, ncu source view)
-constexpr int CR_RAW_NA = 6;
-constexpr int CR_RAW_NT = 12;
+constexpr int CR_SMEM_HDR = 2176;
 
 struct ConvRowParams {
   pbmc_src src[PBMC_MAX_SRC];
@@ -63,7 +64,6 @@ struct ConvRowParams {
   int rpc;      // output rows per CTA
   int max_ctas; // CTA budget (0 = whole GPU)
   int has_staged;  // some source is an operand image: the bulk-copy ring is allocated
-  int raw_loader;  // the bulk-copy ring carries RAW fp32 rows for the producers (several-groups variant, see the producer role)
   const void* wpk;  // [group][dx][part][2 K-chunks][N = k*16 rows (dy, c_out)][8 c_in] 16-bit
   const float* bias;
   float* out;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
   uint32_t* stg_mask = reinterpret_cast<uint32_t*>(smem + 1152 + 512 + 64 + 4 * (CR_MAXG + 1));  // bit g: group g is an operand image
   unsigned char* Bs = smem + CR_SMEM_HDR;
   unsigned char* As = Bs + (size_t)p.ngroups * G::B_GROUP;
-  float* xf_a = reinterpret_cast<float*>(As + (size_t)(p.raw_loader ? CR_RAW_NA + CR_RAW_NT : NSTAGE + (p.has_staged ? CR_NT : 0)) * G::STAGE_BYTES);
+  float* xf_a = reinterpret_cast<float*>(As + (size_t)(NSTAGE + (p.has_staged ? CR_NT : 0)) * G::STAGE_BYTES);
   float* xf_b = xf_a + p.cin_ch;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -183,8 +183,6 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
   // kind of waiter that sees all of its phases in order (a parity wait is unsound for a waiter that skips phases).
   auto t_full = [&](uint32_t s) { return bar0 + (uint32_t)(2 * NSTAGE + 2 * ND + s) * 8u; };
   auto t_empty = [&](uint32_t s) { return bar0 + (uint32_t)(2 * NSTAGE + 2 * ND + CR_NT + s) * 8u; };
-  auto r_full = [&](uint32_t s) { return bar0 + 2176u + s * 8u; };                          // raw-row ring: copying lanes -> producers
-  auto r_empty = [&](uint32_t s) { return bar0 + 2176u + (uint32_t)(CR_RAW_NT + s) * 8u; };  // producers -> copying lanes
 
   // ---- one-time setup
   if (tid == 0) {
@@ -200,10 +198,6 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     for (int s = 0; s < CR_NT; ++s) {
       mbar_init(t_full(s), 1);   // arrive.expect_tx of the copying lane (+ the bytes of the four bulk copies)
       mbar_init(t_empty(s), 1);  // tcgen05.commit
-    }
-    for (int s = 0; s < CR_RAW_NT; ++s) {
-      mbar_init(r_full(s), 1);   // arrive.expect_tx of copying lane 0 (+ the bytes of the plane copies)
-      mbar_init(r_empty(s), 4);  // the 4 warps of the producer group that read the row
     }
     fence_mbar_init();
     int g = 0, c0 = 0;
@@ -725,91 +719,6 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         const uint32_t as_addr = smem_u32(As) + (uint32_t)i * 16u;
         const uint32_t xfa0 = smem_u32(xf_a), xfb0 = smem_u32(xf_b);
         const size_t rstride = (size_t)W * 4;
-        if (PARTS == 2 && p.raw_loader) {
-          // ---- raw rows by TMA: the copying lane (last warp) streams every stage's fp32 row -- 4 channel planes x 130
-          // positions -- into the second ring, up to CR_NT stages ahead; a producer thread reads its own pixel back from
-          // shared memory, transforms, splits and writes the operand image.  No global load, no address arithmetic and no
-          // prefetch registers here: the depth of the prefetch is the ring's, not the register file's (with register
-          // prefetch two stages deep, 27 % of the producers' time was the first use of loaded data, ncu source view).
-          constexpr uint32_t RAWP = PLANE * 16;  // plane stride inside a raw slot (4 planes = one stage slot)
-          const uint32_t raw_pos = (uint32_t)((sx < 0 ? 0 : sx) - (x0 - P)) * 16u;
-          const uint32_t raw_hpos = (uint32_t)(hch >> 2) * RAWP + (uint32_t)((h_on ? hsx[0] : x0) - (x0 - P)) * 16u + (uint32_t)(hch & 3) * 4u;
-          auto lds4 = [](uint32_t addr) {
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-            return v;
-          };
-          auto sts = [](uint32_t addr, uint4 q) {
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
-          };
-          static_assert(CR_NPG <= CR_RAW_NA && CR_NPG <= CR_RAW_NT, "ring positions advance by one wrap at most");
-          int ri = 0, g = pg;
-          while (g >= NG) { g -= NG; ++ri; }
-          uint32_t ts = (uint32_t)pg, tpar = 0u;    // raw ring: slot k % CR_RAW_NT, phase (k / CR_RAW_NT) & 1
-          uint32_t slot = (uint32_t)pg, apar = 0u;  // operand ring: slot k % CR_RAW_NA, phase (k / CR_RAW_NA) & 1
-          for (int k = pg; k < total; k += CR_NPG) {
-            const RowGroup gi = gtab[g];
-            const bool row_ok = pad_index(y0 - P + ri, H, p.pad_mode) >= 0;
-            const uint32_t rbase = smem_u32(As) + (uint32_t)(CR_RAW_NA + ts) * (uint32_t)G::STAGE_BYTES;
-            mbar_wait_parked(r_full(ts), tpar);
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 q0 = z, q1 = z, q2 = z, q3 = z;
-            float hv = 0.f;
-            if (row_ok) {
-              if (col_ok) {
-                q0 = lds4(rbase + raw_pos);
-                if (gi.nb > 1) q1 = lds4(rbase + RAWP + raw_pos);
-                if (gi.nb > 2) q2 = lds4(rbase + 2 * RAWP + raw_pos);
-                if (gi.nb > 3) q3 = lds4(rbase + 3 * RAWP + raw_pos);
-              }
-              if (h_on && (hch >> 2) < gi.nb) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hv) : "r"(rbase + raw_hpos) : "memory");
-            }
-            float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-            __syncwarp();
-            if (lane == 0) mbar_arrive(r_empty(ts));  // this warp has its pixels: the slot may be refilled (4 arrivals)
-            if (gi.xform == PBMC_XFORM_GN_GELU && row_ok) {
-              if (col_ok) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  if (j < gi.nb) {
-                    const float4 a = lds4(xfa0 + (uint32_t)(gi.chan0 + 4 * j) * 4u), bb = lds4(xfb0 + (uint32_t)(gi.chan0 + 4 * j) * 4u);
-                    v[4 * j + 0] = fmaf(v[4 * j + 0], a.x, bb.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, bb.y);
-                    v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, bb.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, bb.w);
-                    gelu_erf2(v[4 * j + 0], v[4 * j + 1]);
-                    gelu_erf2(v[4 * j + 2], v[4 * j + 3]);
-                  }
-                }
-              }
-              if (h_on && (hch >> 2) < gi.nb) hv = gelu_erf(fmaf(hv, xf_a[gi.chan0 + hch], xf_b[gi.chan0 + hch]));
-            }
-            const uint32_t sa = as_addr + slot * (uint32_t)G::STAGE_BYTES;
-            if (k >= CR_RAW_NA) mbar_wait_parked(a_empty(slot), apar ^ 1u);  // first pass: ring is free
-            uint4 h0, l0, h1, l1;
-            split_f16(v, h0, l0);
-            split_f16(v + 8, h1, l1);
-            sts(sa, h0);
-            sts(sa + PLANE * 16, h1);
-            sts(sa + 2 * PLANE * 16, l0);
-            sts(sa + 3 * PLANE * 16, l1);
-            if (wq == 0 && he < KS - 1) {
-              const uint32_t ha = smem_u32(As) + slot * (uint32_t)G::STAGE_BYTES + h_off;
-              const __half hh = __float2half_rn(hv);
-              const __half hl = __float2half_rn(hv - __half2float(hh));
-              asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha), "h"(__half_as_ushort(hh)) : "memory");
-              asm volatile("st.shared.b16 [%0], %1;" ::"r"(ha + (uint32_t)G::PART_BYTES), "h"(__half_as_ushort(hl)) : "memory");
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full(slot));
-            g += CR_NPG;
-            while (g >= NG) { g -= NG; ++ri; }
-            ts += CR_NPG;
-            if (ts >= (uint32_t)CR_RAW_NT) { ts -= CR_RAW_NT; tpar ^= 1u; }
-            slot += CR_NPG;
-            if (slot >= (uint32_t)CR_RAW_NA) { slot -= CR_RAW_NA; apar ^= 1u; }
-          }
-          goto producer_done;
-        }
         struct GBuf {
           float4 v0, v1, v2, v3;
           float h;
@@ -970,20 +879,18 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     };
     if (smask == 0u) {
       // no operand-image group: the stage number is the ring position (this loop is the pace-maker of every plain
-      // conv; the general one below costs ~10 % more per stage); in raw-row mode the operand ring has CR_RAW_NA stages
-      const uint32_t na = p.raw_loader ? (uint32_t)CR_RAW_NA : (uint32_t)NSTAGE;
-      uint32_t ds = 0, d_par = 0, slot = 0u, spar = 0u;
+      // conv; the general one below costs ~10 % more per stage)
+      uint32_t ds = 0, d_par = 0;
       int st = 0;
       bool ready = total > 0 && mbar_test(a_full(0), 0u);
       for (int ri = 0; ri < nin; ++ri) {
         if (ri >= ND) mbar_wait(d_empty(ds), d_par ^ 1u);  // first ND rows: the ring is free
         const uint32_t dcol = tmem_base + ds * (uint32_t)DN;
         for (int g = 0; g < NG; ++g, ++st) {
-          if (!ready) mbar_wait(a_full(slot), spar);
+          const uint32_t slot = (uint32_t)st & (NSTAGE - 1);
+          if (!ready) mbar_wait(a_full(slot), ((uint32_t)st / NSTAGE) & 1u);
           tc_fence_after();
-          uint32_t nslot = slot + 1u, npar = spar;
-          if (nslot == na) { nslot = 0u; npar ^= 1u; }
-          ready = (st + 1 < total) && mbar_test(a_full(nslot), npar);
+          ready = (st + 1 < total) && mbar_test(a_full((uint32_t)(st + 1) & (NSTAGE - 1)), ((uint32_t)(st + 1) / NSTAGE) & 1u);
           if (leader) {
             CR_TR(1400 + 2 * st);
             const uint64_t a_s = a_desc0 + (uint64_t)(slot * (uint32_t)(G::STAGE_BYTES >> 4));
@@ -1008,8 +915,6 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
             if (g == NG - 1) umma_commit(d_full(ds));  // D_ri complete
             CR_TR(1401 + 2 * st);
           }
-          slot = nslot;
-          spar = npar;
         }
         if (++ds == (uint32_t)ND) { ds = 0; d_par ^= 1u; }
       }
@@ -1067,42 +972,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     // copies run up to CR_NT stages ahead of the MMAs.  Replicate padding only (checked on the host): the padded
     // columns are part of the image, a padded row is the clamped row.
     const uint32_t smask = *stg_mask;
-    if (lane < 4 && p.raw_loader && PARTS == 2) {
-      // raw fp32 rows for the producers: stage k = (row ri, group g) lands in slot k % CR_NT of the second ring, one copy per
-      // 4-channel plane covering the in-image part of positions 0 .. PWS-1 (input columns x0-P ..): a padded position is read
-      // by the producers from the position its padding rule points at, a zero-padded row is not copied at all
-      constexpr uint32_t RAWP = PLANE * 16;
-      const int i_lo = x0 == 0 ? P : 0, i_hi = min(G::PWS - 1, W - 1 - (x0 - P)), ncols = i_hi - i_lo + 1;
-      int ri = 0, g = 0;
-      int sy = pad_index(y0 - P, H, p.pad_mode);
-      uint32_t s = 0u, par = 0u;
-      for (int k = 0; k < total; ++k) {
-        if (k >= CR_RAW_NT) mbar_wait_parked(r_empty(s), par ^ 1u);
-        const uint32_t bar = r_full(s);
-        // lane j copies channel plane j; lane 0 announces the bytes (a complete_tx that overtakes it only drives the
-        // transaction count negative for a moment: the phase cannot complete before lane 0's arrival)
-        if (sy < 0) {
-          if (lane == 0) mbar_arrive(bar);  // nothing to copy: the producers stage zeros
-        } else {
-          const RowGroup gi = gtab[g];
-          if (lane == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(gi.nb * ncols * 16)) : "memory");
-          if (lane < gi.nb) {
-            const float* src = gi.base + ((size_t)lane * plane_px + (size_t)sy * W + (size_t)(x0 - P + i_lo)) * 4;
-            const uint32_t dst = smem_u32(As) + (uint32_t)(CR_RAW_NA + s) * (uint32_t)G::STAGE_BYTES + (uint32_t)lane * RAWP + (uint32_t)i_lo * 16u;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                         "r"((uint32_t)(ncols * 16)), "r"(bar)
-                         : "memory");
-          }
-        }
-        if (++g == NG) {
-          g = 0;
-          ++ri;
-          sy = pad_index(y0 - P + ri, H, p.pad_mode);
-        }
-        if (++s == (uint32_t)CR_RAW_NT) { s = 0u; par ^= 1u; }
-      }
-    } else if (lane == 0 && smask != 0u) {
+    if (lane == 0 && smask != 0u) {
       constexpr uint32_t ROW_BYTES = (uint32_t)G::PWS * 16u;
       const size_t wp16 = (size_t)((W + 127) / 128 * 128 + 2) * 16;  // bytes of one plane row of an operand image
       uint32_t tk = 0;
@@ -1167,8 +1037,8 @@ static int choose_rpc(int units, int H, int ks, int max_ctas) {
 template <int KS, int PARTS, int NPG>
 static int launch_row_npg(ConvRowParams& p, cudaStream_t st) {
   using G = RowGeom<KS, PARTS>;
-  const size_t smem = CR_SMEM_HDR + (size_t)p.ngroups * G::B_GROUP +
-                      (size_t)(p.raw_loader ? CR_RAW_NA + CR_RAW_NT : G::NSTAGE + (p.has_staged ? CR_NT : 0)) * G::STAGE_BYTES + (size_t)p.cin_ch * 8;
+  const size_t smem = CR_SMEM_HDR + (size_t)p.ngroups * G::B_GROUP + (size_t)(G::NSTAGE + (p.has_staged ? CR_NT : 0)) * G::STAGE_BYTES +
+                      (size_t)p.cin_ch * 8;
   if (smem > 227 * 1024) return PBMC_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1247,17 +1117,6 @@ int conv_row_dispatch(const pbmc_conv_desc& d, cudaStream_t st) {
   p.max_ctas = d.max_ctas;
   p.has_staged = 0;
   for (int s = 0; s < d.nsrc; ++s) p.has_staged |= d.src[s].layout == PBMC_LAYOUT_STAGED16;
-  // several K groups per row, 3x3, fp16 hi|lo, plain / GN+GELU blocked sources: raw rows arrive by TMA (if the ring fits)
-  p.raw_loader = 0;
-  if (!p.has_staged && p.ngroups >= 3 && d.ksize == 3 && d.impl == PBMC_CONV_ROW_F16X2) {
-    bool simple = true;
-    for (int s = 0; s < d.nsrc; ++s)
-      simple = simple && d.src[s].layout == PBMC_LAYOUT_BLOCKED && (d.src[s].xform == PBMC_XFORM_NONE || d.src[s].xform == PBMC_XFORM_GN_GELU);
-    using G = RowGeom<3, 2, true>;
-    const size_t smem = CR_SMEM_HDR + (size_t)p.ngroups * G::B_GROUP + (size_t)(CR_RAW_NA + CR_RAW_NT) * G::STAGE_BYTES + (size_t)cin * 8;
-    static const int raw_knob = PBMC_DEV_KNOB("PBMC_ROW_RAW", 1);  // developer knob
-    p.raw_loader = simple && smem <= 227 * 1024 && raw_knob;
-  }
   p.trace = nullptr;
   p.dbg_dx = PBMC_DEV_KNOB("PBMC_ROW_DBG_DX", 16);
   p.dbg_flags = PBMC_DEV_KNOB("PBMC_ROW_DBG_FLAGS", 0);
