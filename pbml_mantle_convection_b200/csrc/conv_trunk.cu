@@ -256,6 +256,15 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
         }
         if (h_on && sy >= 0) Rw.h = __ldcg(in_h + ro);
       };
+      // the group's first row is requested before the layer's GroupNorm coefficients are computed (threads 0..15: two
+      // L2 reads and a double-precision rsqrt each), so that the two latencies overlap
+      Row ra;
+      int ri = g, yo = g;
+      if (ri < nin) load_row(ri, ra);
+      if (l > 0) {
+        if (tid < 16) load_coeffs(l);
+        ct_worker_bar();
+      }
       const float h_a = xf_a[hch], h_b = xf_b[hch];
       auto stage_row = [&](int ri, const Row& Rw) {
         float v[16] = {Rw.v0.x, Rw.v0.y, Rw.v0.z, Rw.v0.w, Rw.v1.x, Rw.v1.y, Rw.v1.z, Rw.v1.w,
@@ -391,9 +400,6 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
         }
       };
 
-      Row ra;
-      int ri = g, yo = g;
-      if (ri < nin) load_row(ri, ra);
       while (ri < nin) {
         stage_row(ri, ra);
         ri += CT_SETS;
@@ -412,34 +418,41 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
         const double c2 = warp_sum((double)s2[qb]);
         if (lane == 0) { red[(warp * 4 + qb) * 2] = a; red[(warp * 4 + qb) * 2 + 1] = c2; }
       }
-      ct_worker_bar();
-      if (tid < 8) {
+      ct_worker_bar();  // every output row of the CTA is stored, red[] is complete
+      if (warp == 0) {
+        // one warp finishes the layer for the CTA: lane = (quarter of the 20 warps, moment) adds five partial sums, two
+        // shuffles fold the quarters, lanes 0..7 issue the atomics ...
+        static_assert(CT_WORKERS == 20, "four quarters of five warps");
+        const int m = lane & 7, q = lane >> 3;
         double t = 0.0;
-        for (int w = 0; w < CT_WORKERS; ++w) t += red[(w * 4 + (tid >> 1)) * 2 + (tid & 1)];
-        atomicAdd(Ld.out_stats + ((size_t)b * 4 + (tid >> 1)) * 2 + (tid & 1), t);
+#pragma unroll
+        for (int w = 0; w < 5; ++w) t += red[((q * 5 + w) * 4 + (m >> 1)) * 2 + (m & 1)];
+        t += __shfl_xor_sync(0xffffffffu, t, 8);
+        t += __shfl_xor_sync(0xffffffffu, t, 16);
+        if (lane < 8) atomicAdd(Ld.out_stats + ((size_t)b * 4 + (m >> 1)) * 2 + (m & 1), t);
+        if (l + 1 < R) {
+          // ... and takes the CTA through the grid-wide barrier of this sample's CTAs: every output row and every statistics
+          // contribution of layer l is in L2 before anybody starts layer l + 1 (cooperative-groups pattern: CTA barrier
+          // above, fence, arrive + poll by one thread, CTA barrier below)
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) {
+            atomicAdd(p.sync + b, 1u);
+            const unsigned int target = (unsigned int)(l + 1) * nctas;
+            if (ld_acquire_gpu_u32(p.sync + b) < target) {
+              const long long t0 = clock64();
+              while (ld_acquire_gpu_u32(p.sync + b) < target) {
+                __nanosleep(20);
+                if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: some CTA of the launch is not resident
+              }
+            }
+            __threadfence();
+          }
+        }
       }
       if (l + 1 < R) {
-        // ---- grid-wide barrier of this sample's CTAs: every output row and every statistics contribution of layer l
-        // is in L2 before anybody starts layer l + 1 (cooperative-groups pattern: CTA barrier, fence + arrive + poll by
-        // one thread, CTA barrier)
-        ct_worker_bar();
-        if (tid == 0) {
-          __threadfence();
-          atomicAdd(p.sync + b, 1u);
-          const unsigned int target = (unsigned int)(l + 1) * nctas;
-          if (ld_acquire_gpu_u32(p.sync + b) < target) {
-            const long long t0 = clock64();
-            while (ld_acquire_gpu_u32(p.sync + b) < target) {
-              __nanosleep(20);
-              if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: some CTA of the launch is not resident
-            }
-          }
-          __threadfence();
-        }
         ct_worker_bar();
         if (BULK) request_rows(l + 1);
-        if (tid < 16) load_coeffs(l + 1);
-        ct_worker_bar();
       }
     }
   } else {
