@@ -334,6 +334,12 @@ int pbmc_ctx_create(pbmc_ctx** out);
 int pbmc_ctx_destroy(pbmc_ctx* ctx);
 
 size_t pbmc_workspace_bytes(const pbmc_net* net_h, int B, int H, int W);
+/* How a forward of this network at this size shares the 148 SMs between the pyramid levels (NewFluidNet.forward's trunk,
+ * pytorch_networks_convae.py:1319-1327, runs the levels side by side): budgets[l] = CTAs of level l's conv kernels
+ * (PBMC_MAX_LEVELS entries; 0 = no budget, the level's launches run in waves).  Returns 1 when the trunk runs as persistent
+ * kernels (one launch per level: every level has a budget and the budgets fit the GPU), 0 when it runs one launch per layer,
+ * < 0 on error.  Pure host computation: no GPU needed. */
+int pbmc_trunk_cta_budgets(const pbmc_net* net_h, int B, int H, int W, int* budgets);
 
 /* inp: blocked [B][ceil(c_i/4)][H][W][4] network input (A1's output, or a packed user tensor).
  * u,v,p plain [B][H][W] (mae head with p_pred: p too).  members may be NULL => scaler 1

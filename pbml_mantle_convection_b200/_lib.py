@@ -113,6 +113,7 @@ SIGNATURES = {
     "pbmc_ctx_create": (_i, [C.POINTER(_vp)]),
     "pbmc_ctx_destroy": (_i, [_vp]),
     "pbmc_workspace_bytes": (_sz, [C.POINTER(Net), _i, _i, _i]),
+    "pbmc_trunk_cta_budgets": (_i, [C.POINTER(Net), _i, _i, _i, C.POINTER(C.c_int)]),
     "pbmc_surrogate_forward": (_i, [_vp, C.POINTER(Net), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
     "pbmc_rollout": (_i, [_vp, C.POINTER(Net), _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp,
                           _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),

@@ -298,47 +298,9 @@ static int surrogate_enqueue(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, ch
   return rc;
 }
 
-// pre_zeroed: the caller's previous kernel has already cleared the scratch region [P.stats, P.stats + P.stats_bytes)
-static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, char* ws, const float* inp,
-                                const pbmc_member* members, float* u, float* v, float* p, uint32_t* uvmax, int B, int H,
-                                int W, cudaStream_t st, bool pre_zeroed) {
+// Per-level CTA budgets of one forward and whether the trunk runs as persistent kernels (one launch per pyramid level).
+static bool level_cta_budgets(const pbmc_net& n, const Plan& P, int B, int H, int W, int* cta_budget) {
   const int L = P.L, R = P.R, CB = P.CB;
-  // Programmatic dependent launch on the critical chain (PBMC_CHAIN_PDL overrides the mask; default 1 | 4):
-  //   1  conv[2], conv[3]   on: nothing else runs then; the next conv's set-up overlaps the previous one's drain
-  //   4  conv[1]            on  (0.2348 -> 0.2331 -> 0.2311 ms/step at 512^2 with 1, then 1 | 4)
-  //   8  head kernel        on
-  //  16  conv[0]            on in a rollout (behind the input-build kernel, no memset node in between)
-  //   2  level-0 trunk      off: 0.27 ms -- an early-resident CTA parked in griddepcontrol.wait takes an SM from
-  //                              the other levels' streams
-  static const int chain_pdl = PBMC_DEV_KNOB("PBMC_CHAIN_PDL", 5 | 8 | 16);
-  auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
-  auto S = [&](int slot) { return reinterpret_cast<double*>(ws + P.stat_off(slot, B)); };
-  double* chan_sum = reinterpret_cast<double*>(ws + P.chan_sum);
-  // zero all statistics accumulators (GroupNorm sums, zero-mean sums) in one memset
-  if (!pre_zeroed) {
-    PBMC_CUDA(cudaMemsetAsync(ws + P.stats, 0, P.stats_bytes - (size_t)2 * B * sizeof(uint32_t), st));
-    if (uvmax) PBMC_CUDA(cudaMemsetAsync(uvmax, 0, (size_t)B * sizeof(uint32_t), st));
-  }
-
-  pbmc_conv_desc d;
-  // conv[0]: FluidLayer(c_i -> c_h), :1317
-  fill_conv(d, n, n.conv0, B, H, W, F(P.x0), S(0), nullptr, PBMC_ACT_NONE);
-  d.nsrc = 1;
-  d.src[0] = make_src(inp, P.CIB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
-  g_conv_pdl_next = pre_zeroed ? (chain_pdl & 16) : 0;  // rollout: directly behind the input-build kernel
-  {
-    const int rc0 = conv_enqueue(d, st);
-    g_conv_pdl_next = 0;
-    RC(rc0);
-  }
-  PBMC_CUDA(cudaEventRecord(ctx->ev_fork[0], st));
-
-  // pyramid levels (:1319-1327): level l runs on stream l (level 0 on the caller's stream)
-  // The L level chains run side by side and a tensor-core conv CTA owns an SM, so each level gets a share of the
-  // 148 SMs in proportion to its row-strip count (with a floor so that the small levels do not become the
-  // longest chain): every level then needs about the same time per layer instead of each launch trying to
-  // fill the GPU on its own and queueing behind the others.
-  int cta_budget[PBMC_MAX_LEVELS];
   {
     double tot = 0.0, w[PBMC_MAX_LEVELS];
     for (int l = 0; l < L; ++l) { w[l] = (double)B * ((P.Wl[l] + 127) / 128) * P.Hl[l]; tot += w[l]; }
@@ -354,23 +316,6 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
       cta_budget[l] = L > 1 ? want : 0;
     }
   }
-  // conv[1] is the only reader of the up-sampled levels: when it runs on the fp16 hi|lo row kernel (3x3, replicate
-  // padding, 16 hidden channels) they are written directly as its operand image and staged by bulk copies
-  bool up_staged = n.pad_mode == PBMC_PAD_REPLICATE && CB == 4 && n.conv1.ksize == 3 && n.conv1.wpk_row != nullptr &&
-                   (n.conv_impl == PBMC_CONV_AUTO || n.conv_impl == PBMC_CONV_ROW_F16X2 || n.conv_impl == PBMC_CONV_MUX_F16X2);
-  if (up_staged) {
-    pbmc_conv_desc t;
-    memset(&t, 0, sizeof(t));
-    t.nsrc = L + 1; t.ksize = 3; t.cout = n.conv1.cout;
-    for (int l = 0; l < L; ++l) t.src[l].nblk = CB;
-    for (int l = 1; l < L; ++l) t.src[l].layout = PBMC_LAYOUT_STAGED16;
-    t.src[L].nblk = P.CIB;
-    up_staged = L + 1 <= PBMC_MAX_SRC && conv_row_supported(t);
-  }
-  // Off by default: measured neutral-to-slower in the whole step (512^2: 0.244-0.260 vs 0.241 ms; 32 x 256^2: 1.47 vs
-  // 1.445 ms) -- conv[1] is paced by its MMA issue loop, not by its producers, and the operand-image writer of the
-  // bicubic kernel stores 2 x 8 B per thread.  pbmc_net.flags & PBMC_NET_UP_STAGED turns it on (results are bit-identical).
-  up_staged = up_staged && (n.flags & PBMC_NET_UP_STAGED) != 0;
   // Persistent trunk kernels (csrc/conv_trunk.cu: the R layers of a level in one launch, grid barrier between layers)
   // need EVERY CTA of EVERY level resident at once: taken only when all levels have a budget and the budgets fit 148 SMs.
   bool trunk_persistent = (n.flags & PBMC_NET_TRUNK_PER_LAYER) == 0 && CB == 4 && n.ksize == 3;
@@ -462,6 +407,68 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
     }
     trunk_persistent = trunk_persistent && total <= 148;
   }
+  return trunk_persistent;
+}
+
+// pre_zeroed: the caller's previous kernel has already cleared the scratch region [P.stats, P.stats + P.stats_bytes)
+static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P, char* ws, const float* inp,
+                                const pbmc_member* members, float* u, float* v, float* p, uint32_t* uvmax, int B, int H,
+                                int W, cudaStream_t st, bool pre_zeroed) {
+  const int L = P.L, R = P.R, CB = P.CB;
+  // Programmatic dependent launch on the critical chain (PBMC_CHAIN_PDL overrides the mask; default 1 | 4):
+  //   1  conv[2], conv[3]   on: nothing else runs then; the next conv's set-up overlaps the previous one's drain
+  //   4  conv[1]            on  (0.2348 -> 0.2331 -> 0.2311 ms/step at 512^2 with 1, then 1 | 4)
+  //   8  head kernel        on
+  //  16  conv[0]            on in a rollout (behind the input-build kernel, no memset node in between)
+  //   2  level-0 trunk      off: 0.27 ms -- an early-resident CTA parked in griddepcontrol.wait takes an SM from
+  //                              the other levels' streams
+  static const int chain_pdl = PBMC_DEV_KNOB("PBMC_CHAIN_PDL", 5 | 8 | 16);
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  auto S = [&](int slot) { return reinterpret_cast<double*>(ws + P.stat_off(slot, B)); };
+  double* chan_sum = reinterpret_cast<double*>(ws + P.chan_sum);
+  // zero all statistics accumulators (GroupNorm sums, zero-mean sums) in one memset
+  if (!pre_zeroed) {
+    PBMC_CUDA(cudaMemsetAsync(ws + P.stats, 0, P.stats_bytes - (size_t)2 * B * sizeof(uint32_t), st));
+    if (uvmax) PBMC_CUDA(cudaMemsetAsync(uvmax, 0, (size_t)B * sizeof(uint32_t), st));
+  }
+
+  pbmc_conv_desc d;
+  // conv[0]: FluidLayer(c_i -> c_h), :1317
+  fill_conv(d, n, n.conv0, B, H, W, F(P.x0), S(0), nullptr, PBMC_ACT_NONE);
+  d.nsrc = 1;
+  d.src[0] = make_src(inp, P.CIB, PBMC_XFORM_NONE, nullptr, nullptr, 0.0);
+  g_conv_pdl_next = pre_zeroed ? (chain_pdl & 16) : 0;  // rollout: directly behind the input-build kernel
+  {
+    const int rc0 = conv_enqueue(d, st);
+    g_conv_pdl_next = 0;
+    RC(rc0);
+  }
+  PBMC_CUDA(cudaEventRecord(ctx->ev_fork[0], st));
+
+  // pyramid levels (:1319-1327): level l runs on stream l (level 0 on the caller's stream)
+  // The L level chains run side by side and a tensor-core conv CTA owns an SM, so each level gets a share of the
+  // 148 SMs in proportion to its row-strip count (with a floor so that the small levels do not become the
+  // longest chain): every level then needs about the same time per layer instead of each launch trying to
+  // fill the GPU on its own and queueing behind the others.
+  int cta_budget[PBMC_MAX_LEVELS];
+  const bool trunk_persistent = level_cta_budgets(n, P, B, H, W, cta_budget);
+  // conv[1] is the only reader of the up-sampled levels: when it runs on the fp16 hi|lo row kernel (3x3, replicate
+  // padding, 16 hidden channels) they are written directly as its operand image and staged by bulk copies
+  bool up_staged = n.pad_mode == PBMC_PAD_REPLICATE && CB == 4 && n.conv1.ksize == 3 && n.conv1.wpk_row != nullptr &&
+                   (n.conv_impl == PBMC_CONV_AUTO || n.conv_impl == PBMC_CONV_ROW_F16X2 || n.conv_impl == PBMC_CONV_MUX_F16X2);
+  if (up_staged) {
+    pbmc_conv_desc t;
+    memset(&t, 0, sizeof(t));
+    t.nsrc = L + 1; t.ksize = 3; t.cout = n.conv1.cout;
+    for (int l = 0; l < L; ++l) t.src[l].nblk = CB;
+    for (int l = 1; l < L; ++l) t.src[l].layout = PBMC_LAYOUT_STAGED16;
+    t.src[L].nblk = P.CIB;
+    up_staged = L + 1 <= PBMC_MAX_SRC && conv_row_supported(t);
+  }
+  // Off by default: measured neutral-to-slower in the whole step (512^2: 0.244-0.260 vs 0.241 ms; 32 x 256^2: 1.47 vs
+  // 1.445 ms) -- conv[1] is paced by its MMA issue loop, not by its producers, and the operand-image writer of the
+  // bicubic kernel stores 2 x 8 B per thread.  pbmc_net.flags & PBMC_NET_UP_STAGED turns it on (results are bit-identical).
+  up_staged = up_staged && (n.flags & PBMC_NET_UP_STAGED) != 0;
   const float* level_in[PBMC_MAX_LEVELS];
   level_in[0] = F(P.x0);
   for (int l = 0; l < L; ++l) {
@@ -566,6 +573,14 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
     RC(rch);
   }
   return PBMC_OK;
+}
+
+extern "C" int pbmc_trunk_cta_budgets(const pbmc_net* net, int B, int H, int W, int* budgets) {
+  if (!net || !budgets) return PBMC_ERR_NULL_POINTER;
+  Plan P;
+  RC(make_plan(*net, B, H, W, P));
+  for (int l = 0; l < PBMC_MAX_LEVELS; ++l) budgets[l] = 0;
+  return level_cta_budgets(*net, P, B, H, W, budgets) ? 1 : 0;
 }
 
 extern "C" int pbmc_surrogate_forward(pbmc_ctx* ctx, const pbmc_net* net, const float* inp, const pbmc_member* members,
