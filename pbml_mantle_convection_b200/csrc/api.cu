@@ -32,9 +32,6 @@ extern thread_local int g_conv_pdl_next;  // conv_mux.cu: the next mux launch us
 int build_input_enqueue(const float* T, const float* xc, const float* yc, const float* ycc, const pbmc_member* members, float* inp,
                         float* V, int B, int H, int W, void* zero, size_t zero_bytes, cudaStream_t st, bool pdl);  // pyramid.cu
 extern thread_local int g_stencil_pdl_next;  // stencil.cu: the next plain stencil launch uses programmatic dependent launch
-int advect_diffuse_build_next(const float* T, const float* u, const float* v, const float* xcoef, const float* ycoef,
-                              const pbmc_member* members, const uint32_t* uvmax, int member_stride, double dx_min, double cn_max,
-                              float* T_out, double* dt_out, int B, int H, int W, const StencilBuildNext& bn, cudaStream_t st);  // stencil.cu
 
 }  // namespace pbmc
 
@@ -632,51 +629,23 @@ extern "C" int pbmc_rollout(pbmc_ctx* ctx, const pbmc_net* net, const pbmc_membe
   PBMC_CUDA(cudaEventRecord(ctx->ev_in, caller));
   PBMC_CUDA(cudaStreamWaitEvent(st, ctx->ev_in, 0));
   static const int tail_pdl = PBMC_DEV_KNOB("PBMC_TAIL_PDL", 3);  // 1 stencil behind head, 2 input build behind stencil
-  static const int tail_fuse = PBMC_DEV_KNOB("PBMC_TAIL_FUSE", 1);  // 1 the next step's input build inside the stencil launch
   auto steps = [&]() -> int {
-    // The input build of step i + 1 rides in the stencil launch of step i (the warp that has just computed T' of a cell
-    // writes that cell's input channels; the grid clears the next forward's scratch): one launch less per step.  The CFL
-    // maximum is double-buffered by step parity for that -- the stencil of step i reads slot i & 1 while it clears the
-    // other one for step i + 1.  Only a call's first step has an input-build kernel of its own.
-    float* inp = reinterpret_cast<float*>(ws + P.inp);
-    bool built = false;  // the previous step's stencil launch has already built this step's input and cleared its scratch
     for (int i = first_step; i < first_step + n_steps; ++i) {
       const float* Tin = T_seq + (size_t)((i - 1) % nslots) * field;
       float* Tout = T_seq + (size_t)(i % nslots) * field;
       const bool last = (i == first_step + n_steps - 1);
-      uint32_t* uv_i = uvmax + (size_t)(i & 1) * B;
-      if (!built)
-        RC(build_input_enqueue(Tin, xc, yc, ycc, members, inp, last ? V : nullptr, B, H, W, ws + P.stats, P.stats_bytes, st,
-                               (tail_pdl & 2) && i > first_step));
-      RC(surrogate_enqueue_on(ctx, *net, P, ws, inp, members, u, v, p, uv_i, B, H, W, st, true));
+      // programmatic dependent launch: behind the previous step's stencil (not for the call's first step: whatever
+      // precedes it in the stream is not ours)
+      RC(build_input_enqueue(Tin, xc, yc, ycc, members, reinterpret_cast<float*>(ws + P.inp), last ? V : nullptr, B, H, W, ws + P.stats,
+                             P.stats_bytes, st, (tail_pdl & 2) && i > first_step));
+      RC(surrogate_enqueue_on(ctx, *net, P, ws, reinterpret_cast<float*>(ws + P.inp), members, u, v, p, uvmax, B, H, W, st, true));
       if (!per_member_dt && B > 1) {
-        uvmax_batch_reduce_kernel<<<1, 32, 0, st>>>(uv_i, B);
+        uvmax_batch_reduce_kernel<<<1, 32, 0, st>>>(uvmax, B);
         PBMC_CHECK_LAUNCH("uvmax_batch_reduce_kernel");
       }
-      double* dt_i = dt_seq ? dt_seq + (size_t)(i - 1) * B : nullptr;
-      const bool pdl = (tail_pdl & 1) && (per_member_dt || B == 1);  // directly behind the head kernel
-      built = false;
-      if (!last && (tail_fuse & 1)) {
-        StencilBuildNext bn;
-        bn.xc = xc; bn.yc = yc; bn.ycc = ycc; bn.inp = inp;
-        bn.V = (i + 1 == first_step + n_steps - 1) ? V : nullptr;  // V belongs to the call's last input
-        bn.zero = reinterpret_cast<uint32_t*>(ws + P.stats);
-        bn.zero_words = (unsigned int)(P.stats_bytes / 4);
-        bn.keep_lo = (unsigned int)((P.uvmax - P.stats) / 4 + (size_t)(i & 1) * B);
-        bn.keep_hi = bn.keep_lo + (unsigned int)B;
-        g_stencil_pdl_next = pdl;
-        const int rcf = advect_diffuse_build_next(Tin, u, v, xcoef, ycoef, members, uv_i, per_member_dt ? 1 : 0, dx_min, cn_max, Tout, dt_i,
-                                                  B, H, W, bn, st);
-        g_stencil_pdl_next = 0;
-        if (rcf == PBMC_OK) {
-          built = true;
-          continue;
-        }
-        if (rcf != PBMC_ERR_UNSUPPORTED) return rcf;
-      }
-      g_stencil_pdl_next = pdl;
-      const int rcs = pbmc_advect_diffuse(Tin, u, v, xcoef, ycoef, members, uv_i, per_member_dt ? 1 : 0, dx_min, cn_max, 0.0, Tout, nullptr, dt_i,
-                                          B, H, W, st);
+      g_stencil_pdl_next = (tail_pdl & 1) && (per_member_dt || B == 1);  // directly behind the head kernel
+      const int rcs = pbmc_advect_diffuse(Tin, u, v, xcoef, ycoef, members, uvmax, per_member_dt ? 1 : 0, dx_min, cn_max, 0.0, Tout, nullptr,
+                                          dt_seq ? dt_seq + (size_t)(i - 1) * B : nullptr, B, H, W, st);
       g_stencil_pdl_next = 0;
       RC(rcs);
     }

@@ -61,16 +61,6 @@ static inline cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), dim3 grid, di
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-// The next forward's input build fused into the stencil launch (stencil.cu, used by pbmc_rollout): coordinates, the
-// blocked input tensor, optionally the viscosity field, and the forward's scratch to clear (32-bit words; [keep_lo, keep_hi)
-// stay as they are).
-struct StencilBuildNext {
-  const float* xc; const float* yc; const float* ycc;
-  float* inp; float* V;
-  uint32_t* zero;
-  unsigned int zero_words, keep_lo, keep_hi;
-};
-
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

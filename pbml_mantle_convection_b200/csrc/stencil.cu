@@ -26,14 +26,6 @@ struct StencilParams {
   int store_lo, store_hi, push_up_row, push_down_row;
   float* push_up;
   float* push_down;
-  // next step's input build fused behind the update (pbmc_rollout; BUILD variant of the march kernel): the warp that
-  // has just computed T' of a cell writes the 7-channel input of the following forward (TS.forward :379-407, same
-  // arithmetic as build_input_kernel) and the grid clears that forward's scratch -- words [keep_lo, keep_hi) excepted
-  // (the CFL maximum this very launch reads).
-  const float* b_xc; const float* b_yc; const float* b_ycc;
-  float* b_inp; float* b_V;
-  uint32_t* b_zero;
-  unsigned int b_zero_words, b_keep_lo, b_keep_hi;
 };
 
 // Cross-rank state of the flag-synchronised slab step (pbmc_advect_diffuse_slab_sync): the global CFL reduction and the
@@ -268,19 +260,12 @@ __global__ void __launch_bounds__(ST_BX* ST_BY) stencil_kernel(const StencilPara
 //          rank's slot of the other parity and advances steps_done.  Two parities suffice: a rank can only
 //          overwrite parity (s & 1) at the end of step s + 1, which it enters only after every rank has published
 //          step s + 1's value, i.e. after every rank has finished step s and consumed the tags of step s.
-template <bool SYNC, bool BUILD = false>
+template <bool SYNC>
 __global__ void __launch_bounds__(128, 6) stencil_march_kernel(const StencilParams p, int rpw, const SlabSyncArgs sa) {
-  static_assert(!(SYNC && BUILD), "the fused input build belongs to the single-domain rollout");
   // no-ops unless launched with programmatic stream serialization (the rollout does, behind the head kernel)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int H = p.H, W = p.W, b = blockIdx.z;
-  if (BUILD && p.b_zero != nullptr) {
-    const unsigned int nthr = gridDim.x * gridDim.y * gridDim.z * 128u;
-    const unsigned int first = ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 128u + threadIdx.x;
-    for (unsigned int w = first; w < p.b_zero_words; w += nthr)
-      if (w < p.b_keep_lo || w >= p.b_keep_hi) p.b_zero[w] = 0u;
-  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = (blockIdx.x * 32 + lane) * 4;
   const int y0 = (blockIdx.y * 4 + warp) * rpw;
@@ -367,26 +352,6 @@ __global__ void __launch_bounds__(128, 6) stencil_march_kernel(const StencilPara
       // side columns copy their interior neighbour (replicate pad :565, :470-471)
       if (x0 == 0) o[0] = o[1];
       if (x0 + 4 == W) o[3] = o[2];
-    }
-    if (BUILD && act) {
-      // input channels of the next forward for these four cells: x/4, y/4, log10(clip V)/8, raq_nd | fkt_nd, fkp_nd, T', 0
-      const size_t i0 = (size_t)r * W + x0;
-      const pbmc_member mm = p.mem[b];
-      const float4 xc4 = ldg4(p.b_xc + i0), yc4 = ldg4(p.b_yc + i0), yk4 = ldg4(p.b_ycc + i0);
-      const float xs4[4] = {xc4.x, xc4.y, xc4.z, xc4.w}, ys4[4] = {yc4.x, yc4.y, yc4.z, yc4.w}, yk[4] = {yk4.x, yk4.y, yk4.z, yk4.w};
-      float* i_a = p.b_inp + (((size_t)b * 2 + 0) * plane + i0) * 4;
-      float* i_b = p.b_inp + (((size_t)b * 2 + 1) * plane + i0) * 4;
-      float vis[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float t = o[k];
-        const float z = mm.ln_fkt * (0.0f - t) + mm.ln_fkp * (1.0f - yk[k]);
-        const float l10 = fminf(fmaxf(z * 0.43429448190325182765f, -8.0f), 0.0f);
-        *reinterpret_cast<float4*>(i_a + 4 * k) = make_float4(xs4[k] * 0.25f, ys4[k] * 0.25f, l10 * 0.125f, mm.raq_nd);
-        *reinterpret_cast<float4*>(i_b + 4 * k) = make_float4(mm.fkt_nd, mm.fkp_nd, t, 0.f);
-        if (p.b_V != nullptr) vis[k] = fminf(fmaxf(expf(z), 1e-8f), 1.0f);
-      }
-      if (p.b_V != nullptr) *reinterpret_cast<float4*>(p.b_V + (size_t)b * plane + i0) = make_float4(vis[0], vis[1], vis[2], vis[3]);
     }
     if (act && r >= p.store_lo && r < p.store_hi) {
       const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
@@ -599,24 +564,15 @@ static int advect_diffuse_launch(const float* T, const float* u, const float* v,
                                  const pbmc_member* members, const uint32_t* uvmax_in, int member_stride, double dx_min,
                                  double cn_max, double dt_fixed, float* T_out, uint32_t* uvmax_out, double* dt_out, int B, int H,
                                  int W, int has_up, int has_down, float* peer_up, float* peer_down, void* stream,
-                                 const SlabSyncArgs* sync = nullptr, const StencilBuildNext* bn = nullptr) {
+                                 const SlabSyncArgs* sync = nullptr) {
   if (!T || !u || !v || !x || !y || !T_out) return PBMC_ERR_NULL_POINTER;
   if (!(dt_fixed > 0.0) && !uvmax_in && !sync) return PBMC_ERR_NULL_POINTER;
   if (B <= 0 || H < 3 || W < 3 || (member_stride != 0 && member_stride != 1)) return PBMC_ERR_BAD_SHAPE;
   if (T == T_out) return PBMC_ERR_UNSUPPORTED;  // out-of-place only (neighbours are read)
   const bool slab = has_up || has_down || peer_up || peer_down || sync != nullptr;
   StencilParams p{T, u, v, x, y, members, uvmax_in, uvmax_out, T_out, dt_out, dx_min, cn_max, dt_fixed, member_stride, H, W,
-                  has_up ? 1 : 0, has_down ? H - 1 : H, has_up ? 1 : -1, has_down ? H - 2 : -1, peer_up, peer_down,
-                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0u, 0u, 0u};
-  if (bn != nullptr) {
-    if (slab || !members || !bn->xc || !bn->yc || !bn->ycc || !bn->inp) return PBMC_ERR_NULL_POINTER;
-    p.b_xc = bn->xc; p.b_yc = bn->yc; p.b_ycc = bn->ycc; p.b_inp = bn->inp; p.b_V = bn->V;
-    p.b_zero = bn->zero; p.b_zero_words = bn->zero_words; p.b_keep_lo = bn->keep_lo; p.b_keep_hi = bn->keep_hi;
-  }
+                  has_up ? 1 : 0, has_down ? H - 1 : H, has_up ? 1 : -1, has_down ? H - 2 : -1, peer_up, peer_down};
   const bool vec = (W % 4 == 0) && aligned16(T) && aligned16(u) && aligned16(v) && aligned16(T_out);
-  if (bn != nullptr && !(vec && aligned16(x) && aligned16(bn->xc) && aligned16(bn->yc) && aligned16(bn->ycc) && aligned16(bn->inp) &&
-                         (!bn->V || aligned16(bn->V))))
-    return PBMC_ERR_UNSUPPORTED;  // the caller falls back to the separate input-build kernel
   static const int tiled = PBMC_DEV_KNOB("PBMC_STENCIL_TILED", 0);  // developer knob: old kernel
   if (vec && aligned16(x) && (!tiled || slab)) {
     if ((peer_up && !aligned16(peer_up)) || (peer_down && !aligned16(peer_down))) return PBMC_ERR_MISALIGNED;
@@ -652,15 +608,12 @@ static int advect_diffuse_launch(const float* T, const float* u, const float* v,
     } else {
       const bool pdl = g_stencil_pdl_next != 0;
       g_stencil_pdl_next = 0;
-      if (bn != nullptr)
-        PBMC_CUDA(launch_maybe_pdl(stencil_march_kernel<false, true>, grid, dim3(128), 0, (cudaStream_t)stream, pdl, p, rpw, SlabSyncArgs{}));
-      else
-        PBMC_CUDA(launch_maybe_pdl(stencil_march_kernel<false>, grid, dim3(128), 0, (cudaStream_t)stream, pdl, p, rpw, SlabSyncArgs{}));
+      PBMC_CUDA(launch_maybe_pdl(stencil_march_kernel<false>, grid, dim3(128), 0, (cudaStream_t)stream, pdl, p, rpw, SlabSyncArgs{}));
     }
     PBMC_CHECK_LAUNCH("stencil_march_kernel");
     return PBMC_OK;
   }
-  if (slab || sync || bn) return PBMC_ERR_UNSUPPORTED;  // the slab / fused forms need 16-byte aligned rows (W % 4 == 0)
+  if (slab || sync) return PBMC_ERR_UNSUPPORTED;  // the slab form needs 16-byte aligned rows (W % 4 == 0)
   const int TW = vec ? ST_BX * 4 : ST_BX;
   dim3 grid(cdiv(W, TW), cdiv(H, ST_TH), B);
   if (grid.y > 65535 || grid.z > 65535) return PBMC_ERR_BAD_SHAPE;
@@ -671,17 +624,6 @@ static int advect_diffuse_launch(const float* T, const float* u, const float* v,
   PBMC_CHECK_LAUNCH("stencil_kernel");
   return PBMC_OK;
 }
-
-namespace pbmc {
-// pbmc_advect_diffuse + the input build of the following forward in one launch (PBMC_ERR_UNSUPPORTED: shapes / alignments the
-// vectorised kernel does not take -- the caller then launches the two kernels separately)
-int advect_diffuse_build_next(const float* T, const float* u, const float* v, const float* xcoef, const float* ycoef,
-                              const pbmc_member* members, const uint32_t* uvmax, int member_stride, double dx_min, double cn_max,
-                              float* T_out, double* dt_out, int B, int H, int W, const StencilBuildNext& bn, cudaStream_t st) {
-  return advect_diffuse_launch(T, u, v, xcoef, ycoef, members, uvmax, member_stride, dx_min, cn_max, 0.0, T_out, nullptr, dt_out, B, H, W,
-                               0, 0, nullptr, nullptr, st, nullptr, &bn);
-}
-}  // namespace pbmc
 
 extern "C" int pbmc_advect_diffuse(const float* T, const float* u, const float* v, const float* x, const float* y,
                                    const pbmc_member* members, const uint32_t* uvmax_in, int member_stride,
