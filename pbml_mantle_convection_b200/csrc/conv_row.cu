@@ -47,13 +47,10 @@ extern thread_local int g_conv_pdl_next;  // conv_mux.cu: set by api.cu right be
 //            output row is due after every stage;
 //   NPG = 4: one epilogue set + four producer groups -- several groups per row (conv[1]: 7 stages per output row), where
 //            the epilogue idles and the producers' serial per-stage chain sets the pace (tools/exp_conv1.sh).
-//   NPG = 5: one epilogue set + FIVE producer groups and no bulk-copy warp (no operand-image source): 25 warps = 800 threads is
-//            what the register file holds at 80 registers per thread.
-// Warps 0 .. 4*EPI_SETS-1 epilogue, then 4*NPG producer warps, then the MMA issuer, then (NPG < 5) the warp whose lane 0
-// bulk-copies the stages of operand-image (STAGED16) sources.
-constexpr int cr_epi_sets(int npg) { return npg == 3 ? 2 : 1; }
-constexpr int cr_mma_warp(int npg) { return 4 * (cr_epi_sets(npg) + npg); }
-constexpr int cr_threads(int npg) { return (cr_mma_warp(npg) + (npg < 5 ? 2 : 1)) * 32; }
+constexpr int CR_SETS = 5;
+constexpr int CR_MMA_WARP = 4 * CR_SETS;      // warps 0 .. 4*EPI_SETS-1 epilogue, then 4*NPG producer warps, then the MMA issuer
+constexpr int CR_TMA_WARP = CR_MMA_WARP + 1;  // one lane bulk-copies the stages of operand-image (STAGED16) sources
+constexpr int CR_THREADS = (CR_TMA_WARP + 1) * 32;
 constexpr int CR_NT = 8;                                // stages of the bulk-copy ring (power of two)
 constexpr int CR_MAXG = 24;
 constexpr int CR_SMEM_HDR = 2176;
@@ -144,11 +141,10 @@ __device__ __forceinline__ float xform1(float v, float a, float b, int xform) {
 }
 
 template <int KS, int PARTS, int NPG>
-__global__ void __launch_bounds__(cr_threads(NPG), 1) conv_row_kernel(const __grid_constant__ ConvRowParams p) {
-  constexpr bool MERGE = NPG >= 4 && KS == 3 && PARTS == 2;  // the several-groups-per-row variants (conv[1]) merge two passes
-  constexpr int CR_MMA_WARP = cr_mma_warp(NPG), CR_THREADS = cr_threads(NPG);
+__global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_constant__ ConvRowParams p) {
+  constexpr bool MERGE = NPG == 4 && KS == 3 && PARTS == 2;  // the several-groups-per-row variant (conv[1]) merges two passes
   using G = RowGeom<KS, PARTS, MERGE>;
-  constexpr int CR_NPG = NPG, EPI_SETS = cr_epi_sets(NPG), CR_EPI_WARPS = 4 * EPI_SETS;
+  constexpr int CR_NPG = NPG, EPI_SETS = CR_SETS - NPG, CR_EPI_WARPS = 4 * EPI_SETS;
   static_assert(NPG >= 1 && EPI_SETS >= 1, "role split");
   constexpr int P = G::P, N = G::N, DN = G::DN, NSTAGE = G::NSTAGE, ND = G::ND, PLANE = G::PLANE;
   static_assert(8 * (2 * NSTAGE + 2 * ND + 2 * CR_NT) <= 448, "barrier area");
@@ -1059,7 +1055,7 @@ static int launch_row_npg(ConvRowParams& p, cudaStream_t st) {
   static const int pdl = PBMC_DEV_KNOB("PBMC_ROW_PDL", 0);  // developer knob
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(cr_threads(NPG));
+  cfg.blockDim = dim3(CR_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1077,10 +1073,8 @@ template <int KS, int PARTS>
 static int launch_row(ConvRowParams& p, cudaStream_t st) {
   // several K groups per input row (conv[1]): four producer groups, one epilogue set; else three and two
   static const int forced = PBMC_DEV_KNOB("PBMC_ROW_NPG", 0);  // developer knob
-  const bool heavy = forced ? forced >= 4 : p.ngroups >= 3;
-  if (!heavy) return launch_row_npg<KS, PARTS, 3>(p, st);
-  if (forced != 4 && !p.has_staged) return launch_row_npg<KS, PARTS, 5>(p, st);
-  return launch_row_npg<KS, PARTS, 4>(p, st);
+  const bool heavy = forced ? forced == 4 : p.ngroups >= 3;
+  return heavy ? launch_row_npg<KS, PARTS, 4>(p, st) : launch_row_npg<KS, PARTS, 3>(p, st);
 }
 
 static int row_groups(const pbmc_conv_desc& d) {
