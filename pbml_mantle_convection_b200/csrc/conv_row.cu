@@ -28,6 +28,9 @@
 // 59.4 us with a 12-stage ring, against 58.3 us for the register-prefetch producers -- half of the producers' time then
 // went into waiting for their row (ncu source view), with ALL inputs resident in L2 as well (aliased sources, no flush:
 // 60.4 us), so it is the bulk-copy path's rate for 2 KB copies (about four per 800 clk per SM) that paces it, not DRAM.
+// Also tried: FIVE producer groups (one epilogue set, no bulk-copy warp: 25 warps, which the register file holds at 72
+// registers per thread): 61.4-63.5 us against 58.3 us with four -- more staging warps only crowd the issue slots and the
+// shared-memory pipe they share with the MMA operand fetches.
 // Pipelines: a_full/a_empty (producers <-> MMA, NSTAGE smem stages; one stage = one input row of one
 // 16-channel group), d_full/d_empty (MMA <-> epilogue, ND accumulators; D_r is released by the k output
 // rows that read it).
