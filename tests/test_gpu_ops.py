@@ -144,6 +144,12 @@ ROW_CASES = UMMA_CASES + [
     (2, 40, 16, 70, 130, 3, "zeros"),        # three K groups, last one half full; many rows per CTA
     (1, 16, 16, 200, 256, 3, "replicate"),   # exact strips, accumulator ring wraps many times
     (1, 16, 16, 64, 128, 5, "replicate"),
+    # >= 3 K groups per row: four producer groups + one epilogue set, merged hi*hi / hi*lo MMA (fp16 hi|lo, k = 3)
+    (1, 48, 2, 33, 140, 3, "reflect"),       # c_out = 2 with the zero-mean channel sums, two strips
+    (1, 64, 12, 20, 129, 3, "replicate"),    # three output blocks, one column in the second strip
+    (1, 48, 16, 1, 5, 3, "zeros"),           # a single row
+    (1, 103, 16, 150, 128, 3, "replicate"),  # conv[1]'s channel count; the 5-deep accumulator ring wraps many times
+    (2, 48, 16, 40, 64, 5, "zeros"),         # k = 5 with three groups (four producer groups, passes not merged)
 ]
 
 
@@ -295,6 +301,32 @@ def test_conv_gelu_epilogue():
     out, _, _ = ops.conv_fwd([ops.Source(ops.pack_nchw(cu(x)))], ops.pack_conv_weight(cu(w), [16]), ops.pad_vec(cu(b), 16, DEV),
                              16, 3, "replicate", epi_act=L.ACT_GELU, impl="ffma")
     assert relerr(ops.unpack_nchw(out, 16).cpu().numpy(), ref) < 2e-6
+
+
+@pytest.mark.parametrize("Co,pad", [(16, "replicate"), (3, "zeros")])
+def test_conv_row_several_groups_gelu_epilogue_and_channel_sums(Co, pad):
+    """The several-groups variant of the row kernel (merged MMA passes, 96-column accumulators read in two halves) with
+    everything its epilogue can be asked for: GELU, partial output blocks, GroupNorm sums, zero-mean channel sums."""
+    r = rng(31)
+    B, H, W, chans = 2, 37, 150, [16, 16, 16, 7]
+    xs = [r.standard_normal((B, c, H, W)) for c in chans]
+    w, b = r.standard_normal((Co, sum(chans), 3, 3)) / 20, r.standard_normal(Co)
+    ref = RN.gelu(RN.conv2d_same(np.concatenate(xs, 1), w, b, pad))
+    srcs = [ops.Source(ops.pack_nchw(cu(x))) for x in xs]
+    out, stats, csum = ops.conv_fwd(srcs, ops.pack_conv_weight(cu(w), chans), ops.pad_vec(cu(b), Co, DEV), Co, 3, pad,
+                                    epi_act=L.ACT_GELU, want_stats=True, want_chan_sum=Co <= 4, impl="row_f16x2",
+                                    wpk_row=ops.pack_conv_weight_row(cu(w), chans))
+    y = ops.unpack_nchw(out, Co).cpu().numpy()
+    assert relerr(y, ref) < 3e-6, relerr(y, ref)
+    cb = (Co + 3) // 4
+    refp = np.zeros((B, cb * 4, H, W))
+    refp[:, :Co] = ref
+    rs = refp.reshape(B, cb, -1)
+    st = stats.cpu().numpy()
+    assert np.allclose(st[..., 0], rs.sum(-1), rtol=1e-5, atol=1e-4 * np.sqrt(rs.shape[-1]))
+    assert np.allclose(st[..., 1], (rs**2).sum(-1), rtol=1e-5)
+    if Co <= 4:
+        assert np.allclose(csum.cpu().numpy(), refp.sum((2, 3)), rtol=1e-5, atol=1e-4 * np.sqrt(H * W))
 
 
 @pytest.mark.parametrize("impl", ["ffma", "umma_3xtf32", "umma_f16x2", "row_f16x2", "mux_f16x2"])
