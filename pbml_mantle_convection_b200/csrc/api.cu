@@ -494,7 +494,12 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
       t.max_ctas = L > 1 ? cta_budget[l] : 148;
       t.pre_zeroed = 1;  // the statistics / counter region was zeroed by the memset at the top of the forward
       t.loader = (n.flags & PBMC_NET_TRUNK_BULK_LOADER) ? PBMC_TRUNK_LOADER_BULK : PBMC_TRUNK_LOADER_THREADS;
-      RC(conv_trunk_dispatch(t, sl));
+      g_conv_pdl_next = l == 0 ? (chain_pdl & 2) : 0;  // level 0 runs on the main stream, directly behind conv[0]
+      {
+        const int rct = conv_trunk_dispatch(t, sl);
+        g_conv_pdl_next = 0;
+        RC(rct);
+      }
     }
     for (int r = 0; r < R && !trunk_persistent; ++r) {
       const pbmc_layer& Lr = n.trunk[l * PBMC_MAX_REPEATS + r];

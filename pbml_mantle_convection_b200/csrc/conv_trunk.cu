@@ -29,6 +29,8 @@
 
 namespace pbmc {
 
+extern thread_local int g_conv_pdl_next;  // conv_mux.cu: set by api.cu right before the launch it applies to
+
 constexpr int CT_SETS = 5;                       // groups of 4 worker warps
 constexpr int CT_WORKERS = 4 * CT_SETS;          // 20 worker warps
 constexpr int CT_NMMA = 2;                       // MMA issuer warps (alternate rows); the first one owns TMEM
@@ -157,6 +159,9 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
     xf_b[tid] = bb;
     bias_s[tid] = __ldg(Ld.bias + tid);
   };
+  // Everything above (barriers, TMEM, layer 0's filters) may overlap the drain of the previous kernel in the stream when the
+  // launch carries programmatic stream serialization (api.cu: the level-0 kernel behind conv[0]); without it a no-op.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tid < 16) load_coeffs(0);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -557,7 +562,9 @@ static int launch_trunk(ConvTrunkParams& p, cudaStream_t st) {
   const size_t smem = CT_HDR + (size_t)2 * B_GROUP + (size_t)(p.rpc + 2) * STAGE_BYTES;
   if (smem > 227 * 1024) return PBMC_ERR_UNSUPPORTED;
   dim3 grid(cdiv(p.H, p.rpc), cdiv(p.W, 128), p.B);
-  conv_trunk_kernel<PARTS, BULK><<<grid, CT_THREADS, smem, st>>>(p);
+  const bool pdl = g_conv_pdl_next != 0;
+  g_conv_pdl_next = 0;
+  PBMC_CUDA(launch_maybe_pdl(conv_trunk_kernel<PARTS, BULK>, grid, dim3(CT_THREADS), smem, st, pdl, p));
   PBMC_CHECK_LAUNCH("conv_trunk_kernel");
   return PBMC_OK;
 }
