@@ -412,14 +412,16 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
                                 const pbmc_member* members, float* u, float* v, float* p, uint32_t* uvmax, int B, int H,
                                 int W, cudaStream_t st, bool pre_zeroed) {
   const int L = P.L, R = P.R, CB = P.CB;
-  // Programmatic dependent launch on the critical chain (PBMC_CHAIN_PDL overrides the mask; default 1 | 4):
+  // Programmatic dependent launch on the critical chain (PBMC_CHAIN_PDL overrides the mask in a developer build; default all):
   //   1  conv[2], conv[3]   on: nothing else runs then; the next conv's set-up overlaps the previous one's drain
   //   4  conv[1]            on  (0.2348 -> 0.2331 -> 0.2311 ms/step at 512^2 with 1, then 1 | 4)
   //   8  head kernel        on
   //  16  conv[0]            on in a rollout (behind the input-build kernel, no memset node in between)
-  //   2  level-0 trunk      off: 0.27 ms -- an early-resident CTA parked in griddepcontrol.wait takes an SM from
-  //                              the other levels' streams
-  static const int chain_pdl = PBMC_DEV_KNOB("PBMC_CHAIN_PDL", 5 | 8 | 16);
+  //   2  level-0 trunk      on for the persistent kernel (one launch behind conv[0]; its 96 CTAs leave the other levels
+  //                         their SMs: 0.2011 -> 0.2003 ms/step in 10-step graphs); with one launch PER LAYER it cost
+  //                         0.27 ms -- an early-resident CTA parked in griddepcontrol.wait took an SM from the other
+  //                         levels' streams -- and stays off there
+  static const int chain_pdl = PBMC_DEV_KNOB("PBMC_CHAIN_PDL", 1 | 2 | 4 | 8 | 16);
   auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto S = [&](int slot) { return reinterpret_cast<double*>(ws + P.stat_off(slot, B)); };
   double* chan_sum = reinterpret_cast<double*>(ws + P.chan_sum);
@@ -513,7 +515,7 @@ static int surrogate_enqueue_on(pbmc_ctx* ctx, const pbmc_net& n, const Plan& P,
         d.src[0] = make_src(F(P.ping[l][(r - 1) & 1]), CB, PBMC_XFORM_GN_GELU, S(1 + l * R + r - 1),
                             &n.trunk[l * PBMC_MAX_REPEATS + r - 1], invc);
       }
-      g_conv_pdl_next = l == 0 ? (chain_pdl & 2) : 0;
+      g_conv_pdl_next = 0;  // one launch per layer: never (see the mask above)
       {
         const int rct = conv_enqueue(d, sl);
         g_conv_pdl_next = 0;
