@@ -31,7 +31,10 @@ namespace pbmc {
 
 extern thread_local int g_conv_pdl_next;  // conv_mux.cu: set by api.cu right before the launch it applies to
 
-constexpr int CT_SETS = 5;                       // groups of 4 worker warps
+#ifndef PBMC_CT_SETS
+#define PBMC_CT_SETS 5
+#endif
+constexpr int CT_SETS = PBMC_CT_SETS;            // groups of 4 worker warps
 constexpr int CT_WORKERS = 4 * CT_SETS;          // 20 worker warps
 constexpr int CT_NMMA = 2;                       // MMA issuer warps (alternate rows); the first one owns TMEM
 constexpr int CT_MMA_WARP = CT_WORKERS;
@@ -40,7 +43,7 @@ constexpr int CT_MAXR = 24;                      // input rows per CTA (all resi
 constexpr int CT_ND = 10;                        // TMEM accumulator ring
 constexpr int CT_N = 48;                         // (dy, c_out)
 constexpr int CT_PLANE = 136;                    // positions per K-chunk plane (128 + 2 halo, rounded up to 8)
-constexpr int CT_HDR = 2304;                     // barriers, TMEM slot, reduction scratch, coefficients, raw-row barriers
+constexpr int CT_HDR = 2432;                     // barriers, TMEM slot, reduction scratch, raw-row barriers, coefficients
 
 struct TrunkLayerDev {
   const float* in;       // [B][4][H][W][4] raw producer output (or the level's input for layer 0)
@@ -91,7 +94,7 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
 }
 
 template <int PARTS, bool BULK>
-__global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTrunkParams p) {
+__global__ void __maxnreg__(CT_SETS <= 5 ? 80 : 72) conv_trunk_kernel(const __grid_constant__ ConvTrunkParams p) {
   constexpr int KS = 3, P = 1, N = CT_N, ND = CT_ND, PLANE = CT_PLANE;
   constexpr int PART_BYTES = 2 * PLANE * 16, STAGE_BYTES = PARTS * PART_BYTES;
   constexpr int B_TILE = 2 * N * 16, B_GROUP = KS * PARTS * B_TILE;
@@ -99,15 +102,15 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
   constexpr uint32_t IDESC = row_idesc(FMT, N);
   static_assert(8 * (CT_MAXR + 2 * ND) <= 448, "barrier area");
   static_assert(!BULK || PARTS == 2, "the raw fp32 row fills exactly the fp16 hi|lo stage slot");
-  static_assert(2048 + 8 * CT_MAXR <= CT_HDR, "raw-row barriers");
+  static_assert(512 + CT_WORKERS * 64 <= 2048 && 2048 + 8 * CT_MAXR <= 2240, "reduction scratch, raw-row barriers");
   static_assert(ND * N <= 512, "TMEM has 512 columns");
   static_assert(B_GROUP % 128 == 0, "operand buffers stay 128-byte aligned");
   extern __shared__ __align__(128) unsigned char smem[];
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 448);
-  double* red = reinterpret_cast<double*>(smem + 512);        // 20 warps x 8 doubles
-  float* bias_s = reinterpret_cast<float*>(smem + 1792);      // 16 floats
-  float* xf_a = reinterpret_cast<float*>(smem + 1856);        // GroupNorm scale / shift of the 16 input channels
-  float* xf_b = reinterpret_cast<float*>(smem + 1920);
+  double* red = reinterpret_cast<double*>(smem + 512);        // CT_WORKERS warps x 8 doubles
+  float* bias_s = reinterpret_cast<float*>(smem + 2240);      // 16 floats
+  float* xf_a = reinterpret_cast<float*>(smem + 2304);        // GroupNorm scale / shift of the 16 input channels
+  float* xf_b = reinterpret_cast<float*>(smem + 2368);
   unsigned char* Bs = smem + CT_HDR;                          // two filter buffers: layer l uses Bs + (l & 1) * B_GROUP
   unsigned char* As = Bs + 2 * B_GROUP;
 
@@ -427,11 +430,11 @@ __global__ void __maxnreg__(80) conv_trunk_kernel(const __grid_constant__ ConvTr
       if (warp == 0) {
         // one warp finishes the layer for the CTA: lane = (quarter of the 20 warps, moment) adds five partial sums, two
         // shuffles fold the quarters, lanes 0..7 issue the atomics ...
-        static_assert(CT_WORKERS == 20, "four quarters of five warps");
+        static_assert(CT_WORKERS % 4 == 0, "four quarters of CT_SETS warps");
         const int m = lane & 7, q = lane >> 3;
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < 5; ++w) t += red[((q * 5 + w) * 4 + (m >> 1)) * 2 + (m & 1)];
+        for (int w = 0; w < CT_SETS; ++w) t += red[((q * CT_SETS + w) * 4 + (m >> 1)) * 2 + (m & 1)];
         t += __shfl_xor_sync(0xffffffffu, t, 8);
         t += __shfl_xor_sync(0xffffffffu, t, 16);
         if (lane < 8) atomicAdd(Ld.out_stats + ((size_t)b * 4 + (m >> 1)) * 2 + (m & 1), t);
