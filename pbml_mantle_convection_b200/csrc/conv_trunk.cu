@@ -31,6 +31,9 @@ namespace pbmc {
 
 extern thread_local int g_conv_pdl_next;  // conv_mux.cu: set by api.cu right before the launch it applies to
 
+// Six groups (-DPBMC_CT_SETS=6: 832 threads at 72 registers, three staging rounds instead of four at 16 input rows) were
+// measured against five (tools/exp_ct_sets.sh): 68.6 vs 68.6 us per 4-layer launch at 148 CTAs, 85.1 vs 85.0 at 96 -- fewer
+// rounds, each slower by the same factor: the staging rounds are bound by issued instructions, not by their number.
 #ifndef PBMC_CT_SETS
 #define PBMC_CT_SETS 5
 #endif
